@@ -1,0 +1,165 @@
+/*
+ * mnv_b200.h — C-ABI of the B200-native Mega-NeRF octree render path.
+ *
+ * This header is the drop-in boundary.  Every entry point
+ * replaces one of the reference's host launchers / LibTorch call sites; the
+ * reference interface each one stands in for is cited as
+ * `<path under the reference tree>:<line>`.
+ *
+ * Conventions
+ *   - plain C, no torch / glm / STL types in any signature;
+ *   - every function returns an `int` status (MNV_OK == 0), never calls
+ *     exit()/cudaDeviceReset() (the reference's cuda_assert does,
+ *     src/cuda/common.cu:8-20);
+ *   - pointers named *_dev are device pointers on the tree's device, *_host
+ *     are host pointers (pinned memory makes the async copies truly async);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - there is NO CPU fallback: without a CUDA device every compute call
+ *     returns MNV_ERR_NO_DEVICE.
+ */
+#ifndef MNV_B200_H
+#define MNV_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNV_GLOBAL_BASIS_MAX 25 /* include/render_options.hpp:4 VIEWER_GLOBAL_BASIS_MAX */
+
+enum {
+    MNV_OK = 0,
+    MNV_ERR_INVALID = 1,   /* bad argument / shape */
+    MNV_ERR_NO_DEVICE = 2, /* no CUDA device: there is no CPU fallback */
+    MNV_ERR_CUDA = 3,      /* CUDA runtime error, see mnv_last_error() */
+    MNV_ERR_OOM = 4,
+    MNV_ERR_IO = 5,      /* file missing / unreadable */
+    MNV_ERR_FORMAT = 6,  /* .npz / model container schema violation */
+    MNV_ERR_FULL = 7     /* tree capacity exhausted ("Full", cuda_renderer.cpp:228-231) */
+};
+
+/* include/data_format.hpp:7-22 */
+enum { MNV_FORMAT_RGBA = 0, MNV_FORMAT_SH = 1 };
+
+/* include/render_options.hpp:9-56 — same fields, same order, same defaults
+ * (see mnv_render_options_default).  Layout-compatible with
+ * viewer::RenderOptions on this ABI (bool = 1 byte). */
+typedef struct mnv_render_options {
+    float step_size;
+    float sigma_thresh;
+    float stop_thresh;
+    float background_brightness;
+    float render_bbox[6];
+    int basis_minmax[2];
+    float rot_dirs[3];
+    bool show_grid;
+    int grid_max_depth;
+    bool render_depth;
+    bool use_splitting;
+    bool use_guided_sampling;
+    int max_depth;
+    int samples_per_corner;
+    int split_batch_size;
+    int nerf_batch_size;
+    int max_sample_count;
+    bool need_viewdir;
+    int appearance_embedding;
+    int max_guided_samples;
+} mnv_render_options;
+
+/* include/data_spec.hpp:9-23 CameraSpec + the 12 floats Camera::_update
+ * uploads (src/camera.cpp:113-123).  c2w is glm::mat4x3 column-major:
+ * right(3), up(3), back(3), center(3). */
+typedef struct mnv_camera {
+    int width, height;
+    float fx, fy, cx, cy;
+    float c2w[12];
+} mnv_camera;
+
+/* Host-side view of a loaded tree in the reference's AoS schema
+ * (src/n3tree/n3tree.cpp:28-205). */
+typedef struct mnv_tree_desc {
+    int N;                 /* branching factor, only 2 is supported */
+    int data_dim;          /* 3*basis_dim+1 (SH) or 4 (RGBA) */
+    int format;            /* MNV_FORMAT_* */
+    int basis_dim;         /* -1 for RGBA */
+    int64_t capacity;      /* nodes in use */
+    const uint16_t *data;  /* fp16 bits [capacity][8][data_dim] */
+    const int32_t *child;  /* [capacity][8] relative offset, 0 = leaf */
+    const int32_t *parent; /* [capacity] packed node*8+child, may be NULL */
+    const int16_t *sample_counts; /* [capacity][8], NULL -> 8 everywhere (n3tree.cpp:191-193) */
+    float scale[3];        /* invradius3 */
+    float offset[3];
+} mnv_tree_desc;
+
+typedef struct mnv_tree mnv_tree;   /* opaque device tree (SoA planes) */
+typedef struct mnv_model mnv_model; /* opaque Mega-NeRF MLP container */
+
+/* Per-frame statistics the traversal kernel can produce (bench / roofline). */
+typedef struct mnv_frame_stats {
+    uint64_t rays;
+    uint64_t visits;        /* leaf visits = iterations of rt_core.cuh:220-324 */
+    uint64_t shaded_visits; /* visits with sigma > sigma_thresh */
+    uint64_t rays_hit;      /* rays that entered the bbox */
+} mnv_frame_stats;
+
+/* ---- misc ---------------------------------------------------------------- */
+const char *mnv_version(void);
+const char *mnv_last_error(void); /* thread-local message of the last failure */
+int mnv_device_count(int *count);
+void mnv_render_options_default(mnv_render_options *opt); /* render_options.hpp defaults */
+
+/* ---- tree: N3Tree::move_to_device, src/n3tree/n3tree.cpp:207-246 --------- */
+int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *desc, int64_t max_capacity, int device);
+int mnv_tree_destroy(mnv_tree *tree);
+int mnv_tree_capacity(const mnv_tree *tree, int64_t *capacity, int64_t *max_capacity);
+int mnv_tree_device_bytes(const mnv_tree *tree, uint64_t *bytes);
+/* Read the tree back in the reference's AoS schema (any pointer may be NULL). */
+int mnv_tree_download(const mnv_tree *tree, int64_t first, int64_t count, uint16_t *data,
+                      int32_t *child, int32_t *parent, int16_t *sample_counts);
+
+/* ---- point query: query_single_from_root, include/cuda/rt_core.cuh:117-159
+ * xyz_dev: [n][3] tree-space coordinates; out_dev: [n][3] = chunk, child, depth. */
+int mnv_query_points(const mnv_tree *tree, const float *xyz_dev, int64_t n, int32_t *out_dev,
+                     void *stream);
+
+/* ---- octree render: viewer::render_voxels, src/cuda/renderer_kernel.cu:396-437
+ * (kernel :243-292, march include/cuda/rt_core.cuh:162-332).
+ *   image_arr / depth_arr : cudaArray_t (RGBA8 / R32F surfaces, GL interop) or NULL
+ *   image_linear_dev      : RGBA8 [height][width] linear device buffer or NULL
+ *   to_split_dev/to_sample_dev : f32 [P][3] = (priority, chunk, child) or NULL
+ *   visited_dev           : i32 [max_capacity] or NULL (then track_visit must be false)
+ * Exactly one of image_arr / image_linear_dev must be given.  */
+int mnv_render_voxels(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                      void *image_arr, void *depth_arr, uint8_t *image_linear_dev,
+                      float *to_split_dev, float *to_sample_dev, int32_t *visited_dev,
+                      bool track_visit, bool offscreen, void *stream);
+
+/* Image-tile partition for multi-GPU rendering: render only
+ * the 8x4-pixel-aligned tiles t with (t % tile_mod) == tile_rem of a
+ * tile_w x tile_h tiling; pixels outside are left untouched. */
+int mnv_render_voxels_tiles(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                            uint8_t *image_linear_dev, float *to_split_dev, float *to_sample_dev,
+                            int tile_w, int tile_h, int tile_mod, int tile_rem, void *stream);
+
+/* Debug/parity variant: additionally writes per ray an FNV-1a hash of the
+ * visited (chunk*8+child) sequence, the visit count, and the first `log_cap`
+ * packed leaf indices. All outputs are device pointers; any may be NULL. */
+int mnv_render_voxels_logged(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                             uint8_t *image_linear_dev, uint64_t *visit_hash_dev,
+                             int32_t *visit_count_dev, int32_t *shaded_count_dev,
+                             int32_t *visit_log_dev, int log_cap, void *stream);
+
+/* The call a host application makes per frame with HOST buffers: uploads the
+ * camera (48 B, src/camera.cpp:113-123), renders offscreen, reads the RGBA8
+ * frame back into rgba_host ([height][width][4]); synchronous on return. */
+int mnv_render_frame_host(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                          uint8_t *rgba_host, mnv_frame_stats *stats /* may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNV_B200_H */

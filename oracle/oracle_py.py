@@ -1,0 +1,187 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes loader for oracle/liboracle.so (the CPU
+restatement) and oracle/_ref/libref_render*.so (the reference's own CUDA path).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs may import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_render.so")
+REF_INSTR_SO = os.path.join(HERE, "_ref", "libref_render_instr.so")
+
+
+class RenderOptions(C.Structure):
+    """include/mnv_b200.h mnv_render_options == include/render_options.hpp:9-56."""
+
+    _fields_ = [
+        ("step_size", C.c_float),
+        ("sigma_thresh", C.c_float),
+        ("stop_thresh", C.c_float),
+        ("background_brightness", C.c_float),
+        ("render_bbox", C.c_float * 6),
+        ("basis_minmax", C.c_int * 2),
+        ("rot_dirs", C.c_float * 3),
+        ("show_grid", C.c_bool),
+        ("grid_max_depth", C.c_int),
+        ("render_depth", C.c_bool),
+        ("use_splitting", C.c_bool),
+        ("use_guided_sampling", C.c_bool),
+        ("max_depth", C.c_int),
+        ("samples_per_corner", C.c_int),
+        ("split_batch_size", C.c_int),
+        ("nerf_batch_size", C.c_int),
+        ("max_sample_count", C.c_int),
+        ("need_viewdir", C.c_bool),
+        ("appearance_embedding", C.c_int),
+        ("max_guided_samples", C.c_int),
+    ]
+
+
+def default_options(**kw) -> RenderOptions:
+    """Struct defaults of include/render_options.hpp:12-55."""
+    o = RenderOptions()
+    o.step_size = 1e-4
+    o.sigma_thresh = 1e-2
+    o.stop_thresh = 1e-2
+    o.background_brightness = 1.0
+    o.render_bbox[:] = [0, 0, 0, 1, 1, 1]
+    o.basis_minmax[:] = [0, 24]
+    o.rot_dirs[:] = [0, 0, 0]
+    o.show_grid = False
+    o.grid_max_depth = 4
+    o.render_depth = False
+    o.use_splitting = False
+    o.use_guided_sampling = False
+    o.max_depth = 16
+    o.samples_per_corner = 8
+    o.split_batch_size = 4192
+    o.nerf_batch_size = 1024
+    o.max_sample_count = 256
+    o.need_viewdir = False
+    o.appearance_embedding = -1
+    o.max_guided_samples = 128
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple, np.ndarray)):
+            getattr(o, k)[:] = list(v)
+        else:
+            setattr(o, k, v)
+    return o
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("c2w", C.c_float * 12),
+    ]
+
+
+def make_camera(d: dict) -> Camera:
+    c = Camera()
+    c.width, c.height = int(d["width"]), int(d["height"])
+    c.fx, c.fy, c.cx, c.cy = d["fx"], d["fy"], d["cx"], d["cy"]
+    c.c2w[:] = [float(v) for v in d["c2w"]]
+    return c
+
+
+class TreeDesc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("data_dim", C.c_int), ("format", C.c_int), ("basis_dim", C.c_int),
+        ("capacity", C.c_int64),
+        ("data", C.c_void_p), ("child", C.c_void_p), ("parent", C.c_void_p),
+        ("sample_counts", C.c_void_p),
+        ("scale", C.c_float * 3), ("offset", C.c_float * 3),
+    ]
+
+
+def make_tree_desc(tree, sample_counts: np.ndarray | None = None):
+    """tree: synth.HostTree.  Returns (desc, keepalive)."""
+    d = TreeDesc()
+    d.N = tree.N
+    d.data_dim = tree.data_dim
+    d.format = 1 if tree.data_format.upper().startswith("SH") else 0
+    d.basis_dim = tree.basis_dim
+    d.capacity = tree.capacity
+    data = np.ascontiguousarray(tree.data.view(np.uint16))
+    child = np.ascontiguousarray(tree.child, np.int32)
+    parent = np.ascontiguousarray(tree.parent, np.int32)
+    d.data = data.ctypes.data
+    d.child = child.ctypes.data
+    d.parent = parent.ctypes.data
+    keep = [data, child, parent]
+    if sample_counts is not None:
+        sc = np.ascontiguousarray(sample_counts, np.int16)
+        d.sample_counts = sc.ctypes.data
+        keep.append(sc)
+    d.scale[:] = [float(v) for v in tree.scale]
+    d.offset[:] = [float(v) for v in tree.offset]
+    return d, keep
+
+
+def build_oracle() -> None:
+    subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build_oracle()
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.oracle_query_points.restype = C.c_int
+        _lib.oracle_query_points.argtypes = [C.POINTER(TreeDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+        _lib.oracle_render_voxels.restype = C.c_int
+        _lib.oracle_render_voxels.argtypes = [
+            C.POINTER(TreeDesc), C.POINTER(Camera), C.POINTER(RenderOptions),
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+            C.c_int, C.c_int, C.c_int, C.c_int,
+        ]
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+def query_points(tree, xyz: np.ndarray, nthreads: int = 0) -> np.ndarray:
+    desc, keep = make_tree_desc(tree)
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    out = np.empty((xyz.shape[0], 3), np.int32)
+    rc = lib().oracle_query_points(C.byref(desc), xyz.ctypes.data, xyz.shape[0], out.ctypes.data, nthreads)
+    assert rc == 0, rc
+    return out
+
+
+def render_voxels(tree, cam: dict, opt: RenderOptions, *, trackers=False, log_cap=0, stats=True,
+                  y0=0, y1=None, row_step=1, nthreads=0, sample_counts=None):
+    """Returns dict(rgba[H,W,4], to_split, to_sample, hash, count, shaded, log)."""
+    desc, keep = make_tree_desc(tree, sample_counts)
+    c = make_camera(cam)
+    H, W = c.height, c.width
+    P = H * W
+    rgba = np.zeros((H, W, 4), np.uint8)
+    split = np.full((P, 3), -1, np.float32) if trackers else None
+    sample = np.full((P, 3), -1, np.float32) if trackers else None
+    vh = np.zeros(P, np.uint64) if stats else None
+    vc = np.zeros(P, np.int32) if stats else None
+    vs = np.zeros(P, np.int32) if stats else None
+    vlog = np.full((P, log_cap), -1, np.int32) if log_cap > 0 else None
+    rc = lib().oracle_render_voxels(
+        C.byref(desc), C.byref(c), C.byref(opt), rgba.ctypes.data, None, _ptr(split), _ptr(sample),
+        None, 0, 1, _ptr(vh), _ptr(vc), _ptr(vs), _ptr(vlog), log_cap,
+        y0, H if y1 is None else y1, row_step, nthreads)
+    assert rc == 0, rc
+    return dict(rgba=rgba, to_split=split, to_sample=sample, hash=vh, count=vc, shaded=vs, log=vlog)

@@ -1,0 +1,252 @@
+// TEST INFRASTRUCTURE ONLY — never linked into or called from the product path.
+//
+// Headless C driver around the UNMODIFIED reference sources, compiled where
+// they lie under /root/reference by oracle/build_ref.sh into
+// oracle/_ref/libref_render.so (and libref_render_instr.so for the visit-log
+// variant).  It exposes the reference's own host launchers
+// (include/cuda/renderer_kernel.hpp:12-79) through a tiny extern "C" surface so
+// that tests/ and bench.py (--impl reference) can run the reference's CUDA
+// kernel rebuilt for sm_100 next to the B200-native path.
+//
+// Flow mirrors main.cpp / cuda_renderer.cpp: N3Tree::open -> move_to_device ->
+// Camera::_update -> viewer::render_voxels(..., offscreen=true).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "include/cuda/renderer_kernel.hpp"  // resolved with -I$REF (the reference root)
+
+#ifdef REF_VISIT_LOG
+// defined by the generated patch in the instrumented copy of renderer_kernel.cu
+extern "C" void ref_instr_set_buffers(unsigned long long *hash, int *count, int *log, int log_cap);
+#endif
+
+namespace {
+struct RefCtx {
+    viewer::N3Tree tree;
+    long max_cap = 0;
+    viewer::Camera *cam = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaArray_t img = nullptr;
+    cudaArray_t depth = nullptr;
+    int w = 0, h = 0;
+    torch::Tensor split, sample, visited;
+};
+
+void ensure_target(RefCtx *c, int w, int h) {
+    if (c->img && c->w == w && c->h == h) return;
+    if (c->img) cudaFreeArray(c->img);
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<uchar4>();
+    cudaMallocArray(&c->img, &desc, w, h, cudaArraySurfaceLoadStore);
+    c->w = w;
+    c->h = h;
+    auto f32 = torch::TensorOptions().dtype(torch::kFloat32).device(torch::kCUDA);
+    c->split = torch::ones({(long) w * h, 3}, f32) * -1;
+    c->sample = torch::ones({(long) w * h, 3}, f32) * -1;
+}
+
+void set_camera(RefCtx *c, int w, int h, const float *intr, const float *c2w) {
+    viewer::Camera &cam = *c->cam;
+    cam.width = w;
+    cam.height = h;
+    cam.fx = intr[0];
+    cam.fy = intr[1];
+    cam.cx = intr[2];
+    cam.cy = intr[3];
+    for (int col = 0; col < 4; ++col)
+        for (int r = 0; r < 3; ++r) cam.transform[col][r] = c2w[col * 3 + r];
+    cam._update(/*transform_from_vecs=*/false, /*copy_cuda=*/true);
+}
+}  // namespace
+
+extern "C" {
+
+void *ref_open(const char *npz_path, long max_capacity) {
+    auto *c = new RefCtx();
+    c->tree.open(npz_path);
+    if (c->tree.N == 0) {
+        delete c;
+        return nullptr;
+    }
+    if (max_capacity < c->tree.capacity) max_capacity = c->tree.capacity;
+    c->max_cap = max_capacity;
+    c->tree.move_to_device(max_capacity, true, true);
+    // move_to_device leaves sample_counts uninitialised on the device
+    // (src/n3tree/n3tree.cpp:235-241); the host-side value is 8 (:191-193).
+    c->tree.sample_counts.fill_(8);
+    c->cam = new viewer::Camera();
+    cudaStreamCreateWithFlags(&c->stream, cudaStreamDefault);
+    c->visited = torch::zeros({max_capacity},
+                              torch::TensorOptions().device(torch::kCUDA).dtype(torch::kInt32));
+    return c;
+}
+
+void ref_close(void *ctx) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (!c) return;
+    if (c->img) cudaFreeArray(c->img);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c->cam;
+    delete c;
+}
+
+int ref_capacity(void *ctx) { return static_cast<RefCtx *>(ctx)->tree.capacity; }
+int ref_data_dim(void *ctx) { return static_cast<RefCtx *>(ctx)->tree.data_dim; }
+
+// Copies the loaded tree (first `capacity` rows) back to host arrays in the
+// reference's own layout, so the caller can feed the identical tree to the
+// B200-native path without going through a second loader.
+int ref_download(void *ctx, uint16_t *data, int32_t *child, int32_t *parent, float *scale,
+                 float *offset) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    const long cap = c->tree.capacity;
+    if (data) {
+        auto t = c->tree.data.slice(0, 0, cap).cpu().contiguous();
+        std::memcpy(data, t.data_ptr(), t.numel() * 2);
+    }
+    if (child) {
+        auto t = c->tree.child.slice(0, 0, cap).cpu().contiguous();
+        std::memcpy(child, t.data_ptr(), t.numel() * 4);
+    }
+    if (parent) {
+        auto t = c->tree.parent.slice(0, 0, cap).cpu().contiguous();
+        std::memcpy(parent, t.data_ptr(), t.numel() * 4);
+    }
+    if (scale) {
+        auto t = c->tree.scale.cpu();
+        std::memcpy(scale, t.data_ptr(), 12);
+    }
+    if (offset) {
+        auto t = c->tree.offset.cpu();
+        std::memcpy(offset, t.data_ptr(), 12);
+    }
+    return 0;
+}
+
+// viewer::render_voxels (src/cuda/renderer_kernel.cu:396-437) into an
+// offscreen RGBA8 cudaArray; `iters` back-to-back launches, CUDA-event timed
+// individually on the launching stream. Outputs are host pointers (nullable).
+int ref_render_voxels(void *ctx, int w, int h, const float *intr, const float *c2w,
+                      const void *opt_pod, int opt_size, unsigned char *rgba_out, float *split_out,
+                      float *sample_out, int iters, float *ms_out) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) {
+        fprintf(stderr, "ref_render_voxels: RenderOptions size mismatch %d vs %zu\n", opt_size,
+                sizeof(viewer::RenderOptions));
+        return 1;
+    }
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    ensure_target(c, w, h);
+    set_camera(c, w, h, intr, c2w);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int it = 0; it < std::max(iters, 1); ++it) {
+        c->split.fill_(-1);
+        c->sample.fill_(-1);
+        cudaDeviceSynchronize();
+        cudaEventRecord(e0, c->stream);
+        viewer::render_voxels(c->tree, *c->cam, opt, c->img, c->depth, c->stream, c->split,
+                              c->sample, c->visited, /*track_visit=*/false, /*offscreen=*/true);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms_out) ms_out[it] = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        fprintf(stderr, "ref_render_voxels: %s\n", cudaGetErrorString(err));
+        return 2;
+    }
+    if (rgba_out)
+        cudaMemcpy2DFromArray(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h,
+                              cudaMemcpyDeviceToHost);
+    if (split_out) {
+        auto t = c->split.cpu();
+        std::memcpy(split_out, t.data_ptr(), t.numel() * 4);
+    }
+    if (sample_out) {
+        auto t = c->sample.cpu();
+        std::memcpy(sample_out, t.data_ptr(), t.numel() * 4);
+    }
+    return 0;
+}
+
+// The whole reference frame as a host application sees it with host buffers:
+// camera upload + tracker fills + kernel + read-back of the RGBA8 frame.
+// Wall-clock around the synchronous sequence; used for the e2e reference arm.
+int ref_render_frame_host(void *ctx, int w, int h, const float *intr, const float *c2w,
+                          const void *opt_pod, int opt_size, unsigned char *rgba_out) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    ensure_target(c, w, h);
+    set_camera(c, w, h, intr, c2w);
+    c->split.fill_(-1);   // cuda_renderer.cpp:97-98
+    c->sample.fill_(-1);
+    viewer::render_voxels(c->tree, *c->cam, opt, c->img, c->depth, c->stream, c->split, c->sample,
+                          c->visited, false, true);
+    cudaMemcpy2DFromArrayAsync(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h,
+                               cudaMemcpyDeviceToHost, c->stream);
+    return cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : 2;
+}
+
+#ifdef REF_VISIT_LOG
+// Instrumented build only: one render with per-ray visit hash / count / log.
+int ref_render_voxels_logged(void *ctx, int w, int h, const float *intr, const float *c2w,
+                             const void *opt_pod, int opt_size, unsigned char *rgba_out,
+                             unsigned long long *hash_out, int *count_out, int *log_out,
+                             int log_cap) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    ensure_target(c, w, h);
+    set_camera(c, w, h, intr, c2w);
+    const size_t P = (size_t) w * h;
+    unsigned long long *d_hash = nullptr;
+    int *d_count = nullptr, *d_log = nullptr;
+    cudaMalloc(&d_hash, P * 8);
+    cudaMalloc(&d_count, P * 4);
+    // FNV-1a offset basis, same as the native logged kernel
+    std::vector<unsigned long long> init(P, 0xcbf29ce484222325ULL);
+    cudaMemcpy(d_hash, init.data(), P * 8, cudaMemcpyHostToDevice);
+    cudaMemset(d_count, 0, P * 4);
+    if (log_out && log_cap > 0) {
+        cudaMalloc(&d_log, P * (size_t) log_cap * 4);
+        cudaMemset(d_log, 0xff, P * (size_t) log_cap * 4);
+    }
+    ref_instr_set_buffers(d_hash, d_count, d_log, d_log ? log_cap : 0);
+    c->split.fill_(-1);
+    c->sample.fill_(-1);
+    viewer::render_voxels(c->tree, *c->cam, opt, c->img, c->depth, c->stream, c->split, c->sample,
+                          c->visited, false, true);
+    cudaError_t err = cudaDeviceSynchronize();
+    ref_instr_set_buffers(nullptr, nullptr, nullptr, 0);
+    if (err != cudaSuccess) {
+        fprintf(stderr, "ref_render_voxels_logged: %s\n", cudaGetErrorString(err));
+        return 2;
+    }
+    if (rgba_out)
+        cudaMemcpy2DFromArray(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h,
+                              cudaMemcpyDeviceToHost);
+    if (hash_out) cudaMemcpy(hash_out, d_hash, P * 8, cudaMemcpyDeviceToHost);
+    if (count_out) cudaMemcpy(count_out, d_count, P * 4, cudaMemcpyDeviceToHost);
+    if (log_out && d_log) cudaMemcpy(log_out, d_log, P * (size_t) log_cap * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d_hash);
+    cudaFree(d_count);
+    if (d_log) cudaFree(d_log);
+    return 0;
+}
+#endif
+
+}  // extern "C"
