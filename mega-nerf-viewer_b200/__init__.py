@@ -1,0 +1,312 @@
+"""mega-nerf-viewer_b200 — B200-native octree render path of mega-nerf-viewer.
+
+Python is plumbing only: this module binds ``libmnv_b200.so`` (hand-written
+sm_100a CUDA behind the C-ABI declared in ``include/mnv_b200.h``) with ctypes
+and uses torch for device buffers / streams.  There is NO fallback: if the
+shared library is missing or no CUDA device is present, every compute entry
+point raises.
+
+The directory name contains '-', so import it through the root-level shim::
+
+    import mega_nerf_viewer_b200 as mnv
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import synth  # noqa: F401  (synthetic N3Tree generator)
+from .synth import HostTree
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmnv_b200.so")
+
+MNV_OK = 0
+ERR_NAMES = {1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "OOM", 5: "IO", 6: "FORMAT", 7: "FULL"}
+
+
+class MnvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mnv_b200 error {code} ({ERR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class RenderOptions(C.Structure):
+    """mnv_render_options == viewer::RenderOptions (include/render_options.hpp:9-56)."""
+
+    _fields_ = [
+        ("step_size", C.c_float),
+        ("sigma_thresh", C.c_float),
+        ("stop_thresh", C.c_float),
+        ("background_brightness", C.c_float),
+        ("render_bbox", C.c_float * 6),
+        ("basis_minmax", C.c_int * 2),
+        ("rot_dirs", C.c_float * 3),
+        ("show_grid", C.c_bool),
+        ("grid_max_depth", C.c_int),
+        ("render_depth", C.c_bool),
+        ("use_splitting", C.c_bool),
+        ("use_guided_sampling", C.c_bool),
+        ("max_depth", C.c_int),
+        ("samples_per_corner", C.c_int),
+        ("split_batch_size", C.c_int),
+        ("nerf_batch_size", C.c_int),
+        ("max_sample_count", C.c_int),
+        ("need_viewdir", C.c_bool),
+        ("appearance_embedding", C.c_int),
+        ("max_guided_samples", C.c_int),
+    ]
+
+
+class Camera(C.Structure):
+    """mnv_camera: CameraSpec (include/data_spec.hpp:9-23) + the 4x3 c2w."""
+
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("c2w", C.c_float * 12),
+    ]
+
+
+class TreeDesc(C.Structure):
+    _fields_ = [
+        ("N", C.c_int), ("data_dim", C.c_int), ("format", C.c_int), ("basis_dim", C.c_int),
+        ("capacity", C.c_int64),
+        ("data", C.c_void_p), ("child", C.c_void_p), ("parent", C.c_void_p),
+        ("sample_counts", C.c_void_p),
+        ("scale", C.c_float * 3), ("offset", C.c_float * 3),
+    ]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("visits", C.c_uint64), ("shaded_visits", C.c_uint64),
+                ("rays_hit", C.c_uint64)]
+
+
+_lib = None
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile csrc/ for sm_100a into libmnv_b200.so (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libmnv_b200.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stderr[-2000:])
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """The CUDA extension; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU / PyTorch fallback for the render path)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.mnv_version.restype = C.c_char_p
+    L.mnv_last_error.restype = C.c_char_p
+    L.mnv_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.mnv_render_options_default.argtypes = [C.POINTER(RenderOptions)]
+    L.mnv_render_options_default.restype = None
+    L.mnv_tree_create.argtypes = [C.POINTER(vp), C.POINTER(TreeDesc), i64, i32]
+    L.mnv_tree_destroy.argtypes = [vp]
+    L.mnv_tree_capacity.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.mnv_tree_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.mnv_tree_download.argtypes = [vp, i64, i64, vp, vp, vp, vp]
+    L.mnv_query_points.argtypes = [vp, vp, i64, vp, vp]
+    L.mnv_render_voxels.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, vp,
+                                    vp, vp, C.c_bool, C.c_bool, vp]
+    L.mnv_render_voxels_tiles.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp,
+                                          i32, i32, i32, i32, vp]
+    L.mnv_render_voxels_logged.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp,
+                                           vp, vp, i32, vp]
+    L.mnv_render_frame_host.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp,
+                                        C.POINTER(FrameStats)]
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != MNV_OK:
+        raise MnvError(rc, lib().mnv_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _check(lib().mnv_device_count(C.byref(n)))
+    return n.value
+
+
+def default_options(**kw) -> RenderOptions:
+    """RenderOptions with the struct defaults of include/render_options.hpp."""
+    o = RenderOptions()
+    lib().mnv_render_options_default(C.byref(o))
+    for k, v in kw.items():
+        if isinstance(v, (list, tuple, np.ndarray)):
+            getattr(o, k)[:] = list(v)
+        else:
+            setattr(o, k, v)
+    return o
+
+
+def make_camera(d) -> Camera:
+    if isinstance(d, Camera):
+        return d
+    c = Camera()
+    c.width, c.height = int(d["width"]), int(d["height"])
+    c.fx, c.fy, c.cx, c.cy = d["fx"], d["fy"], d["cx"], d["cy"]
+    c.c2w[:] = [float(v) for v in d["c2w"]]
+    return c
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise MnvError(2, "torch sees no CUDA device; the render path has no CPU fallback")
+    return torch
+
+
+def _dptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+class DeviceTree:
+    """Device-resident N3Tree in the SoA layout (csrc/mnv_internal.cuh)."""
+
+    def __init__(self, tree: HostTree, max_capacity: int = 0, device: int = 0,
+                 sample_counts: np.ndarray | None = None):
+        d = TreeDesc()
+        d.N = tree.N
+        d.data_dim = tree.data_dim
+        d.format = 1 if tree.data_format.upper().startswith("SH") else 0
+        d.basis_dim = tree.basis_dim
+        d.capacity = tree.capacity
+        self._keep = [np.ascontiguousarray(tree.data.view(np.uint16)),
+                      np.ascontiguousarray(tree.child, np.int32),
+                      np.ascontiguousarray(tree.parent, np.int32)]
+        d.data, d.child, d.parent = (a.ctypes.data for a in self._keep)
+        if sample_counts is not None:
+            sc = np.ascontiguousarray(sample_counts, np.int16)
+            self._keep.append(sc)
+            d.sample_counts = sc.ctypes.data
+        d.scale[:] = [float(v) for v in tree.scale]
+        d.offset[:] = [float(v) for v in tree.offset]
+        self.data_dim = tree.data_dim
+        self.device = device
+        self._h = C.c_void_p()
+        _check(lib().mnv_tree_create(C.byref(self._h), C.byref(d), max_capacity, device))
+        self._keep = None  # host arrays are not referenced after the upload
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _lib is not None:
+            _lib.mnv_tree_destroy(h)
+        self._h = None
+
+    __del__ = close
+
+    @property
+    def capacity(self) -> int:
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().mnv_tree_capacity(self._h, C.byref(a), C.byref(b)))
+        return a.value
+
+    @property
+    def max_capacity(self) -> int:
+        a, b = C.c_int64(), C.c_int64()
+        _check(lib().mnv_tree_capacity(self._h, C.byref(a), C.byref(b)))
+        return b.value
+
+    def device_bytes(self) -> int:
+        n = C.c_uint64()
+        _check(lib().mnv_tree_device_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def download(self, first: int = 0, count: int | None = None):
+        """Back to the reference's AoS arrays: (data f16, child, parent, sample_counts)."""
+        count = self.capacity - first if count is None else count
+        data = np.empty((count, 8, self.data_dim), np.uint16)
+        child = np.empty((count, 8), np.int32)
+        parent = np.empty(count, np.int32)
+        sc = np.empty((count, 8), np.int16)
+        _check(lib().mnv_tree_download(self._h, first, count, data.ctypes.data, child.ctypes.data,
+                                       parent.ctypes.data, sc.ctypes.data))
+        return data.view(np.float16), child, parent, sc
+
+    # ---- point query (rt_core.cuh:117-159) ---------------------------------
+    def query_points(self, xyz, stream=None):
+        torch = _torch()
+        xyz = torch.as_tensor(xyz, dtype=torch.float32, device=f"cuda:{self.device}").contiguous()
+        out = torch.empty((xyz.shape[0], 3), dtype=torch.int32, device=xyz.device)
+        _check(lib().mnv_query_points(self._h, _dptr(xyz), xyz.shape[0], _dptr(out), _stream_ptr(stream)))
+        return out
+
+    # ---- octree render (renderer_kernel.cu:396-437) --------------------------
+    def render(self, cam, opt: RenderOptions, *, out=None, to_split=None, to_sample=None,
+               visited=None, track_visit=False, stream=None):
+        """Offscreen render into a device RGBA8 tensor [H, W, 4]."""
+        torch = _torch()
+        cam = make_camera(cam)
+        if out is None:
+            out = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+        _check(lib().mnv_render_voxels(self._h, C.byref(cam), C.byref(opt), None, None, _dptr(out),
+                                       _dptr(to_split), _dptr(to_sample), _dptr(visited),
+                                       track_visit, True, _stream_ptr(stream)))
+        return out
+
+    def render_tiles(self, cam, opt, out, tile_w, tile_h, tile_mod, tile_rem, *, to_split=None,
+                     to_sample=None, stream=None):
+        cam = make_camera(cam)
+        _check(lib().mnv_render_voxels_tiles(self._h, C.byref(cam), C.byref(opt), _dptr(out),
+                                             _dptr(to_split), _dptr(to_sample), tile_w, tile_h,
+                                             tile_mod, tile_rem, _stream_ptr(stream)))
+        return out
+
+    def render_logged(self, cam, opt, log_cap: int = 0, stream=None):
+        """Parity helper: image + per-ray visit hash / count / shaded count / log."""
+        torch = _torch()
+        cam = make_camera(cam)
+        dev = f"cuda:{self.device}"
+        P = cam.width * cam.height
+        img = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=dev)
+        vh = torch.zeros(P, dtype=torch.int64, device=dev)
+        vc = torch.zeros(P, dtype=torch.int32, device=dev)
+        vs = torch.zeros(P, dtype=torch.int32, device=dev)
+        vlog = torch.full((P, log_cap), -1, dtype=torch.int32, device=dev) if log_cap > 0 else None
+        _check(lib().mnv_render_voxels_logged(self._h, C.byref(cam), C.byref(opt), _dptr(img), _dptr(vh),
+                                              _dptr(vc), _dptr(vs), _dptr(vlog), log_cap,
+                                              _stream_ptr(stream)))
+        torch.cuda.synchronize()
+        return dict(rgba=img.cpu().numpy(), hash=vh.cpu().numpy().view(np.uint64),
+                    count=vc.cpu().numpy(), shaded=vs.cpu().numpy(),
+                    log=None if vlog is None else vlog.cpu().numpy())
+
+    def render_frame_host(self, cam, opt, rgba_host: np.ndarray | None = None, stats: bool = False):
+        """The per-frame call with HOST buffers (camera in, RGBA8 frame out)."""
+        cam = make_camera(cam)
+        if rgba_host is None:
+            rgba_host = np.empty((cam.height, cam.width, 4), np.uint8)
+        st = FrameStats() if stats else None
+        _check(lib().mnv_render_frame_host(self._h, C.byref(cam), C.byref(opt),
+                                           C.c_void_p(rgba_host.ctypes.data),
+                                           C.byref(st) if stats else None))
+        if stats:
+            return rgba_host, dict(rays=st.rays, visits=st.visits, shaded_visits=st.shaded_visits,
+                                   rays_hit=st.rays_hit)
+        return rgba_host

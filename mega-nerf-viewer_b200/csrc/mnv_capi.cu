@@ -1,0 +1,303 @@
+// extern "C" surface of libmnv_b200.so (include/mnv_b200.h).
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "mnv_internal.cuh"
+
+using namespace mnv;
+
+struct mnv_tree {
+    DeviceTree t;
+    std::map<void *, cudaSurfaceObject_t> surfaces;  // cudaArray_t -> surface, created once
+};
+
+namespace {
+
+int check_device(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return MNV_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device %d out of range (have %d)", device, n);
+        return MNV_ERR_INVALID;
+    }
+    return MNV_OK;
+}
+
+// The reference creates a cudaSurfaceObject_t per launch and never destroys it
+// (src/cuda/renderer_kernel.cu:377-385,410-428); here one per array, cached.
+int surface_for(mnv_tree *tree, void *arr, cudaSurfaceObject_t *out) {
+    *out = 0;
+    if (!arr) return MNV_OK;
+    auto it = tree->surfaces.find(arr);
+    if (it != tree->surfaces.end()) {
+        *out = it->second;
+        return MNV_OK;
+    }
+    cudaResourceDesc rd;
+    std::memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = static_cast<cudaArray_t>(arr);
+    cudaSurfaceObject_t s = 0;
+    MNV_CUDA(cudaCreateSurfaceObject(&s, &rd));
+    tree->surfaces[arr] = s;
+    *out = s;
+    return MNV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mnv_version(void) { return "mnv_b200 0.1 (sm_100a)"; }
+const char *mnv_last_error(void) { return last_error_cstr(); }
+
+int mnv_device_count(int *count) {
+    if (!count) return MNV_ERR_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    *count = n;
+    return MNV_OK;
+}
+
+void mnv_render_options_default(mnv_render_options *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->step_size = 1e-4f;
+    o->sigma_thresh = 1e-2f;
+    o->stop_thresh = 1e-2f;
+    o->background_brightness = 1.f;
+    o->render_bbox[3] = o->render_bbox[4] = o->render_bbox[5] = 1.f;
+    o->basis_minmax[0] = 0;
+    o->basis_minmax[1] = MNV_GLOBAL_BASIS_MAX - 1;
+    o->grid_max_depth = 4;
+    o->max_depth = 16;
+    o->samples_per_corner = 8;
+    o->split_batch_size = 4192;
+    o->nerf_batch_size = 1024;
+    o->max_sample_count = 256;
+    o->appearance_embedding = -1;
+    o->max_guided_samples = 128;
+}
+
+int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *d, int64_t max_capacity, int device) {
+    if (!out || !d) return MNV_ERR_INVALID;
+    *out = nullptr;
+    if (d->N != 2) {
+        set_error("only N == 2 octrees are supported (got N = %d)", d->N);
+        return MNV_ERR_INVALID;
+    }
+    if (d->capacity <= 0 || !d->data || !d->child || d->data_dim <= 0) {
+        set_error("empty tree / missing arrays");
+        return MNV_ERR_INVALID;
+    }
+    if (d->format == MNV_FORMAT_SH) {
+        const int b = d->basis_dim;
+        if (!(b == 1 || b == 4 || b == 9 || b == 16 || b == 25) || d->data_dim != 3 * b + 1) {
+            set_error("SH tree needs basis_dim in {1,4,9,16,25} and data_dim == 3*basis_dim+1 "
+                      "(got %d, %d)", b, d->data_dim);
+            return MNV_ERR_FORMAT;
+        }
+    } else if (d->format == MNV_FORMAT_RGBA) {
+        if (d->data_dim != 4) {
+            set_error("RGBA tree needs data_dim == 4 (got %d)", d->data_dim);
+            return MNV_ERR_FORMAT;
+        }
+    } else {
+        set_error("unknown data format %d", d->format);
+        return MNV_ERR_FORMAT;
+    }
+    if (max_capacity < d->capacity) max_capacity = d->capacity;
+    if (max_capacity >= (1ll << 28)) {
+        set_error("max_capacity %lld too large (limit 2^28 nodes)", (long long) max_capacity);
+        return MNV_ERR_INVALID;
+    }
+    int rc = check_device(device);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaSetDevice(device));
+    mnv_tree *h = new (std::nothrow) mnv_tree();
+    if (!h) return MNV_ERR_OOM;
+    DeviceTree &t = h->t;
+    t.N = d->N;
+    t.data_dim = d->data_dim;
+    t.format = d->format;
+    t.basis_dim = d->format == MNV_FORMAT_SH ? d->basis_dim : -1;
+    t.capacity = d->capacity;
+    t.max_capacity = max_capacity;
+    t.device = device;
+    for (int i = 0; i < 3; ++i) {
+        t.scale[i] = d->scale[i];
+        t.offset[i] = d->offset[i];
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
+    }
+    rc = build_device_tree(t, *d);
+    if (rc != MNV_OK) {
+        mnv_tree_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return MNV_OK;
+}
+
+int mnv_tree_destroy(mnv_tree *h) {
+    if (!h) return MNV_OK;
+    cudaSetDevice(h->t.device);
+    for (auto &kv : h->surfaces) cudaDestroySurfaceObject(kv.second);
+    DeviceTree &t = h->t;
+    cudaFree(t.cell);
+    cudaFree(t.payload);
+    cudaFree(t.parent);
+    cudaFree(t.sample_counts);
+    cudaFree(t.frame_dev);
+    cudaFree(t.stats_dev);
+    if (t.stream) cudaStreamDestroy(t.stream);
+    delete h;
+    return MNV_OK;
+}
+
+int mnv_tree_capacity(const mnv_tree *h, int64_t *capacity, int64_t *max_capacity) {
+    if (!h) return MNV_ERR_INVALID;
+    if (capacity) *capacity = h->t.capacity;
+    if (max_capacity) *max_capacity = h->t.max_capacity;
+    return MNV_OK;
+}
+
+int mnv_tree_device_bytes(const mnv_tree *h, uint64_t *bytes) {
+    if (!h || !bytes) return MNV_ERR_INVALID;
+    const DeviceTree &t = h->t;
+    *bytes = (uint64_t) t.max_capacity * (8ull * (4 + 2 + 16ull * t.rec_u4) + 4);
+    return MNV_OK;
+}
+
+int mnv_tree_download(const mnv_tree *h, int64_t first, int64_t count, uint16_t *data,
+                      int32_t *child, int32_t *parent, int16_t *sample_counts) {
+    if (!h) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return download_device_tree(h->t, first, count, data, child, parent, sample_counts);
+}
+
+int mnv_query_points(const mnv_tree *h, const float *xyz_dev, int64_t n, int32_t *out_dev,
+                     void *stream) {
+    if (!h || (n > 0 && (!xyz_dev || !out_dev))) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return launch_query_points(h->t, xyz_dev, n, out_dev, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_voxels(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                      void *image_arr, void *depth_arr, uint8_t *image_linear_dev,
+                      float *to_split_dev, float *to_sample_dev, int32_t *visited_dev,
+                      bool track_visit, bool offscreen, void *stream) {
+    if (!h || !cam || !opt) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    RenderTargets tg;
+    tg.image_linear = image_linear_dev;
+    int rc = surface_for(h, image_arr, &tg.image_surf);
+    if (rc != MNV_OK) return rc;
+    if (!offscreen) {
+        if (!image_arr || !depth_arr) {
+            set_error("offscreen == false needs image and depth surfaces");
+            return MNV_ERR_INVALID;
+        }
+        rc = surface_for(h, depth_arr, &tg.depth_surf);
+        if (rc != MNV_OK) return rc;
+    }
+    tg.to_split = to_split_dev;
+    tg.to_sample = to_sample_dev;
+    tg.visited = visited_dev;
+    tg.track_visit = track_visit;
+    tg.offscreen = offscreen;
+    return launch_render_voxels(h->t, *cam, *opt, tg, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_voxels_tiles(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                            uint8_t *image_linear_dev, float *to_split_dev, float *to_sample_dev,
+                            int tile_w, int tile_h, int tile_mod, int tile_rem, void *stream) {
+    if (!h || !cam || !opt || !image_linear_dev) return MNV_ERR_INVALID;
+    if (tile_mod < 1 || tile_rem < 0 || tile_rem >= tile_mod) {
+        set_error("bad tile partition %d / %d", tile_rem, tile_mod);
+        return MNV_ERR_INVALID;
+    }
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    RenderTargets tg;
+    tg.image_linear = image_linear_dev;
+    tg.to_split = to_split_dev;
+    tg.to_sample = to_sample_dev;
+    tg.tile_w = tile_w;
+    tg.tile_h = tile_h;
+    tg.tile_mod = tile_mod;
+    tg.tile_rem = tile_rem;
+    return launch_render_voxels(h->t, *cam, *opt, tg, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_voxels_logged(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                             uint8_t *image_linear_dev, uint64_t *visit_hash_dev,
+                             int32_t *visit_count_dev, int32_t *shaded_count_dev,
+                             int32_t *visit_log_dev, int log_cap, void *stream) {
+    if (!h || !cam || !opt || !image_linear_dev) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    RenderTargets tg;
+    tg.image_linear = image_linear_dev;
+    tg.visit_hash = reinterpret_cast<unsigned long long *>(visit_hash_dev);
+    tg.visit_count = visit_count_dev;
+    tg.shaded_count = shaded_count_dev;
+    tg.visit_log = visit_log_dev;
+    tg.log_cap = visit_log_dev ? log_cap : 0;
+    if (!tg.visit_hash && !tg.visit_count && !tg.shaded_count && !tg.visit_log) {
+        set_error("no log output given");
+        return MNV_ERR_INVALID;
+    }
+    return launch_render_voxels(h->t, *cam, *opt, tg, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_frame_host(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                          uint8_t *rgba_host, mnv_frame_stats *stats) {
+    if (!h || !cam || !opt || !rgba_host) return MNV_ERR_INVALID;
+    DeviceTree &t = h->t;
+    MNV_CUDA(cudaSetDevice(t.device));
+    const size_t bytes = (size_t) cam->width * cam->height * 4;
+    if (bytes == 0) return MNV_ERR_INVALID;
+    if (t.frame_bytes < bytes) {
+        cudaFree(t.frame_dev);
+        t.frame_dev = nullptr;
+        t.frame_bytes = 0;
+        MNV_CUDA(cudaMalloc(&t.frame_dev, bytes));
+        t.frame_bytes = bytes;
+    }
+    RenderTargets tg;
+    tg.image_linear = t.frame_dev;
+    if (stats) {
+        if (!t.stats_dev) MNV_CUDA(cudaMalloc(&t.stats_dev, 4 * sizeof(unsigned long long)));
+        MNV_CUDA(cudaMemsetAsync(t.stats_dev, 0, 4 * sizeof(unsigned long long), t.stream));
+        tg.frame_stats = t.stats_dev;
+    }
+    int rc = launch_render_voxels(t, *cam, *opt, tg, t.stream);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaMemcpyAsync(rgba_host, t.frame_dev, bytes, cudaMemcpyDeviceToHost, t.stream));
+    if (stats) {
+        unsigned long long hs[4];
+        MNV_CUDA(cudaMemcpyAsync(hs, t.stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, t.stream));
+        MNV_CUDA(cudaStreamSynchronize(t.stream));
+        stats->rays = hs[0];
+        stats->visits = hs[1];
+        stats->shaded_visits = hs[2];
+        stats->rays_hit = hs[3];
+    } else {
+        MNV_CUDA(cudaStreamSynchronize(t.stream));
+    }
+    return MNV_OK;
+}
+
+}  // extern "C"

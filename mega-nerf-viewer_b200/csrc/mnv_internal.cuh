@@ -1,0 +1,135 @@
+// Internal declarations shared by the CUDA translation units of libmnv_b200.so.
+// Nothing here is part of the public C-ABI (include/mnv_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/mnv_b200.h"
+
+namespace mnv {
+
+// ---------------------------------------------------------------- errors ----
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define MNV_CUDA(call)                                                            \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return ::mnv::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------- device tree (SoA) --
+//
+// The reference keeps the tree as four AoS tensors (include/data_spec.hpp:25-50):
+//   data[max][8][D] f16, child[max][8] i32 (relative), parent[max] i32,
+//   sample_counts[max][8] i16.
+// Here a leaf visit needs exactly ONE 4-byte load to learn everything the
+// march needs to decide what to do with a cell:
+//
+//   cell[node*8 + slot]  (u32 plane)
+//     bit31 = 0 : internal -> bits 0..30 = ABSOLUTE index of the child node
+//     bit31 = 1 : leaf     -> bits 16..30 = sample count (i16 >= 0),
+//                             bits 0..15  = sigma, fp16 bits
+//
+//   payload[(node*8 + slot) * rec_u4]  (uint4 plane, 16-byte aligned records)
+//     the leaf's data_dim fp16 values (colour / SH coefficients, sigma last),
+//     zero-padded to a multiple of 8 halfs: SH9 -> 28 halfs -> one 64-byte
+//     record = two 32-byte sectors, fetched with 4 LDG.128 instead of the
+//     reference's 27 scalar LDG.U16 of a 56-byte record straddling 3 sectors.
+//
+//   parent[node] (i32 plane, packed parent slot = parent_node*8 + child) is
+//     only touched by refinement / pruning.
+struct DeviceTree {
+    uint32_t *cell = nullptr;
+    uint4 *payload = nullptr;
+    int32_t *parent = nullptr;
+    int16_t *sample_counts = nullptr;  // [max*8] authoritative counts (refinement only)
+    int N = 2;
+    int data_dim = 0;
+    int format = MNV_FORMAT_RGBA;
+    int basis_dim = -1;
+    int rec_u4 = 0;  // uint4 per payload record
+    int64_t capacity = 0;
+    int64_t max_capacity = 0;
+    float scale[3] = {1, 1, 1};
+    float offset[3] = {0, 0, 0};
+    int device = 0;
+    // scratch for mnv_render_frame_host
+    uint8_t *frame_dev = nullptr;
+    size_t frame_bytes = 0;
+    unsigned long long *stats_dev = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+
+__host__ __device__ inline uint32_t make_leaf_cell(uint16_t sigma_bits, int sample_count) {
+    const uint32_t sc = (uint32_t) (sample_count < 0 ? 0 : (sample_count > 32767 ? 32767 : sample_count));
+    return kLeafBit | (sc << 16) | sigma_bits;
+}
+
+// Kernel-side view, passed by value.
+struct TreeView {
+    const uint32_t *__restrict__ cell;
+    const uint4 *__restrict__ payload;
+    int rec_u4;
+    int data_dim;
+    int format;
+    int basis_dim;
+    float scale[3];
+    float offset[3];
+};
+
+inline TreeView make_view(const DeviceTree &t) {
+    TreeView v;
+    v.cell = t.cell;
+    v.payload = t.payload;
+    v.rec_u4 = t.rec_u4;
+    v.data_dim = t.data_dim;
+    v.format = t.format;
+    v.basis_dim = t.basis_dim;
+    for (int i = 0; i < 3; ++i) {
+        v.scale[i] = t.scale[i];
+        v.offset[i] = t.offset[i];
+    }
+    return v;
+}
+
+// Outputs / modes of one render launch.
+struct RenderTargets {
+    uint8_t *image_linear = nullptr;      // RGBA8 [H][W]
+    cudaSurfaceObject_t image_surf = 0;   // or an RGBA8 surface (GL interop)
+    cudaSurfaceObject_t depth_surf = 0;   // R32F t_max surface, read when !offscreen
+    float *to_split = nullptr;            // [P][3]
+    float *to_sample = nullptr;           // [P][3]
+    int32_t *visited = nullptr;           // [max_capacity]
+    bool track_visit = false;
+    bool offscreen = true;
+    // parity / statistics
+    unsigned long long *visit_hash = nullptr;
+    int32_t *visit_count = nullptr;
+    int32_t *shaded_count = nullptr;
+    int32_t *visit_log = nullptr;
+    int log_cap = 0;
+    unsigned long long *frame_stats = nullptr;  // [4] rays, visits, shaded, rays_hit
+    // image-tile partition (multi-GPU): render tiles with (tile % mod) == rem
+    int tile_w = 0, tile_h = 0, tile_mod = 1, tile_rem = 0;
+};
+
+int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
+                         const mnv_render_options &opt, const RenderTargets &tg,
+                         cudaStream_t stream);
+
+int launch_query_points(const DeviceTree &tree, const float *xyz, int64_t n, int32_t *out,
+                        cudaStream_t stream);
+
+const char *last_error_cstr();
+int build_device_tree(DeviceTree &t, const mnv_tree_desc &desc);
+int download_device_tree(const DeviceTree &t, int64_t first, int64_t count, uint16_t *data,
+                         int32_t *child, int32_t *parent, int16_t *sample_counts);
+
+}  // namespace mnv

@@ -1,0 +1,501 @@
+// Octree traversal + volume-rendering integration for sm_100a.
+//
+// Replaces the reference's render_voxels_kernel
+// (src/cuda/renderer_kernel.cu:243-292) and device::render_voxels_trace_ray /
+// query_single_from_root (include/cuda/rt_core.cuh:117-332).
+//
+// What is different from the reference (all of it layout / schedule, none of
+// it arithmetic — see mnv_math.cuh for the numeric contract):
+//   * query: the reference restarts at the root for every step of every ray
+//     (depth dependent loads).  The descent x*=2; f=floor(x); x-=f is exact in
+//     fp32, so the leaf containing pos is exactly the integer cell
+//     floor(pos*2^d).  Each ray keeps q = floor(pos*2^24) per axis and the node
+//     path of its previous leaf in shared memory; a step re-descends only below
+//     the deepest common ancestor of the old and new cell (clz of the XOR),
+//     ~2 dependent loads instead of ~10, usually L1 hits.
+//   * one 4-byte "cell" word per slot holds child link OR (leaf, sigma, sample
+//     count): an empty leaf visit costs exactly one load.
+//   * shaded leaves fetch one aligned 64-byte record with 4 x LDG.128.
+//   * warps own 8x4-pixel tiles (rays of a warp stay in neighbouring leaves)
+//     instead of 32x1 row segments.
+//   * split / re-sample candidates live in registers and are written once per
+//     ray; camera and options travel as kernel parameters (no 48-byte upload).
+#include <cuda_fp16.h>
+
+#include "mnv_internal.cuh"
+#include "mnv_math.cuh"
+
+namespace mnv {
+namespace {
+
+constexpr int kThreads = 128;    // 4 warps: block tile = 16 x 8 pixels
+constexpr int kTileW = 16, kTileH = 8;
+constexpr int kMaxLevel = 23;    // q carries 24 bits per axis
+
+struct RenderParams {
+    TreeView tree;
+    mnv_camera cam;
+    mnv_render_options opt;
+    RenderTargets tg;
+    int tiles_x, tiles_y;
+    int mtiles_x;  // macro tiles per row (multi-GPU partition)
+};
+
+template <int R>
+__device__ __forceinline__ float rec_half(const uint32_t (&w)[R], int h) {
+    const uint32_t v = w[h >> 1];
+    return __half2float(__ushort_as_half((unsigned short) ((h & 1) ? (v >> 16) : (v & 0xffffu))));
+}
+
+// One colour channel: tmp = B0*C0 (+ per-degree groups, each an FMUL + FFMA
+// chain then one FADD) — include/cuda/rt_core.cuh:257-286 as compiled.
+template <int TERMS, int R>
+__device__ __forceinline__ float sh_channel(const float (&B)[TERMS], const uint32_t (&w)[R],
+                                            int off) {
+    float tmp = __fmul_rn(B[0], rec_half(w, off));
+    if constexpr (TERMS >= 25) {
+        float s = __fmul_rn(B[17], rec_half(w, off + 17));
+        s = __fmaf_rn(B[16], rec_half(w, off + 16), s);
+#pragma unroll
+        for (int k = 18; k <= 24; ++k) s = __fmaf_rn(B[k < TERMS ? k : 0], rec_half(w, off + k), s);
+        tmp = __fadd_rn(tmp, s);
+    }
+    if constexpr (TERMS >= 16) {
+        float s = __fmul_rn(B[10 < TERMS ? 10 : 0], rec_half(w, off + 10));
+        s = __fmaf_rn(B[9 < TERMS ? 9 : 0], rec_half(w, off + 9), s);
+#pragma unroll
+        for (int k = 11; k <= 15; ++k) s = __fmaf_rn(B[k < TERMS ? k : 0], rec_half(w, off + k), s);
+        tmp = __fadd_rn(tmp, s);
+    }
+    if constexpr (TERMS >= 9) {
+        float s = __fmul_rn(B[5 < TERMS ? 5 : 0], rec_half(w, off + 5));
+        s = __fmaf_rn(B[4 < TERMS ? 4 : 0], rec_half(w, off + 4), s);
+#pragma unroll
+        for (int k = 6; k <= 8; ++k) s = __fmaf_rn(B[k < TERMS ? k : 0], rec_half(w, off + k), s);
+        tmp = __fadd_rn(tmp, s);
+    }
+    if constexpr (TERMS >= 4) {
+        float s = __fmul_rn(B[2 < TERMS ? 2 : 0], rec_half(w, off + 2));
+        s = __fmaf_rn(B[1 < TERMS ? 1 : 0], rec_half(w, off + 1), s);
+        s = __fmaf_rn(B[3 < TERMS ? 3 : 0], rec_half(w, off + 3), s);
+        tmp = __fadd_rn(tmp, s);
+    }
+    return tmp;
+}
+
+// TERMS: 0 = RGBA, else SH basis dimension (1,4,9,16,25).
+// TRACK: produce split / re-sample candidates.  LOGV: visit hash/count/log/stats.
+// VISIT: mark visited nodes (track_visit).
+template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
+__global__ void __launch_bounds__(kThreads)
+render_voxels_kernel(const RenderParams p) {
+    __shared__ int32_t s_path[kMaxLevel + 1][kThreads];
+
+    // ---- pixel mapping: block tile 16x8, warp tile 8x4 ---------------------
+    const int bt = blockIdx.x;
+    const int bty = bt / p.tiles_x, btx = bt - bty * p.tiles_x;
+    if (p.tg.tile_mod > 1) {
+        const int mt = ((bty * kTileH) / p.tg.tile_h) * p.mtiles_x + (btx * kTileW) / p.tg.tile_w;
+        if (mt % p.tg.tile_mod != p.tg.tile_rem) return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = btx * kTileW + (warp & 1) * 8 + (lane & 7);
+    const int y = bty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    const int W = p.cam.width, H = p.cam.height;
+    if (x >= W || y >= H) return;
+    const int idx = y * W + x;
+    const mnv_render_options &opt = p.opt;
+
+    uint32_t rgbx_init = 0;
+    if (!p.tg.offscreen) rgbx_init = surf2Dread<uint32_t>(p.tg.image_surf, x * 4, y, cudaBoundaryModeZero);
+
+    float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
+
+    // ---- ray generation: screen2worlddir, renderer_kernel.cu:30-38 ----------
+    const float *m = p.cam.c2w;
+    const float vx = __fdiv_rn(__fadd_rn(__fadd_rn((float) x, 0.5f), -p.cam.cx), p.cam.fx);
+    const float vy = __fdiv_rn(-__fadd_rn(__fadd_rn((float) y, 0.5f), -p.cam.cy), p.cam.fy);
+    float d0 = __fadd_rn(__fmaf_rn(vx, m[0], __fmul_rn(vy, m[3])), -m[6]);
+    float d1 = __fadd_rn(__fmaf_rn(vx, m[1], __fmul_rn(vy, m[4])), -m[7]);
+    float d2 = __fadd_rn(__fmaf_rn(vx, m[2], __fmul_rn(vy, m[5])), -m[8]);
+    {
+        const float inv = __frcp_rn(ref_norm3(d0, d1, d2));
+        d0 = __fmul_rn(d0, inv);
+        d1 = __fmul_rn(d1, inv);
+        d2 = __fmul_rn(d2, inv);
+    }
+    // cen = offset + scale * cen, renderer_kernel.cu:272-275 (FFMA)
+    const float c0 = __fmaf_rn(p.tree.scale[0], m[9], p.tree.offset[0]);
+    const float c1 = __fmaf_rn(p.tree.scale[1], m[10], p.tree.offset[1]);
+    const float c2 = __fmaf_rn(p.tree.scale[2], m[11], p.tree.offset[2]);
+
+    float tmax_bg = 1e9f;
+    if (!p.tg.offscreen) tmax_bg = surf2Dread<float>(p.tg.depth_surf, x * 4, y, cudaBoundaryModeZero);
+
+    float v0 = d0, v1 = d1, v2 = d2;  // view direction for the SH basis
+    ref_rodrigues(opt.rot_dirs, v0, v1, v2);
+
+    // ---- render_voxels_trace_ray, rt_core.cuh:162-332 ----------------------
+    float split_prio = (float) (opt.max_depth + 1), split_chunk = -1.f, split_child = -1.f;
+    float samp_prio = (float) (opt.max_sample_count + 1), samp_chunk = -1.f, samp_child = -1.f;
+    unsigned long long vhash = 0xcbf29ce484222325ULL;
+    int nvis = 0, nshaded = 0;
+    bool hit = false;
+
+    // _get_delta_scale, rt_core.cuh:102-115
+    d0 = __fmul_rn(d0, p.tree.scale[0]);
+    d1 = __fmul_rn(d1, p.tree.scale[1]);
+    d2 = __fmul_rn(d2, p.tree.scale[2]);
+    const float delta_scale = __frcp_rn(ref_norm3(d0, d1, d2));
+    d0 = __fmul_rn(d0, delta_scale);
+    d1 = __fmul_rn(d1, delta_scale);
+    d2 = __fmul_rn(d2, delta_scale);
+    tmax_bg = __fdiv_rn(tmax_bg, delta_scale);
+
+    // invdir = 1.f / (dir + 1e-9): double add + double reciprocal, rt_core.cuh:188-190
+    const float i0 = d2f(__drcp_rn(__dadd_rn((double) d0, 1e-9)));
+    const float i1 = d2f(__drcp_rn(__dadd_rn((double) d1, 1e-9)));
+    const float i2 = d2f(__drcp_rn(__dadd_rn((double) d2, 1e-9)));
+
+    // _dda_world, rt_core.cuh:70-86 (double, rounded to float per term)
+    float tmin = 0.f, tmax = 1e4f;
+    {
+        const float cc[3] = {c0, c1, c2};
+        const float ii[3] = {i0, i1, i2};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const double ci = (double) cc[i], inv = (double) ii[i];
+            const float t1 = d2f(__dmul_rn(
+                    __dadd_rn(__dadd_rn((double) opt.render_bbox[i], 1e-6), -ci), inv));
+            const float t2 = d2f(__dmul_rn(
+                    __dadd_rn(__dadd_rn((double) opt.render_bbox[i + 3], -1e-6), -ci), inv));
+            tmin = fmaxf(tmin, fminf(t1, t2));
+            tmax = fminf(tmax, fmaxf(t1, t2));
+        }
+    }
+    tmax = fminf(tmax, tmax_bg);
+
+    if (tmax < 0.f || tmin > tmax) {
+        if (opt.render_depth) out3 = 1.f;
+    } else {
+        hit = true;
+        float B[TERMS > 0 ? TERMS : 1];
+        if (TERMS > 0) {
+            ref_sh_basis<(TERMS > 0 ? TERMS : 1)>(v0, v1, v2, B);
+#pragma unroll
+            for (int k = 0; k < TERMS; ++k)
+                if (k < opt.basis_minmax[0] || k > opt.basis_minmax[1]) B[k] = 0.f;
+        }
+        constexpr int REC_W = TERMS > 0 ? ((3 * TERMS + 1 + 7) / 8) * 4 : 4;  // u32 words / record
+
+        float T = 1.f;
+        float t = tmin;
+        float max_weight = -1.f, max_sample_weight = -1.f;
+        uint32_t pqx = 0, pqy = 0, pqz = 0;
+        int pdepth = 1;  // previous leaf depth: path valid for levels < pdepth
+        const float clamp_hi = f_from_bits(0x3F7FFFEFu);  // 1.f - 1e-6f
+
+        while (t < tmax) {
+            // pos = cen + t*dir  (FFMA), clamp to [0, 1-1e-6]  (rt_core.cuh:221-223,125-127)
+            const float px = fmaxf(fminf(__fmaf_rn(t, d0, c0), clamp_hi), 0.f);
+            const float py = fmaxf(fminf(__fmaf_rn(t, d1, c1), clamp_hi), 0.f);
+            const float pz = fmaxf(fminf(__fmaf_rn(t, d2, c2), clamp_hi), 0.f);
+            // exact integer cell coordinates at level 24
+            const uint32_t qx = __float2uint_rd(__fmul_rn(px, 16777216.f));
+            const uint32_t qy = __float2uint_rd(__fmul_rn(py, 16777216.f));
+            const uint32_t qz = __float2uint_rd(__fmul_rn(pz, 16777216.f));
+            const uint32_t diff = (qx ^ pqx) | (qy ^ pqy) | (qz ^ pqz);
+            pqx = qx;
+            pqy = qy;
+            pqz = qz;
+            // number of leading (from bit 23) bits shared with the previous cell
+            int lvl = min(__clz((int) diff) - 8, pdepth - 1);
+            int32_t node = lvl > 0 ? s_path[lvl][threadIdx.x] : 0;
+            uint32_t cw;
+            int cidx;
+            for (;;) {
+                if (VISIT) {
+                    if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
+                }
+                const int bit = 23 - lvl;
+                cidx = (((qx >> bit) & 1u) << 2) | (((qy >> bit) & 1u) << 1) | ((qz >> bit) & 1u);
+                cw = __ldg(p.tree.cell + ((int64_t) node * 8 + cidx));
+                if ((cw & kLeafBit) || lvl >= kMaxLevel) break;
+                node = (int32_t) cw;
+                ++lvl;
+                s_path[lvl][threadIdx.x] = node;
+            }
+            const int depth = lvl + 1;
+            pdepth = depth;
+            if (LOGV) {
+                const long long packed = (long long) node * 8 + cidx;
+                vhash = (vhash ^ (unsigned long long) packed) * 0x100000001b3ULL;
+                if (p.tg.visit_log && nvis < p.tg.log_cap)
+                    p.tg.visit_log[(size_t) idx * p.tg.log_cap + nvis] = (int32_t) packed;
+                ++nvis;
+            }
+
+            // position inside the leaf, in leaf units: frac(pos * 2^depth) (exact)
+            const float cube = __uint_as_float((uint32_t) (127 + depth) << 23);
+            const float icube = __uint_as_float((uint32_t) (127 - depth) << 23);
+            const float sx = __fmul_rn(px, cube), sy = __fmul_rn(py, cube), sz = __fmul_rn(pz, cube);
+            const float fx = __fadd_rn(sx, -floorf(sx));
+            const float fy = __fadd_rn(sy, -floorf(sy));
+            const float fz = __fadd_rn(sz, -floorf(sz));
+            // _dda_unit, rt_core.cuh:88-100: FMUL then FADD (not fused in the reference build)
+            float tm;
+            {
+                const float a1 = __fmul_rn(-fx, i0), a2 = __fadd_rn(a1, i0);
+                const float b1 = __fmul_rn(-fy, i1), b2 = __fadd_rn(b1, i1);
+                const float e1 = __fmul_rn(-fz, i2), e2 = __fadd_rn(e1, i2);
+                tm = fminf(fminf(fminf(fmaxf(a1, a2), 1e4f), fmaxf(b1, b2)), fmaxf(e1, e2));
+            }
+            // / cube_size (exact power of two), + step_size
+            const float delta_t = __fadd_rn(__fmul_rn(tm, icube), opt.step_size);
+            const float sigma = __half2float(__ushort_as_half((unsigned short) (cw & 0xffffu)));
+            const int scount = (int) ((cw >> 16) & 0x7fffu);
+
+            if ((cw & kLeafBit) && sigma > opt.sigma_thresh) {
+                if (LOGV) ++nshaded;
+                const float att =
+                        ref_expf(__fmul_rn(__fmul_rn(delta_scale, -delta_t), sigma));
+                const float weight = __fmul_rn(T, __fadd_rn(1.f, -att));
+                if (TRACK) {
+                    if (weight > max_weight && depth < opt.max_depth) {
+                        split_chunk = (float) node;
+                        split_child = (float) cidx;
+                        split_prio = (float) depth;
+                        max_weight = weight;
+                    }
+                    if (weight > max_sample_weight && scount < opt.max_sample_count) {
+                        samp_chunk = (float) node;
+                        samp_child = (float) cidx;
+                        samp_prio = (float) scount;
+                        max_sample_weight = weight;
+                    }
+                }
+                if (opt.render_depth) {
+                    out0 = __fmaf_rn(t, weight, out0);
+                } else {
+                    const uint4 *rec = p.tree.payload + ((int64_t) node * 8 + cidx) * (REC_W / 4);
+                    uint32_t w[REC_W];
+#pragma unroll
+                    for (int j = 0; j < REC_W / 4; ++j) {
+                        const uint4 v = __ldg(rec + j);
+                        w[4 * j] = v.x;
+                        w[4 * j + 1] = v.y;
+                        w[4 * j + 2] = v.z;
+                        w[4 * j + 3] = v.w;
+                    }
+                    if (TERMS > 0) {
+                        out0 = __fadd_rn(out0, ref_weighted_sigmoid(
+                                weight, sh_channel<(TERMS > 0 ? TERMS : 1), REC_W>(B, w, 0)));
+                        out1 = __fadd_rn(out1, ref_weighted_sigmoid(
+                                weight, sh_channel<(TERMS > 0 ? TERMS : 1), REC_W>(B, w, TERMS)));
+                        out2 = __fadd_rn(out2, ref_weighted_sigmoid(
+                                weight, sh_channel<(TERMS > 0 ? TERMS : 1), REC_W>(B, w, 2 * TERMS)));
+                    } else {
+                        out0 = __fmaf_rn(weight, rec_half(w, 0), out0);
+                        out1 = __fmaf_rn(weight, rec_half(w, 1), out1);
+                        out2 = __fmaf_rn(weight, rec_half(w, 2), out2);
+                    }
+                }
+                T = __fmul_rn(T, att);
+                if (T < opt.stop_thresh) {
+                    if (opt.render_depth) out0 = out1 = out2 = fminf(__fmul_rn(out0, 0.3f), 1.0f);
+                    const float scale = __frcp_rn(__fadd_rn(1.f, -T));
+                    out0 = __fmul_rn(out0, scale);
+                    out1 = __fmul_rn(out1, scale);
+                    out2 = __fmul_rn(out2, scale);
+                    out3 = 1.f;
+                    T = -1.f;  // marks "terminated early"
+                    break;
+                }
+            } else if (TRACK) {
+                if (max_weight == -1.f && depth < opt.max_depth) {
+                    split_chunk = (float) node;
+                    split_child = (float) cidx;
+                    split_prio = (float) depth;
+                }
+                if (max_sample_weight == -1.f && scount < opt.max_sample_count) {
+                    samp_chunk = (float) node;
+                    samp_child = (float) cidx;
+                    samp_prio = (float) scount;
+                }
+            }
+            t = __fadd_rn(t, delta_t);
+        }
+        if (T >= 0.f) {
+            if (opt.render_depth) {
+                out0 = out1 = out2 = fminf(__fmul_rn(out0, 0.3f), 1.0f);
+                out3 = 1.f;
+            } else {
+                out3 = __fadd_rn(1.f, -T);
+            }
+        }
+    }
+
+    // ---- composite_and_write, renderer_kernel.cu:215-241 --------------------
+    const float nalpha = __fadd_rn(1.f, -out3);
+    if (p.tg.offscreen) {
+        const float remain = __fmul_rn(nalpha, opt.background_brightness);
+        out0 = __fadd_rn(out0, remain);
+        out1 = __fadd_rn(out1, remain);
+        out2 = __fadd_rn(out2, remain);
+    } else {
+        const float r0 = __fdiv_rn((float) (rgbx_init & 0xffu), 255.f);
+        const float r1 = __fdiv_rn((float) ((rgbx_init >> 8) & 0xffu), 255.f);
+        const float r2 = __fdiv_rn((float) ((rgbx_init >> 16) & 0xffu), 255.f);
+        out0 = __fmaf_rn(r0, nalpha, out0);
+        out1 = __fadd_rn(__fmul_rn(r1, nalpha), out1);
+        out2 = __fadd_rn(__fmul_rn(r2, nalpha), out2);
+    }
+    const uint32_t rgba = ref_to_u8(out0) | (ref_to_u8(out1) << 8) | (ref_to_u8(out2) << 16) | 0xff000000u;
+    if (p.tg.image_linear)
+        reinterpret_cast<uint32_t *>(p.tg.image_linear)[idx] = rgba;
+    else
+        surf2Dwrite(rgba, p.tg.image_surf, x * 4, y, cudaBoundaryModeZero);
+
+    if (TRACK) {
+        float *ts = p.tg.to_split + (size_t) idx * 3;
+        ts[0] = split_prio;
+        ts[1] = split_chunk;
+        ts[2] = split_child;
+        float *tp = p.tg.to_sample + (size_t) idx * 3;
+        tp[0] = samp_prio;
+        tp[1] = samp_chunk;
+        tp[2] = samp_child;
+    }
+    if (LOGV) {
+        if (p.tg.visit_hash) p.tg.visit_hash[idx] = vhash;
+        if (p.tg.visit_count) p.tg.visit_count[idx] = nvis;
+        if (p.tg.shaded_count) p.tg.shaded_count[idx] = nshaded;
+        if (p.tg.frame_stats) {
+            atomicAdd(p.tg.frame_stats + 0, 1ull);
+            atomicAdd(p.tg.frame_stats + 1, (unsigned long long) nvis);
+            atomicAdd(p.tg.frame_stats + 2, (unsigned long long) nshaded);
+            atomicAdd(p.tg.frame_stats + 3, hit ? 1ull : 0ull);
+        }
+    }
+}
+
+// query_single_from_root for arbitrary points (include/cuda/rt_core.cuh:117-159).
+__global__ void query_points_kernel(TreeView tree, const float *__restrict__ xyz, int64_t n,
+                                    int32_t *__restrict__ out) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float hi = f_from_bits(0x3F7FFFEFu);
+    const float px = fmaxf(fminf(xyz[3 * i], hi), 0.f);
+    const float py = fmaxf(fminf(xyz[3 * i + 1], hi), 0.f);
+    const float pz = fmaxf(fminf(xyz[3 * i + 2], hi), 0.f);
+    const uint32_t qx = __float2uint_rd(__fmul_rn(px, 16777216.f));
+    const uint32_t qy = __float2uint_rd(__fmul_rn(py, 16777216.f));
+    const uint32_t qz = __float2uint_rd(__fmul_rn(pz, 16777216.f));
+    int32_t node = 0;
+    int lvl = 0, cidx;
+    for (;;) {
+        const int bit = 23 - lvl;
+        cidx = (((qx >> bit) & 1u) << 2) | (((qy >> bit) & 1u) << 1) | ((qz >> bit) & 1u);
+        const uint32_t cw = __ldg(tree.cell + ((int64_t) node * 8 + cidx));
+        if ((cw & kLeafBit) || lvl >= kMaxLevel) break;
+        node = (int32_t) cw;
+        ++lvl;
+    }
+    out[3 * i] = node;
+    out[3 * i + 1] = cidx;
+    out[3 * i + 2] = lvl + 1;
+}
+
+template <int TERMS>
+int dispatch(const RenderParams &p, bool track, bool logv, bool visit, dim3 grid,
+             cudaStream_t stream) {
+#define MNV_LAUNCH(T, L, V) \
+    render_voxels_kernel<TERMS, T, L, V><<<grid, kThreads, 0, stream>>>(p)
+    if (logv) {
+        if (track) MNV_LAUNCH(true, true, false);
+        else MNV_LAUNCH(false, true, false);
+    } else if (visit) {
+        if (track) MNV_LAUNCH(true, false, true);
+        else MNV_LAUNCH(false, false, true);
+    } else {
+        if (track) MNV_LAUNCH(true, false, false);
+        else MNV_LAUNCH(false, false, false);
+    }
+#undef MNV_LAUNCH
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+
+}  // namespace
+
+int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
+                         const mnv_render_options &opt, const RenderTargets &tg,
+                         cudaStream_t stream) {
+    if (cam.width <= 0 || cam.height <= 0) {
+        set_error("camera size %dx%d", cam.width, cam.height);
+        return MNV_ERR_INVALID;
+    }
+    if ((tg.image_linear == nullptr) == (tg.image_surf == 0)) {
+        set_error("exactly one of image_linear / image surface must be given");
+        return MNV_ERR_INVALID;
+    }
+    if ((tg.to_split == nullptr) != (tg.to_sample == nullptr)) {
+        set_error("to_split and to_sample must be given together");
+        return MNV_ERR_INVALID;
+    }
+    if (tg.track_visit && !tg.visited) {
+        set_error("track_visit needs a visited buffer");
+        return MNV_ERR_INVALID;
+    }
+    RenderParams p;
+    p.tree = make_view(tree);
+    p.cam = cam;
+    p.opt = opt;
+    p.tg = tg;
+    p.tiles_x = (cam.width + kTileW - 1) / kTileW;
+    p.tiles_y = (cam.height + kTileH - 1) / kTileH;
+    if (p.tg.tile_mod > 1) {
+        if (p.tg.tile_w < kTileW || p.tg.tile_h < kTileH || p.tg.tile_w % kTileW ||
+            p.tg.tile_h % kTileH) {
+            set_error("tile size must be a multiple of %dx%d", kTileW, kTileH);
+            return MNV_ERR_INVALID;
+        }
+        p.mtiles_x = (cam.width + p.tg.tile_w - 1) / p.tg.tile_w;
+    } else {
+        p.tg.tile_mod = 1;
+        p.mtiles_x = 1;
+    }
+    const bool track = tg.to_split != nullptr;
+    const bool logv = tg.visit_hash || tg.visit_count || tg.shaded_count || tg.visit_log ||
+                      tg.frame_stats;
+    const bool visit = tg.track_visit;
+    if (logv && visit) {
+        set_error("visit logging and track_visit cannot be combined");
+        return MNV_ERR_INVALID;
+    }
+    const dim3 grid((unsigned) (p.tiles_x * p.tiles_y));
+    const int terms = tree.format == MNV_FORMAT_SH ? tree.basis_dim : 0;
+    switch (terms) {
+        case 0: return dispatch<0>(p, track, logv, visit, grid, stream);
+        case 1: return dispatch<1>(p, track, logv, visit, grid, stream);
+        case 4: return dispatch<4>(p, track, logv, visit, grid, stream);
+        case 9: return dispatch<9>(p, track, logv, visit, grid, stream);
+        case 16: return dispatch<16>(p, track, logv, visit, grid, stream);
+        case 25: return dispatch<25>(p, track, logv, visit, grid, stream);
+        default:
+            set_error("unsupported SH basis_dim %d", terms);
+            return MNV_ERR_INVALID;
+    }
+}
+
+int launch_query_points(const DeviceTree &tree, const float *xyz, int64_t n, int32_t *out,
+                        cudaStream_t stream) {
+    if (n <= 0) return MNV_OK;
+    const int th = 256;
+    query_points_kernel<<<(unsigned) ((n + th - 1) / th), th, 0, stream>>>(make_view(tree), xyz, n,
+                                                                           out);
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+
+}  // namespace mnv

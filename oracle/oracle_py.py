@@ -185,3 +185,103 @@ def render_voxels(tree, cam: dict, opt: RenderOptions, *, trackers=False, log_ca
         y0, H if y1 is None else y1, row_step, nthreads)
     assert rc == 0, rc
     return dict(rgba=rgba, to_split=split, to_sample=sample, hash=vh, count=vc, shaded=vs, log=vlog)
+
+
+# ---------------------------------------------------------------------------
+# The reference's own CUDA path (oracle/_ref, built by oracle/build_ref.sh)
+# ---------------------------------------------------------------------------
+def ref_available(instr: bool = False) -> bool:
+    return os.path.exists(REF_INSTR_SO if instr else REF_SO)
+
+
+class RefRenderer:
+    """Runs the unmodified reference kernel (rebuilt for sm_100) headlessly."""
+
+    def __init__(self, npz_path: str, max_capacity: int = 0, instr: bool = False):
+        import torch  # noqa: F401  (loads libtorch / libc10 before the driver .so)
+
+        so = REF_INSTR_SO if instr else REF_SO
+        if not os.path.exists(so):
+            raise FileNotFoundError(so)
+        self.instr = instr
+        self.L = C.CDLL(so)
+        L = self.L
+        L.ref_open.restype = C.c_void_p
+        L.ref_open.argtypes = [C.c_char_p, C.c_long]
+        L.ref_close.argtypes = [C.c_void_p]
+        L.ref_capacity.argtypes = [C.c_void_p]
+        L.ref_data_dim.argtypes = [C.c_void_p]
+        L.ref_download.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ref_render_voxels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p]
+        L.ref_render_frame_host.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_void_p]
+        if instr:
+            L.ref_render_voxels_logged.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_int]
+        self.h = L.ref_open(npz_path.encode(), max_capacity)
+        if not self.h:
+            raise RuntimeError(f"reference N3Tree::open failed for {npz_path}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ref_close(self.h)
+            self.h = None
+
+    __del__ = close
+
+    @property
+    def capacity(self):
+        return self.L.ref_capacity(self.h)
+
+    def download(self):
+        cap, D = self.capacity, self.L.ref_data_dim(self.h)
+        data = np.empty((cap, 8, D), np.uint16)
+        child = np.empty((cap, 8), np.int32)
+        parent = np.empty(cap, np.int32)
+        scale = np.empty(3, np.float32)
+        offset = np.empty(3, np.float32)
+        self.L.ref_download(self.h, data.ctypes.data, child.ctypes.data, parent.ctypes.data,
+                            scale.ctypes.data, offset.ctypes.data)
+        return data.view(np.float16), child, parent, scale, offset
+
+    @staticmethod
+    def _cam_args(cam: dict):
+        intr = np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32)
+        c2w = np.ascontiguousarray(cam["c2w"], np.float32)
+        return int(cam["width"]), int(cam["height"]), intr, c2w
+
+    def render(self, cam: dict, opt: RenderOptions, iters: int = 1, trackers: bool = True):
+        w, h, intr, c2w = self._cam_args(cam)
+        rgba = np.zeros((h, w, 4), np.uint8)
+        split = np.zeros((h * w, 3), np.float32) if trackers else None
+        sample = np.zeros((h * w, 3), np.float32) if trackers else None
+        ms = np.zeros(max(iters, 1), np.float32)
+        rc = self.L.ref_render_voxels(self.h, w, h, intr.ctypes.data, c2w.ctypes.data, C.byref(opt),
+                                      C.sizeof(opt), rgba.ctypes.data, _ptr(split), _ptr(sample),
+                                      iters, ms.ctypes.data)
+        assert rc == 0, rc
+        return dict(rgba=rgba, to_split=split, to_sample=sample, ms=ms)
+
+    def render_frame_host(self, cam: dict, opt: RenderOptions, rgba: np.ndarray):
+        w, h, intr, c2w = self._cam_args(cam)
+        rc = self.L.ref_render_frame_host(self.h, w, h, intr.ctypes.data, c2w.ctypes.data,
+                                          C.byref(opt), C.sizeof(opt), rgba.ctypes.data)
+        assert rc == 0, rc
+        return rgba
+
+    def render_logged(self, cam: dict, opt: RenderOptions, log_cap: int = 0):
+        assert self.instr
+        w, h, intr, c2w = self._cam_args(cam)
+        P = w * h
+        rgba = np.zeros((h, w, 4), np.uint8)
+        vh = np.zeros(P, np.uint64)
+        vc = np.zeros(P, np.int32)
+        vlog = np.full((P, log_cap), -1, np.int32) if log_cap > 0 else None
+        rc = self.L.ref_render_voxels_logged(self.h, w, h, intr.ctypes.data, c2w.ctypes.data,
+                                             C.byref(opt), C.sizeof(opt), rgba.ctypes.data,
+                                             vh.ctypes.data, vc.ctypes.data, _ptr(vlog), log_cap)
+        assert rc == 0, rc
+        return dict(rgba=rgba, hash=vh, count=vc, log=vlog)
