@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native octree render path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): one headless 1920x1080 frame of the
+synthetic depth-10 SH-deg-2 N3Tree (mega-nerf-viewer_b200/synth.py), camera
+orbiting 16 poses.  A "step" is one frame = one launch of the traversal kernel
+over all rays of the frame.  Metric: Mrays/s (rays of the frame / device time).
+
+  value     kernel-only throughput, tree resident in HBM, CUDA-event timed on
+            the launching stream, L2 flushed between timed frames
+  e2e       the same frames through the C-ABI host call
+            (mnv_render_frame_host[_bands]): camera + options in from the host,
+            RGBA8 frame read back into pinned host memory every step
+  roofline  algorithmic bytes (6 B per empty leaf visit, 60 B per shaded visit,
+            + 4 B / 28 B per pixel) over the measured kernel
+            time, against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (port of the reference's device code) on the
+            host cores, same frame
+
+N > 1: the frame is split into interleaved 8-row bands, one process per GPU,
+tree replicated, no data-path collective (strong scaling of one frame).
+
+--impl reference: the reference's own CUDA kernel rebuilt for sm_100
+(oracle/_ref/libref_render.so, unmodified sources) on the same workload; falls
+back to the CPU oracle when that library is absent.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, DEPTH, FMT, N_POSES = 1920, 1080, 10, "SH9", 16
+BAND_ROWS = 8
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--depth", type=int, default=DEPTH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the run (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
+                 "-i", str(gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        self.marks = []
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        allsm = []
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk = float(f[0]); mx = float(f[1])
+            except ValueError:
+                continue
+            allsm.append(clk)
+            if t0 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        use = sm if sm else allsm[-3:]
+        return {"sm_mhz": float(np.median(use)) if use else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stats: dict, pixels: int, trackers: bool) -> int:
+    """6 B per empty visit (cell word + sigma), 60 B per shaded
+    visit (SH9), + 4 B RGBA8 per pixel (+ 24 B when candidate tracking is on)."""
+    empty = stats["visits"] - stats["shaded_visits"]
+    return int(empty * 6 + stats["shaded_visits"] * 60 + pixels * (4 + (24 if trackers else 0)))
+
+
+def ncu_traffic():
+    """dram bytes per launch from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traversal_ncu_summary.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
+    """CPU oracle (port) on all host cores; bounded sample: whole frames of the
+    orbit until ~seconds_budget elapsed (at least one)."""
+    opt = O.default_options(**opt_kw)
+    cores = O.lib().oracle_num_threads()
+    t_all, rays, n = 0.0, 0, 0
+    O.render_voxels(tree, cams[0], opt, stats=False, row_step=8)  # warm-up (1/8 frame)
+    while n < len(cams) and (n == 0 or t_all < seconds_budget):
+        t0 = time.perf_counter()
+        O.render_voxels(tree, cams[n], opt, stats=False)
+        t_all += time.perf_counter() - t0
+        rays += cams[n]["width"] * cams[n]["height"]
+        n += 1
+    return {"value": rays / t_all / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": "port",
+            "sample": f"{n} full {cams[0]['width']}x{cams[0]['height']} frame(s) of the orbit, {t_all:.1f} s"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    W, H = args.width, args.height
+    P = W * H
+
+    if args.impl == "reference" and rank != 0:
+        return 0  # the reference arm is single-GPU; other ranks exit without work
+
+    import torch
+    import mega_nerf_viewer_b200 as mnv
+
+    have_gpu = torch.cuda.is_available()
+    if have_gpu:
+        torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1 and args.impl == "native":
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl" if have_gpu else "gloo")
+
+    tree = mnv.synth.make_tree(depth=args.depth, data_format=FMT)
+    cams = [mnv.synth.default_camera(W, H, pose=i, n_poses=N_POSES) for i in range(N_POSES)]
+    opt_kw = dict(background_brightness=0.0, basis_minmax=[0, 8])  # CLI bg default; set() basis range
+    config = {"workload": f"headless {W}x{H} frame, synthetic depth-{args.depth} {FMT} N3Tree "
+                          f"({tree.capacity} nodes, {tree.nbytes() / 1e9:.2f} GB AoS), {N_POSES}-pose orbit",
+              "resolution": [W, H], "tree_nodes": tree.capacity, "data_format": FMT,
+              "options": "RenderOptions defaults, background_brightness=0",
+              "l2_policy": "L2 flushed (256 MiB write) between timed frames; camera pose changes every frame"}
+
+    if args.impl == "reference":
+        return run_reference(args, tree, cams, opt_kw, config, have_gpu)
+    if not have_gpu:
+        raise SystemExit("bench.py: no CUDA device — the native path has no CPU fallback")
+
+    dev = torch.device("cuda", local_rank)
+    dt = mnv.DeviceTree(tree, device=local_rank)
+    opt = mnv.default_options(**opt_kw)
+    out = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+    ts = torch.empty((P, 3), device=dev)
+    tp = torch.empty((P, 3), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    tile = (((W + 15) // 16) * 16, BAND_ROWS, world, rank)
+
+    def launch(i, trackers=True):
+        cam = cams[i % N_POSES]
+        if world == 1:
+            dt.render(cam, opt, out=out, to_split=ts if trackers else None, to_sample=tp if trackers else None)
+        else:
+            dt.render_tiles(cam, opt, out, *tile, to_split=ts if trackers else None,
+                            to_sample=tp if trackers else None)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        evs = []
+        for i in range(steps):
+            flush.fill_(i & 0xff)  # evict L2 (untimed)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(i)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = np.array([a.elapsed_time(b) for a, b in evs], np.float64)
+        if dist is not None:
+            t = torch.tensor(ms, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # per-step max over ranks
+            ms = t.cpu().numpy()
+        return ms
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_start = time.time()
+    ms = timed(lambda i: launch(i, True), args.steps, args.warmup)
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    ms_nt = timed(lambda i: launch(i, False), max(args.steps // 4, 3), 3)
+
+    # e2e: the host-buffer C-ABI call, wall clock around K synchronous frames
+    def e2e_frame(i):
+        cam = cams[i % N_POSES]
+        if world == 1:
+            dt.render_frame_host(cam, opt, host)
+        else:
+            dt.render_frame_host(cam, opt, host, bands=(BAND_ROWS, world, rank))
+
+    for i in range(max(args.warmup, 3)):
+        e2e_frame(i)
+    barrier()
+    e2e_ms = []
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_frame(i)
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    barrier()
+    e2e_ms = np.array(e2e_ms)
+    if dist is not None:
+        t = torch.tensor(e2e_ms, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = t.cpu().numpy()
+
+    if rank != 0:
+        dist.destroy_process_group()
+        return 0
+
+    # algorithmic bytes: visit statistics of the timed frames (whole frame, all ranks' tiles)
+    alg = []
+    for i in range(min(args.steps, N_POSES)):
+        _, st = dt.render_frame_host(cams[i % N_POSES], opt, stats=True)
+        alg.append((algorithmic_bytes(st, P, True), st))
+    alg_bytes = float(np.mean([a for a, _ in alg]))
+    visits = float(np.mean([s["visits"] for _, s in alg]))
+    shaded = float(np.mean([s["shaded_visits"] for _, s in alg]))
+    ms_step = float(ms.mean())
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / world / (ms_step * 1e-3) / 1e9  # per-GPU kernel
+    line = {
+        "metric": "Mrays/s", "value": P / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (fp16 storage, fp64 ray setup)", "data": "synthetic", "config": config,
+        "fps": 1e3 / ms_step,
+        "value_no_trackers": P / (float(ms_nt.mean()) * 1e-3) / 1e6,
+        "e2e": {"value": P / (float(e2e_ms.mean()) * 1e-3) / 1e6, "unit": "Mrays/s",
+                "ms_per_step": float(e2e_ms.mean()),
+                "h2d_bytes_per_step": 72 + 104,  # mnv_camera + mnv_render_options (kernel params)
+                "d2h_bytes_per_step": P * 4 // world, "api": "mnv_render_frame_host (C-ABI)"},
+        "gpu_launches": args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "kernel": "mnv::render_voxels_kernel<9,track>",
+                     "algorithmic_bytes_per_launch": alg_bytes / world,
+                     "leaf_visits_per_frame": visits, "shaded_visits_per_frame": shaded,
+                     "gvisits_per_s": visits / (ms_step * 1e-3) / 1e9},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle_py as O
+        line["cpu_baseline"] = cpu_baseline(tree, cams, O, opt_kw)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_reference(args, tree, cams, opt_kw, config, have_gpu):
+    """The reference arm: its own CUDA kernel (unmodified sources rebuilt for
+    sm_100, oracle/_ref) when available, else the CPU port of its device code."""
+    from oracle import oracle_py as O
+    W, H = args.width, args.height
+    P = W * H
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_baseline(tree, cams, O, opt_kw, seconds_budget=10.0)
+    if have_gpu and O.ref_available():
+        import torch
+        npz = "/tmp/mnv_bench_tree.npz"
+        tree.save_npz(npz)
+        ref = O.RefRenderer(npz)
+        opt = O.default_options(**opt_kw)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        sampler = ClockSampler(0)
+        t_start = time.time()
+        for i in range(args.warmup):
+            ref.render(cams[i % N_POSES], opt, iters=1, trackers=False)
+        ms = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            ms.append(float(ref.render(cams[i % N_POSES], opt, iters=1, trackers=False)["ms"][0]))
+        t_end = time.time()
+        clocks = sampler.stop(t_start, t_end)
+        host = np.empty((H, W, 4), np.uint8)
+        for i in range(3):
+            ref.render_frame_host(cams[i % N_POSES], opt, host)
+        e2e = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ref.render_frame_host(cams[i % N_POSES], opt, host)
+            e2e.append((time.perf_counter() - t0) * 1e3)
+        ms_step = float(np.mean(ms))
+        line = {"impl": "reference", "reference_kind": "reference CUDA kernel (render_voxels_kernel, "
+                "unmodified sources rebuilt for sm_100) on the same GPU",
+                "metric": "Mrays/s", "value": P / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
+                "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (fp16 storage, fp64 ray setup)", "data": "synthetic", "config": config,
+                "fps": 1e3 / ms_step,
+                "e2e": {"value": P / (float(np.mean(e2e)) * 1e-3) / 1e6, "unit": "Mrays/s",
+                        "ms_per_step": float(np.mean(e2e)), "h2d_bytes_per_step": 48,
+                        "d2h_bytes_per_step": P * 4,
+                        "api": "Camera::_update + render_voxels + cudaMemcpy2DFromArray"},
+                "gpu_launches": args.steps, "clocks": clocks}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+        return 0
+    if cpu is None:
+        cpu = cpu_baseline(tree, cams, O, opt_kw, seconds_budget=10.0)
+    line = {"impl": "reference", "reference_kind": "CPU port of the reference's device code "
+            "(the reference CUDA kernel needs a GPU and oracle/_ref)",
+            "metric": "Mrays/s", "value": cpu["value"], "unit": "Mrays/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": P / cpu["value"] / 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config, "cpu_baseline": cpu,
+            "e2e": {"value": cpu["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

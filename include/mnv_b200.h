@@ -155,9 +155,25 @@ int mnv_render_voxels_logged(mnv_tree *tree, const mnv_camera *cam, const mnv_re
 
 /* The call a host application makes per frame with HOST buffers: uploads the
  * camera (48 B, src/camera.cpp:113-123), renders offscreen, reads the RGBA8
- * frame back into rgba_host ([height][width][4]); synchronous on return. */
+ * frame back into rgba_host ([height][width][4]); synchronous on return.
+ * When opt->use_splitting is set the split / re-sample candidates are produced
+ * too (into tree-owned device buffers, see mnv_tree_trackers). */
 int mnv_render_frame_host(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
                           uint8_t *rgba_host, mnv_frame_stats *stats /* may be NULL */);
+
+/* Device pointers of the tree-owned candidate buffers filled by the host frame
+ * calls when opt->use_splitting is set: f32 [P][3] each (valid until the next
+ * frame call with a different size). */
+int mnv_tree_trackers(mnv_tree *tree, float **to_split_dev, float **to_sample_dev);
+
+/* Multi-GPU form of mnv_render_frame_host (image tiles with the
+ * tree replicated): the frame is cut into bands of band_rows full-width pixel
+ * rows (band_rows a multiple of 8); this call renders the bands b with
+ * (b % band_mod) == band_rem and copies exactly those bands to their place in
+ * the full-size host frame rgba_host (one strided D2H copy). No collective. */
+int mnv_render_frame_host_bands(mnv_tree *tree, const mnv_camera *cam,
+                                const mnv_render_options *opt, uint8_t *rgba_host, int band_rows,
+                                int band_mod, int band_rem, mnv_frame_stats *stats);
 
 #ifdef __cplusplus
 }

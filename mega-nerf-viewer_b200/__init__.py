@@ -129,6 +129,9 @@ def lib() -> C.CDLL:
                                            vp, vp, i32, vp]
     L.mnv_render_frame_host.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp,
                                         C.POINTER(FrameStats)]
+    L.mnv_render_frame_host_bands.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp,
+                                              i32, i32, i32, C.POINTER(FrameStats)]
+    L.mnv_tree_trackers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     _lib = L
     return L
 
@@ -297,15 +300,22 @@ class DeviceTree:
                     count=vc.cpu().numpy(), shaded=vs.cpu().numpy(),
                     log=None if vlog is None else vlog.cpu().numpy())
 
-    def render_frame_host(self, cam, opt, rgba_host: np.ndarray | None = None, stats: bool = False):
-        """The per-frame call with HOST buffers (camera in, RGBA8 frame out)."""
+    def render_frame_host(self, cam, opt, rgba_host=None, stats: bool = False, bands=None):
+        """The per-frame call with HOST buffers (camera in, RGBA8 frame out).
+        rgba_host: numpy array or a (pinned) torch CPU tensor [H, W, 4] uint8.
+        bands=(band_rows, mod, rem): multi-GPU band partition of the frame."""
         cam = make_camera(cam)
         if rgba_host is None:
             rgba_host = np.empty((cam.height, cam.width, 4), np.uint8)
+        ptr = rgba_host.ctypes.data if isinstance(rgba_host, np.ndarray) else rgba_host.data_ptr()
         st = FrameStats() if stats else None
-        _check(lib().mnv_render_frame_host(self._h, C.byref(cam), C.byref(opt),
-                                           C.c_void_p(rgba_host.ctypes.data),
-                                           C.byref(st) if stats else None))
+        if bands is None:
+            _check(lib().mnv_render_frame_host(self._h, C.byref(cam), C.byref(opt), C.c_void_p(ptr),
+                                               C.byref(st) if stats else None))
+        else:
+            _check(lib().mnv_render_frame_host_bands(self._h, C.byref(cam), C.byref(opt),
+                                                     C.c_void_p(ptr), bands[0], bands[1], bands[2],
+                                                     C.byref(st) if stats else None))
         if stats:
             return rgba_host, dict(rays=st.rays, visits=st.visits, shaded_visits=st.shaded_visits,
                                    rays_hit=st.rays_hit)

@@ -162,6 +162,8 @@ int mnv_tree_destroy(mnv_tree *h) {
     cudaFree(t.parent);
     cudaFree(t.sample_counts);
     cudaFree(t.frame_dev);
+    cudaFree(t.split_dev);
+    cudaFree(t.sample_dev);
     cudaFree(t.stats_dev);
     if (t.stream) cudaStreamDestroy(t.stream);
     delete h;
@@ -262,8 +264,9 @@ int mnv_render_voxels_logged(mnv_tree *h, const mnv_camera *cam, const mnv_rende
     return launch_render_voxels(h->t, *cam, *opt, tg, static_cast<cudaStream_t>(stream));
 }
 
-int mnv_render_frame_host(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
-                          uint8_t *rgba_host, mnv_frame_stats *stats) {
+static int frame_host_impl(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                           uint8_t *rgba_host, int band_rows, int band_mod, int band_rem,
+                           mnv_frame_stats *stats) {
     if (!h || !cam || !opt || !rgba_host) return MNV_ERR_INVALID;
     DeviceTree &t = h->t;
     MNV_CUDA(cudaSetDevice(t.device));
@@ -271,13 +274,34 @@ int mnv_render_frame_host(mnv_tree *h, const mnv_camera *cam, const mnv_render_o
     if (bytes == 0) return MNV_ERR_INVALID;
     if (t.frame_bytes < bytes) {
         cudaFree(t.frame_dev);
+        cudaFree(t.split_dev);
+        cudaFree(t.sample_dev);
         t.frame_dev = nullptr;
+        t.split_dev = t.sample_dev = nullptr;
         t.frame_bytes = 0;
         MNV_CUDA(cudaMalloc(&t.frame_dev, bytes));
         t.frame_bytes = bytes;
     }
     RenderTargets tg;
     tg.image_linear = t.frame_dev;
+    if (opt->use_splitting) {
+        if (!t.split_dev) {
+            MNV_CUDA(cudaMalloc(&t.split_dev, bytes * 3));
+            MNV_CUDA(cudaMalloc(&t.sample_dev, bytes * 3));
+        }
+        tg.to_split = t.split_dev;
+        tg.to_sample = t.sample_dev;
+    }
+    if (band_mod > 1) {
+        if (band_rows < 8 || band_rows % 8 || band_rem < 0 || band_rem >= band_mod) {
+            set_error("bad band partition rows=%d %d/%d", band_rows, band_rem, band_mod);
+            return MNV_ERR_INVALID;
+        }
+        tg.tile_w = ((cam->width + 15) / 16) * 16;
+        tg.tile_h = band_rows;
+        tg.tile_mod = band_mod;
+        tg.tile_rem = band_rem;
+    }
     if (stats) {
         if (!t.stats_dev) MNV_CUDA(cudaMalloc(&t.stats_dev, 4 * sizeof(unsigned long long)));
         MNV_CUDA(cudaMemsetAsync(t.stats_dev, 0, 4 * sizeof(unsigned long long), t.stream));
@@ -285,7 +309,27 @@ int mnv_render_frame_host(mnv_tree *h, const mnv_camera *cam, const mnv_render_o
     }
     int rc = launch_render_voxels(t, *cam, *opt, tg, t.stream);
     if (rc != MNV_OK) return rc;
-    MNV_CUDA(cudaMemcpyAsync(rgba_host, t.frame_dev, bytes, cudaMemcpyDeviceToHost, t.stream));
+    if (band_mod > 1) {
+        // bands owned by this rank: contiguous band_bytes each, band_mod*band_bytes apart
+        const size_t row_bytes = (size_t) cam->width * 4;
+        const size_t band_bytes = row_bytes * band_rows;
+        const int n_bands = (cam->height + band_rows - 1) / band_rows;
+        const int full = cam->height / band_rows;  // complete bands
+        int mine_full = 0;
+        for (int b = band_rem; b < full; b += band_mod) ++mine_full;
+        const size_t off = (size_t) band_rem * band_bytes;
+        if (mine_full > 0)
+            MNV_CUDA(cudaMemcpy2DAsync(rgba_host + off, band_bytes * band_mod, t.frame_dev + off,
+                                       band_bytes * band_mod, band_bytes, mine_full,
+                                       cudaMemcpyDeviceToHost, t.stream));
+        if (n_bands > full && (n_bands - 1) % band_mod == band_rem) {  // ragged last band
+            const size_t o2 = (size_t) full * band_bytes;
+            MNV_CUDA(cudaMemcpyAsync(rgba_host + o2, t.frame_dev + o2, bytes - o2,
+                                     cudaMemcpyDeviceToHost, t.stream));
+        }
+    } else {
+        MNV_CUDA(cudaMemcpyAsync(rgba_host, t.frame_dev, bytes, cudaMemcpyDeviceToHost, t.stream));
+    }
     if (stats) {
         unsigned long long hs[4];
         MNV_CUDA(cudaMemcpyAsync(hs, t.stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, t.stream));
@@ -297,6 +341,25 @@ int mnv_render_frame_host(mnv_tree *h, const mnv_camera *cam, const mnv_render_o
     } else {
         MNV_CUDA(cudaStreamSynchronize(t.stream));
     }
+    return MNV_OK;
+}
+
+int mnv_render_frame_host(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                          uint8_t *rgba_host, mnv_frame_stats *stats) {
+    return frame_host_impl(h, cam, opt, rgba_host, 0, 1, 0, stats);
+}
+
+int mnv_render_frame_host_bands(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                                uint8_t *rgba_host, int band_rows, int band_mod, int band_rem,
+                                mnv_frame_stats *stats) {
+    if (band_mod < 1) return MNV_ERR_INVALID;
+    return frame_host_impl(h, cam, opt, rgba_host, band_rows, band_mod, band_rem, stats);
+}
+
+int mnv_tree_trackers(mnv_tree *h, float **to_split_dev, float **to_sample_dev) {
+    if (!h) return MNV_ERR_INVALID;
+    if (to_split_dev) *to_split_dev = h->t.split_dev;
+    if (to_sample_dev) *to_sample_dev = h->t.sample_dev;
     return MNV_OK;
 }
 

@@ -60,6 +60,7 @@ struct DeviceTree {
     int device = 0;
     // scratch for mnv_render_frame_host
     uint8_t *frame_dev = nullptr;
+    float *split_dev = nullptr, *sample_dev = nullptr;
     size_t frame_bytes = 0;
     unsigned long long *stats_dev = nullptr;
     cudaStream_t stream = nullptr;

@@ -330,6 +330,11 @@ static void trace_ray(const mnv_tree_desc *tree, int32_t *visited, float *dir, c
 
     if (tmax < 0 || tmin > tmax) {
         if (opt->render_depth) out[3] = 1.f;
+        if (sink) { /* ray misses the box: empty visit sequence */
+            if (sink->hash) sink->hash[ray] = 0xcbf29ce484222325ULL;
+            if (sink->count) sink->count[ray] = 0;
+            if (sink->shaded) sink->shaded[ray] = 0;
+        }
         return;
     }
 
