@@ -22,7 +22,7 @@ from . import synth  # noqa: F401  (synthetic N3Tree generator)
 from .synth import HostTree
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmnv_b200.so")
+LIB_PATH = os.environ.get("MNV_B200_LIB") or os.path.join(_HERE, "libmnv_b200.so")  # env override: dev A/B builds
 
 MNV_OK = 0
 ERR_NAMES = {1: "INVALID", 2: "NO_DEVICE", 3: "CUDA", 4: "OOM", 5: "IO", 6: "FORMAT", 7: "FULL"}

@@ -2,6 +2,7 @@
 #include <cstring>
 #include <map>
 #include <new>
+#include <vector>
 
 #include "mnv_internal.cuh"
 
@@ -49,6 +50,36 @@ int surface_for(mnv_tree *tree, void *arr, cudaSurfaceObject_t *out) {
     tree->surfaces[arr] = s;
     *out = s;
     return MNV_OK;
+}
+
+// Depth of the deepest leaf (root's children are depth 1), -1 on malformed links.
+int host_max_leaf_depth(const int32_t *child, int64_t cap) {
+    std::vector<int8_t> depth((size_t) cap, -1);  // level of each node, root = 0
+    depth[0] = 0;
+    int maxd = 1;
+    bool pending = true;
+    for (int pass = 0; pass < 64 && pending; ++pass) {  // one pass when children follow parents
+        pending = false;
+        for (int64_t n = 0; n < cap; ++n) {
+            if (depth[n] < 0) {
+                pending = true;
+                continue;
+            }
+            for (int c = 0; c < 8; ++c) {
+                const int32_t rel = child[n * 8 + c];
+                if (rel == 0) continue;
+                const int64_t m = n + rel;
+                if (m <= 0 || m >= cap) return -1;
+                if (depth[m] < 0) {
+                    if (depth[n] >= 100) return -1;
+                    depth[m] = (int8_t) (depth[n] + 1);
+                    if (m < n) pending = true;
+                    if (depth[m] + 1 > maxd) maxd = depth[m] + 1;
+                }
+            }
+        }
+    }
+    return maxd;
 }
 
 }  // namespace
@@ -137,6 +168,17 @@ int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *d, int64_t max_capacity
     for (int i = 0; i < 3; ++i) {
         t.scale[i] = d->scale[i];
         t.offset[i] = d->offset[i];
+    }
+    t.max_leaf_depth = host_max_leaf_depth(d->child, d->capacity);
+    if (t.max_leaf_depth < 0) {
+        delete h;
+        set_error("child links do not form a tree rooted at node 0");
+        return MNV_ERR_FORMAT;
+    }
+    if (t.max_leaf_depth > 23) {
+        delete h;
+        set_error("tree depth %d exceeds the supported maximum of 23", t.max_leaf_depth);
+        return MNV_ERR_FORMAT;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {

@@ -58,6 +58,7 @@ struct DeviceTree {
     float scale[3] = {1, 1, 1};
     float offset[3] = {0, 0, 0};
     int device = 0;
+    int max_leaf_depth = 1;  // deepest leaf (reference counting: root's children are depth 1)
     // scratch for mnv_render_frame_host
     uint8_t *frame_dev = nullptr;
     float *split_dev = nullptr, *sample_dev = nullptr;

@@ -9,10 +9,11 @@
 //   * query: the reference restarts at the root for every step of every ray
 //     (depth dependent loads).  The descent x*=2; f=floor(x); x-=f is exact in
 //     fp32, so the leaf containing pos is exactly the integer cell
-//     floor(pos*2^d).  Each ray keeps q = floor(pos*2^24) per axis and the node
-//     path of its previous leaf in shared memory; a step re-descends only below
-//     the deepest common ancestor of the old and new cell (clz of the XOR),
-//     ~2 dependent loads instead of ~10, usually L1 hits.
+//     floor(pos*2^d).  Each ray keeps q = floor(pos*2^23) per axis (one
+//     FFMA.RM against the magic constant 2^23, no F2I) and the node path of its
+//     previous leaf in shared memory; a step re-descends only below the deepest
+//     common ancestor of the old and new cell (clz of the XOR), ~2 dependent
+//     loads instead of ~10, usually L1 hits.
 //   * one 4-byte "cell" word per slot holds child link OR (leaf, sigma, sample
 //     count): an empty leaf visit costs exactly one load.
 //   * shaded leaves fetch one aligned 64-byte record with 4 x LDG.128.
@@ -22,23 +23,31 @@
 //     ray; camera and options travel as kernel parameters (no 48-byte upload).
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdlib>
+
 #include "mnv_internal.cuh"
 #include "mnv_math.cuh"
 
 namespace mnv {
 namespace {
 
-constexpr int kThreads = 128;    // 4 warps: block tile = 16 x 8 pixels
-constexpr int kTileW = 16, kTileH = 8;
-constexpr int kMaxLevel = 23;    // q carries 24 bits per axis
+constexpr int kThreads = 128;    // 4 warps per CTA, each warp owns 8x4-pixel tiles
+#ifndef MNV_MIN_BLOCKS
+#define MNV_MIN_BLOCKS 10  // resident CTAs per SM the register allocation targets
+#endif
+constexpr int kTileW = 16, kTileH = 8;  // granularity of the multi-GPU tile partition
+constexpr int kMaxLevel = 22;    // q carries 23 bits per axis: leaf depth <= 23
 
 struct RenderParams {
     TreeView tree;
     mnv_camera cam;
     mnv_render_options opt;
     RenderTargets tg;
-    int tiles_x, tiles_y;
-    int mtiles_x;  // macro tiles per row (multi-GPU partition)
+    int mtiles_x;   // partition tiles per row (multi-GPU partition)
+    int tiles_x;    // 16x8-pixel CTA tiles per row
+    int max_level;  // deepest level a descent may reach (tree max leaf depth - 1, <= 22)
+    int path_levels;  // rows of the shared-memory node path (= max_level + 1)
 };
 
 template <int R>
@@ -87,22 +96,10 @@ __device__ __forceinline__ float sh_channel(const float (&B)[TERMS], const uint3
 // TRACK: produce split / re-sample candidates.  LOGV: visit hash/count/log/stats.
 // VISIT: mark visited nodes (track_visit).
 template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
-__global__ void __launch_bounds__(kThreads)
-render_voxels_kernel(const RenderParams p) {
-    __shared__ int32_t s_path[kMaxLevel + 1][kThreads];
-
-    // ---- pixel mapping: block tile 16x8, warp tile 8x4 ---------------------
-    const int bt = blockIdx.x;
-    const int bty = bt / p.tiles_x, btx = bt - bty * p.tiles_x;
-    if (p.tg.tile_mod > 1) {
-        const int mt = ((bty * kTileH) / p.tg.tile_h) * p.mtiles_x + (btx * kTileW) / p.tg.tile_w;
-        if (mt % p.tg.tile_mod != p.tg.tile_rem) return;
-    }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = btx * kTileW + (warp & 1) * 8 + (lane & 7);
-    const int y = bty * kTileH + (warp >> 1) * 4 + (lane >> 3);
-    const int W = p.cam.width, H = p.cam.height;
-    if (x >= W || y >= H) return;
+__device__ __forceinline__ void render_pixel(const RenderParams &p, const int x, const int y,
+                                             int32_t *__restrict__ s_path,
+                                             float *__restrict__ s_basis) {
+    const int W = p.cam.width;
     const int idx = y * W + x;
     const mnv_render_options &opt = p.opt;
 
@@ -179,56 +176,65 @@ render_voxels_kernel(const RenderParams p) {
         if (opt.render_depth) out3 = 1.f;
     } else {
         hit = true;
-        float B[TERMS > 0 ? TERMS : 1];
         if (TERMS > 0) {
+            // SH basis of the view direction: needed only by shaded leaves, so it is parked
+            // in shared memory instead of occupying 9..25 registers across the whole march
+            float B[TERMS > 0 ? TERMS : 1];
             ref_sh_basis<(TERMS > 0 ? TERMS : 1)>(v0, v1, v2, B);
 #pragma unroll
             for (int k = 0; k < TERMS; ++k)
-                if (k < opt.basis_minmax[0] || k > opt.basis_minmax[1]) B[k] = 0.f;
+                s_basis[k * kThreads] = (k < opt.basis_minmax[0] || k > opt.basis_minmax[1]) ? 0.f : B[k];
         }
         constexpr int REC_W = TERMS > 0 ? ((3 * TERMS + 1 + 7) / 8) * 4 : 4;  // u32 words / record
 
         float T = 1.f;
         float t = tmin;
         float max_weight = -1.f, max_sample_weight = -1.f;
-        uint32_t pqx = 0, pqy = 0, pqz = 0;
+        // raw bits of (floor(pos * 2^23) + 2^23) as float: 0x4B000000 | q, q = 23-bit cell coords
+        uint32_t pqx = 0x4B000000u, pqy = 0x4B000000u, pqz = 0x4B000000u;
         int pdepth = 1;  // previous leaf depth: path valid for levels < pdepth
         const float clamp_hi = f_from_bits(0x3F7FFFEFu);  // 1.f - 1e-6f
+        const uint32_t *__restrict__ cells = p.tree.cell;
 
         while (t < tmax) {
-            // pos = cen + t*dir  (FFMA), clamp to [0, 1-1e-6]  (rt_core.cuh:221-223,125-127)
-            const float px = fmaxf(fminf(__fmaf_rn(t, d0, c0), clamp_hi), 0.f);
-            const float py = fmaxf(fminf(__fmaf_rn(t, d1, c1), clamp_hi), 0.f);
-            const float pz = fmaxf(fminf(__fmaf_rn(t, d2, c2), clamp_hi), 0.f);
-            // exact integer cell coordinates at level 24
-            const uint32_t qx = __float2uint_rd(__fmul_rn(px, 16777216.f));
-            const uint32_t qy = __float2uint_rd(__fmul_rn(py, 16777216.f));
-            const uint32_t qz = __float2uint_rd(__fmul_rn(pz, 16777216.f));
-            const uint32_t diff = (qx ^ pqx) | (qy ^ pqy) | (qz ^ pqz);
+            // pos = cen + t*dir (FFMA), clamp to [0, 1-1e-6] (rt_core.cuh:221-223,125-127);
+            // .SAT gives the clamp to [0,1] for free, min() finishes it.
+            const float px = fminf(__saturatef(__fmaf_rn(t, d0, c0)), clamp_hi);
+            const float py = fminf(__saturatef(__fmaf_rn(t, d1, c1)), clamp_hi);
+            const float pz = fminf(__saturatef(__fmaf_rn(t, d2, c2)), clamp_hi);
+            // exact integer cell coordinates at level 23: floor(p * 2^23) sits in the
+            // mantissa of fma_rd(p, 2^23, 2^23)
+            const uint32_t qx = __float_as_uint(__fmaf_rd(px, 8388608.f, 8388608.f));
+            const uint32_t qy = __float_as_uint(__fmaf_rd(py, 8388608.f, 8388608.f));
+            const uint32_t qz = __float_as_uint(__fmaf_rd(pz, 8388608.f, 8388608.f));
+            const uint32_t diff = (qx ^ pqx) | (qy ^ pqy) | (qz ^ pqz);  // exponent bits cancel
             pqx = qx;
             pqy = qy;
             pqz = qz;
-            // number of leading (from bit 23) bits shared with the previous cell
-            int lvl = min(__clz((int) diff) - 8, pdepth - 1);
-            int32_t node = lvl > 0 ? s_path[lvl][threadIdx.x] : 0;
-            uint32_t cw;
-            int cidx;
+            // number of leading (from bit 22) bits shared with the previous cell
+            int lvl = min(__clz((int) diff) - 9, pdepth - 1);
+            uint32_t node = lvl > 0 ? (uint32_t) s_path[lvl * kThreads] : 0u;
+            // level-lvl child bit of each axis moved to bit 31
+            uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
+            uint32_t cw, cidx;
             for (;;) {
                 if (VISIT) {
                     if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
                 }
-                const int bit = 23 - lvl;
-                cidx = (((qx >> bit) & 1u) << 2) | (((qy >> bit) & 1u) << 1) | ((qz >> bit) & 1u);
-                cw = __ldg(p.tree.cell + ((int64_t) node * 8 + cidx));
-                if ((cw & kLeafBit) || lvl >= kMaxLevel) break;
-                node = (int32_t) cw;
+                cidx = ((sx >> 31) << 2) | ((sy >> 31) << 1) | (sz >> 31);
+                cw = __ldg(cells + (node * 8u + cidx));
+                if ((int32_t) cw < 0 || lvl >= p.max_level) break;
+                node = cw;
                 ++lvl;
-                s_path[lvl][threadIdx.x] = node;
+                sx <<= 1;
+                sy <<= 1;
+                sz <<= 1;
+                s_path[lvl * kThreads] = (int32_t) node;
             }
             const int depth = lvl + 1;
             pdepth = depth;
             if (LOGV) {
-                const long long packed = (long long) node * 8 + cidx;
+                const long long packed = (long long) (node * 8u + cidx);
                 vhash = (vhash ^ (unsigned long long) packed) * 0x100000001b3ULL;
                 if (p.tg.visit_log && nvis < p.tg.log_cap)
                     p.tg.visit_log[(size_t) idx * p.tg.log_cap + nvis] = (int32_t) packed;
@@ -238,10 +244,13 @@ render_voxels_kernel(const RenderParams p) {
             // position inside the leaf, in leaf units: frac(pos * 2^depth) (exact)
             const float cube = __uint_as_float((uint32_t) (127 + depth) << 23);
             const float icube = __uint_as_float((uint32_t) (127 - depth) << 23);
-            const float sx = __fmul_rn(px, cube), sy = __fmul_rn(py, cube), sz = __fmul_rn(pz, cube);
-            const float fx = __fadd_rn(sx, -floorf(sx));
-            const float fy = __fadd_rn(sy, -floorf(sy));
-            const float fz = __fadd_rn(sz, -floorf(sz));
+            // floor(p*2^depth) via the 2^23 magic constant (exact), then an exact FFMA
+            const float flx = __fadd_rn(__fmaf_rd(px, cube, 8388608.f), -8388608.f);
+            const float fly = __fadd_rn(__fmaf_rd(py, cube, 8388608.f), -8388608.f);
+            const float flz = __fadd_rn(__fmaf_rd(pz, cube, 8388608.f), -8388608.f);
+            const float fx = __fmaf_rn(px, cube, -flx);
+            const float fy = __fmaf_rn(py, cube, -fly);
+            const float fz = __fmaf_rn(pz, cube, -flz);
             // _dda_unit, rt_core.cuh:88-100: FMUL then FADD (not fused in the reference build)
             float tm;
             {
@@ -255,7 +264,7 @@ render_voxels_kernel(const RenderParams p) {
             const float sigma = __half2float(__ushort_as_half((unsigned short) (cw & 0xffffu)));
             const int scount = (int) ((cw >> 16) & 0x7fffu);
 
-            if ((cw & kLeafBit) && sigma > opt.sigma_thresh) {
+            if ((int32_t) cw < 0 && sigma > opt.sigma_thresh) {
                 if (LOGV) ++nshaded;
                 const float att =
                         ref_expf(__fmul_rn(__fmul_rn(delta_scale, -delta_t), sigma));
@@ -277,7 +286,7 @@ render_voxels_kernel(const RenderParams p) {
                 if (opt.render_depth) {
                     out0 = __fmaf_rn(t, weight, out0);
                 } else {
-                    const uint4 *rec = p.tree.payload + ((int64_t) node * 8 + cidx) * (REC_W / 4);
+                    const uint4 *rec = p.tree.payload + (size_t) (node * 8u + cidx) * (REC_W / 4);
                     uint32_t w[REC_W];
 #pragma unroll
                     for (int j = 0; j < REC_W / 4; ++j) {
@@ -288,6 +297,9 @@ render_voxels_kernel(const RenderParams p) {
                         w[4 * j + 3] = v.w;
                     }
                     if (TERMS > 0) {
+                        float B[TERMS > 0 ? TERMS : 1];
+#pragma unroll
+                        for (int k = 0; k < TERMS; ++k) B[k] = s_basis[k * kThreads];
                         out0 = __fadd_rn(out0, ref_weighted_sigmoid(
                                 weight, sh_channel<(TERMS > 0 ? TERMS : 1), REC_W>(B, w, 0)));
                         out1 = __fadd_rn(out1, ref_weighted_sigmoid(
@@ -379,6 +391,36 @@ render_voxels_kernel(const RenderParams p) {
     }
 }
 
+// ---- ray-coherent tiles ----------------------------------------------------------
+// One CTA = 4 warps = a 16x8-pixel tile; each warp owns an 8x4-pixel sub-tile, so the
+// 32 rays of a warp stay in neighbouring leaves (the reference maps a warp to 32
+// pixels of one image row).  CTAs are dispatched in row-major tile order.  A
+// persistent variant (per-SM Morton segments + work stealing) was measured slower on
+// B200 ("rejected"): the march is bound by dependent-load latency, and the
+// plain grid keeps more independent warps in flight.
+//
+// TERMS: 0 = RGBA, else SH basis dimension (1,4,9,16,25).
+// TRACK: produce split / re-sample candidates.  LOGV: visit hash/count/log/stats.
+// VISIT: mark visited nodes (track_visit).
+template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
+__global__ void __launch_bounds__(kThreads, MNV_MIN_BLOCKS)
+render_voxels_kernel(const RenderParams p) {
+    extern __shared__ int32_t s_dyn[];  // [path_levels][kThreads] node path, then [TERMS][kThreads] basis
+    const int bt = blockIdx.x;
+    const int bty = bt / p.tiles_x, btx = bt - bty * p.tiles_x;
+    if (p.tg.tile_mod > 1) {
+        const int mt = ((bty * kTileH) / p.tg.tile_h) * p.mtiles_x + (btx * kTileW) / p.tg.tile_w;
+        if (mt % p.tg.tile_mod != p.tg.tile_rem) return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int x = btx * kTileW + (warp & 1) * 8 + (lane & 7);
+    const int y = bty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    if (x >= p.cam.width || y >= p.cam.height) return;
+    render_pixel<TERMS, TRACK, LOGV, VISIT>(
+            p, x, y, s_dyn + threadIdx.x,
+            reinterpret_cast<float *>(s_dyn + p.path_levels * kThreads) + threadIdx.x);
+}
+
 // query_single_from_root for arbitrary points (include/cuda/rt_core.cuh:117-159).
 __global__ void query_points_kernel(TreeView tree, const float *__restrict__ xyz, int64_t n,
                                     int32_t *__restrict__ out) {
@@ -388,13 +430,13 @@ __global__ void query_points_kernel(TreeView tree, const float *__restrict__ xyz
     const float px = fmaxf(fminf(xyz[3 * i], hi), 0.f);
     const float py = fmaxf(fminf(xyz[3 * i + 1], hi), 0.f);
     const float pz = fmaxf(fminf(xyz[3 * i + 2], hi), 0.f);
-    const uint32_t qx = __float2uint_rd(__fmul_rn(px, 16777216.f));
-    const uint32_t qy = __float2uint_rd(__fmul_rn(py, 16777216.f));
-    const uint32_t qz = __float2uint_rd(__fmul_rn(pz, 16777216.f));
+    const uint32_t qx = __float_as_uint(__fmaf_rd(px, 8388608.f, 8388608.f));
+    const uint32_t qy = __float_as_uint(__fmaf_rd(py, 8388608.f, 8388608.f));
+    const uint32_t qz = __float_as_uint(__fmaf_rd(pz, 8388608.f, 8388608.f));
     int32_t node = 0;
     int lvl = 0, cidx;
     for (;;) {
-        const int bit = 23 - lvl;
+        const int bit = 22 - lvl;
         cidx = (((qx >> bit) & 1u) << 2) | (((qy >> bit) & 1u) << 1) | ((qz >> bit) & 1u);
         const uint32_t cw = __ldg(tree.cell + ((int64_t) node * 8 + cidx));
         if ((cw & kLeafBit) || lvl >= kMaxLevel) break;
@@ -407,10 +449,10 @@ __global__ void query_points_kernel(TreeView tree, const float *__restrict__ xyz
 }
 
 template <int TERMS>
-int dispatch(const RenderParams &p, bool track, bool logv, bool visit, dim3 grid,
+int dispatch(const RenderParams &p, bool track, bool logv, bool visit, dim3 grid, size_t smem,
              cudaStream_t stream) {
 #define MNV_LAUNCH(T, L, V) \
-    render_voxels_kernel<TERMS, T, L, V><<<grid, kThreads, 0, stream>>>(p)
+    render_voxels_kernel<TERMS, T, L, V><<<grid, kThreads, smem, stream>>>(p)
     if (logv) {
         if (track) MNV_LAUNCH(true, true, false);
         else MNV_LAUNCH(false, true, false);
@@ -453,7 +495,10 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
     p.opt = opt;
     p.tg = tg;
     p.tiles_x = (cam.width + kTileW - 1) / kTileW;
-    p.tiles_y = (cam.height + kTileH - 1) / kTileH;
+    const int tiles_y = (cam.height + kTileH - 1) / kTileH;
+    // a leaf at depth d is found in a node of level d-1; refinement may deepen the tree
+    p.max_level = std::min(kMaxLevel, std::max(tree.max_leaf_depth, 1) - 1);
+    p.path_levels = p.max_level + 1;
     if (p.tg.tile_mod > 1) {
         if (p.tg.tile_w < kTileW || p.tg.tile_h < kTileH || p.tg.tile_w % kTileW ||
             p.tg.tile_h % kTileH) {
@@ -473,15 +518,16 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
         set_error("visit logging and track_visit cannot be combined");
         return MNV_ERR_INVALID;
     }
-    const dim3 grid((unsigned) (p.tiles_x * p.tiles_y));
     const int terms = tree.format == MNV_FORMAT_SH ? tree.basis_dim : 0;
+    const dim3 grid((unsigned) (p.tiles_x * tiles_y));
+    const size_t smem = (size_t) (p.path_levels + terms) * kThreads * sizeof(int32_t);
     switch (terms) {
-        case 0: return dispatch<0>(p, track, logv, visit, grid, stream);
-        case 1: return dispatch<1>(p, track, logv, visit, grid, stream);
-        case 4: return dispatch<4>(p, track, logv, visit, grid, stream);
-        case 9: return dispatch<9>(p, track, logv, visit, grid, stream);
-        case 16: return dispatch<16>(p, track, logv, visit, grid, stream);
-        case 25: return dispatch<25>(p, track, logv, visit, grid, stream);
+        case 0: return dispatch<0>(p, track, logv, visit, grid, smem, stream);
+        case 1: return dispatch<1>(p, track, logv, visit, grid, smem, stream);
+        case 4: return dispatch<4>(p, track, logv, visit, grid, smem, stream);
+        case 9: return dispatch<9>(p, track, logv, visit, grid, smem, stream);
+        case 16: return dispatch<16>(p, track, logv, visit, grid, smem, stream);
+        case 25: return dispatch<25>(p, track, logv, visit, grid, smem, stream);
         default:
             set_error("unsupported SH basis_dim %d", terms);
             return MNV_ERR_INVALID;

@@ -101,6 +101,7 @@ int build_device_tree(DeviceTree &t, const mnv_tree_desc &d) {
     MNV_CUDA(cudaMalloc(&t.payload, max_slots * t.rec_u4 * sizeof(uint4)));
     MNV_CUDA(cudaMalloc(&t.parent, t.max_capacity * sizeof(int32_t)));
     MNV_CUDA(cudaMalloc(&t.sample_counts, max_slots * sizeof(int16_t)));
+
     MNV_CUDA(cudaMemsetAsync(t.parent, 0, t.max_capacity * sizeof(int32_t), t.stream));
     if (d.parent)
         MNV_CUDA(cudaMemcpyAsync(t.parent, d.parent, cap * sizeof(int32_t), cudaMemcpyHostToDevice,
