@@ -32,12 +32,23 @@
 namespace mnv {
 namespace {
 
-constexpr int kThreads = 128;    // 4 warps per CTA, each warp owns 8x4-pixel tiles
-#ifndef MNV_MIN_BLOCKS
-#define MNV_MIN_BLOCKS 10  // resident CTAs per SM the register allocation targets
+#ifndef MNV_TILE_H
+#define MNV_TILE_H 8   // CTA tile = 16 x MNV_TILE_H pixels (8 -> 4 warps, 16 -> 8 warps)
 #endif
-constexpr int kTileW = 16, kTileH = 8;  // granularity of the multi-GPU tile partition
+#ifndef MNV_SMEM_STATE
+#define MNV_SMEM_STATE 1  // park SH basis + shaded-only ray state in shared memory
+#endif
+constexpr int kThreads = 16 * MNV_TILE_H;  // each warp owns an 8x4-pixel tile
+#ifndef MNV_MIN_BLOCKS
+#define MNV_MIN_BLOCKS (1024 / (16 * MNV_TILE_H))  // resident CTAs per SM the register allocation targets
+#endif
+constexpr int kTileW = 16, kTileH = MNV_TILE_H;  // CTA tile; the multi-GPU partition is a multiple of 16x8
 constexpr int kMaxLevel = 22;    // q carries 23 bits per axis: leaf depth <= 23
+
+// words of per-ray state parked in shared memory (render_pixel)
+enum { kRsDeltaScale = 0, kRsT, kRsOut0, kRsOut1, kRsOut2, kRsWordsBase,
+       kRsMaxW = kRsWordsBase, kRsMaxSW, kRsSplitId, kRsSplitPrio, kRsSampId, kRsSampPrio,
+       kRsWordsTrack };
 
 struct RenderParams {
     TreeView tree;
@@ -98,7 +109,8 @@ __device__ __forceinline__ float sh_channel(const float (&B)[TERMS], const uint3
 template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
 __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x, const int y,
                                              int32_t *__restrict__ s_path,
-                                             float *__restrict__ s_basis) {
+                                             float *__restrict__ s_basis,
+                                             float *__restrict__ s_ray) {
     const int W = p.cam.width;
     const int idx = y * W + x;
     const mnv_render_options &opt = p.opt;
@@ -106,7 +118,20 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
     uint32_t rgbx_init = 0;
     if (!p.tg.offscreen) rgbx_init = surf2Dread<uint32_t>(p.tg.image_surf, x * 4, y, cudaBoundaryModeZero);
 
-    float out0 = 0.f, out1 = 0.f, out2 = 0.f, out3 = 0.f;
+    // Per-ray state that only shaded leaves touch lives in shared memory (word k of
+    // this thread at s_ray[k * kThreads]) so that the march itself needs few registers.
+#if MNV_SMEM_STATE
+#define RS(k) s_ray[(k) * kThreads]
+#define RSI(k) reinterpret_cast<int32_t *>(s_ray)[(k) * kThreads]
+#else
+    float rs_regs[kRsWordsTrack];
+#define RS(k) rs_regs[k]
+#define RSI(k) reinterpret_cast<int32_t *>(rs_regs)[k]
+#endif
+    RS(kRsOut0) = 0.f;
+    RS(kRsOut1) = 0.f;
+    RS(kRsOut2) = 0.f;
+    float out3 = 0.f;
 
     // ---- ray generation: screen2worlddir, renderer_kernel.cu:30-38 ----------
     const float *m = p.cam.c2w;
@@ -133,8 +158,14 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
     ref_rodrigues(opt.rot_dirs, v0, v1, v2);
 
     // ---- render_voxels_trace_ray, rt_core.cuh:162-332 ----------------------
-    float split_prio = (float) (opt.max_depth + 1), split_chunk = -1.f, split_child = -1.f;
-    float samp_prio = (float) (opt.max_sample_count + 1), samp_chunk = -1.f, samp_child = -1.f;
+    if (TRACK) {
+        RS(kRsSplitPrio) = (float) (opt.max_depth + 1);
+        RS(kRsSampPrio) = (float) (opt.max_sample_count + 1);
+        RSI(kRsSplitId) = -1;  // packed leaf id node*8 + child
+        RSI(kRsSampId) = -1;
+        RS(kRsMaxW) = -1.f;
+        RS(kRsMaxSW) = -1.f;
+    }
     unsigned long long vhash = 0xcbf29ce484222325ULL;
     int nvis = 0, nshaded = 0;
     bool hit = false;
@@ -148,6 +179,8 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
     d1 = __fmul_rn(d1, delta_scale);
     d2 = __fmul_rn(d2, delta_scale);
     tmax_bg = __fdiv_rn(tmax_bg, delta_scale);
+    RS(kRsDeltaScale) = delta_scale;
+    RS(kRsT) = 1.f;
 
     // invdir = 1.f / (dir + 1e-9): double add + double reciprocal, rt_core.cuh:188-190
     const float i0 = d2f(__drcp_rn(__dadd_rn((double) d0, 1e-9)));
@@ -176,20 +209,25 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         if (opt.render_depth) out3 = 1.f;
     } else {
         hit = true;
+        float B[TERMS > 0 ? TERMS : 1];
         if (TERMS > 0) {
-            // SH basis of the view direction: needed only by shaded leaves, so it is parked
-            // in shared memory instead of occupying 9..25 registers across the whole march
-            float B[TERMS > 0 ? TERMS : 1];
+            // SH basis of the view direction: needed only by shaded leaves; with
+            // MNV_SMEM_STATE it is parked in shared memory instead of 9..25 registers
             ref_sh_basis<(TERMS > 0 ? TERMS : 1)>(v0, v1, v2, B);
 #pragma unroll
-            for (int k = 0; k < TERMS; ++k)
-                s_basis[k * kThreads] = (k < opt.basis_minmax[0] || k > opt.basis_minmax[1]) ? 0.f : B[k];
+            for (int k = 0; k < TERMS; ++k) {
+                if (k < opt.basis_minmax[0] || k > opt.basis_minmax[1]) B[k] = 0.f;
+#if MNV_SMEM_STATE
+                s_basis[k * kThreads] = B[k];
+#endif
+            }
         }
         constexpr int REC_W = TERMS > 0 ? ((3 * TERMS + 1 + 7) / 8) * 4 : 4;  // u32 words / record
 
-        float T = 1.f;
         float t = tmin;
-        float max_weight = -1.f, max_sample_weight = -1.f;
+        // bit 0 / 1: a shaded leaf already set the split / re-sample candidate
+        // (max_weight / max_sample_weight != -1 in rt_core.cuh:308-321); bit 2: stopped early
+        uint32_t flags = 0;
         // raw bits of (floor(pos * 2^23) + 2^23) as float: 0x4B000000 | q, q = 23-bit cell coords
         uint32_t pqx = 0x4B000000u, pqy = 0x4B000000u, pqz = 0x4B000000u;
         int pdepth = 1;  // previous leaf depth: path valid for levels < pdepth
@@ -233,6 +271,9 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             }
             const int depth = lvl + 1;
             pdepth = depth;
+            const float sigma = __half2float(__ushort_as_half((unsigned short) (cw & 0xffffu)));
+            const bool shaded = (int32_t) cw < 0 && sigma > opt.sigma_thresh;
+            const uint4 *rec = p.tree.payload + (size_t) (node * 8u + cidx) * (REC_W / 4);
             if (LOGV) {
                 const long long packed = (long long) (node * 8u + cidx);
                 vhash = (vhash ^ (unsigned long long) packed) * 0x100000001b3ULL;
@@ -261,32 +302,32 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             }
             // / cube_size (exact power of two), + step_size
             const float delta_t = __fadd_rn(__fmul_rn(tm, icube), opt.step_size);
-            const float sigma = __half2float(__ushort_as_half((unsigned short) (cw & 0xffffu)));
             const int scount = (int) ((cw >> 16) & 0x7fffu);
 
-            if ((int32_t) cw < 0 && sigma > opt.sigma_thresh) {
+            if (shaded) {
                 if (LOGV) ++nshaded;
+                float T = RS(kRsT);
                 const float att =
-                        ref_expf(__fmul_rn(__fmul_rn(delta_scale, -delta_t), sigma));
+                        ref_expf(__fmul_rn(__fmul_rn(RS(kRsDeltaScale), -delta_t), sigma));
                 const float weight = __fmul_rn(T, __fadd_rn(1.f, -att));
                 if (TRACK) {
-                    if (weight > max_weight && depth < opt.max_depth) {
-                        split_chunk = (float) node;
-                        split_child = (float) cidx;
-                        split_prio = (float) depth;
-                        max_weight = weight;
+                    if (weight > RS(kRsMaxW) && depth < opt.max_depth) {
+                        RSI(kRsSplitId) = (int32_t) (node * 8u + cidx);
+                        RS(kRsSplitPrio) = (float) depth;
+                        RS(kRsMaxW) = weight;
+                        flags |= 1u;
                     }
-                    if (weight > max_sample_weight && scount < opt.max_sample_count) {
-                        samp_chunk = (float) node;
-                        samp_child = (float) cidx;
-                        samp_prio = (float) scount;
-                        max_sample_weight = weight;
+                    if (weight > RS(kRsMaxSW) && scount < opt.max_sample_count) {
+                        RSI(kRsSampId) = (int32_t) (node * 8u + cidx);
+                        RS(kRsSampPrio) = (float) scount;
+                        RS(kRsMaxSW) = weight;
+                        flags |= 2u;
                     }
                 }
+                float out0 = RS(kRsOut0), out1 = RS(kRsOut1), out2 = RS(kRsOut2);
                 if (opt.render_depth) {
                     out0 = __fmaf_rn(t, weight, out0);
                 } else {
-                    const uint4 *rec = p.tree.payload + (size_t) (node * 8u + cidx) * (REC_W / 4);
                     uint32_t w[REC_W];
 #pragma unroll
                     for (int j = 0; j < REC_W / 4; ++j) {
@@ -297,9 +338,10 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                         w[4 * j + 3] = v.w;
                     }
                     if (TERMS > 0) {
-                        float B[TERMS > 0 ? TERMS : 1];
+#if MNV_SMEM_STATE
 #pragma unroll
                         for (int k = 0; k < TERMS; ++k) B[k] = s_basis[k * kThreads];
+#endif
                         out0 = __fadd_rn(out0, ref_weighted_sigmoid(
                                 weight, sh_channel<(TERMS > 0 ? TERMS : 1), REC_W>(B, w, 0)));
                         out1 = __fadd_rn(out1, ref_weighted_sigmoid(
@@ -313,42 +355,48 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                     }
                 }
                 T = __fmul_rn(T, att);
+                RS(kRsT) = T;
                 if (T < opt.stop_thresh) {
                     if (opt.render_depth) out0 = out1 = out2 = fminf(__fmul_rn(out0, 0.3f), 1.0f);
                     const float scale = __frcp_rn(__fadd_rn(1.f, -T));
-                    out0 = __fmul_rn(out0, scale);
-                    out1 = __fmul_rn(out1, scale);
-                    out2 = __fmul_rn(out2, scale);
+                    RS(kRsOut0) = __fmul_rn(out0, scale);
+                    RS(kRsOut1) = __fmul_rn(out1, scale);
+                    RS(kRsOut2) = __fmul_rn(out2, scale);
                     out3 = 1.f;
-                    T = -1.f;  // marks "terminated early"
+                    flags |= 4u;  // terminated early
                     break;
                 }
+                RS(kRsOut0) = out0;
+                RS(kRsOut1) = out1;
+                RS(kRsOut2) = out2;
             } else if (TRACK) {
-                if (max_weight == -1.f && depth < opt.max_depth) {
-                    split_chunk = (float) node;
-                    split_child = (float) cidx;
-                    split_prio = (float) depth;
+                if (!(flags & 1u) && depth < opt.max_depth) {
+                    RSI(kRsSplitId) = (int32_t) (node * 8u + cidx);
+                    RS(kRsSplitPrio) = (float) depth;
                 }
-                if (max_sample_weight == -1.f && scount < opt.max_sample_count) {
-                    samp_chunk = (float) node;
-                    samp_child = (float) cidx;
-                    samp_prio = (float) scount;
+                if (!(flags & 2u) && scount < opt.max_sample_count) {
+                    RSI(kRsSampId) = (int32_t) (node * 8u + cidx);
+                    RS(kRsSampPrio) = (float) scount;
                 }
             }
             t = __fadd_rn(t, delta_t);
         }
-        if (T >= 0.f) {
+        if (!(flags & 4u)) {
             if (opt.render_depth) {
-                out0 = out1 = out2 = fminf(__fmul_rn(out0, 0.3f), 1.0f);
+                const float dv = fminf(__fmul_rn(RS(kRsOut0), 0.3f), 1.0f);
+                RS(kRsOut0) = dv;
+                RS(kRsOut1) = dv;
+                RS(kRsOut2) = dv;
                 out3 = 1.f;
             } else {
-                out3 = __fadd_rn(1.f, -T);
+                out3 = __fadd_rn(1.f, -RS(kRsT));
             }
         }
     }
 
     // ---- composite_and_write, renderer_kernel.cu:215-241 --------------------
     const float nalpha = __fadd_rn(1.f, -out3);
+    float out0 = RS(kRsOut0), out1 = RS(kRsOut1), out2 = RS(kRsOut2);
     if (p.tg.offscreen) {
         const float remain = __fmul_rn(nalpha, opt.background_brightness);
         out0 = __fadd_rn(out0, remain);
@@ -369,15 +417,19 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         surf2Dwrite(rgba, p.tg.image_surf, x * 4, y, cudaBoundaryModeZero);
 
     if (TRACK) {
+        // (priority, chunk, child) as floats, like the reference's trackers
+        const int32_t sid = RSI(kRsSplitId), pid = RSI(kRsSampId);
         float *ts = p.tg.to_split + (size_t) idx * 3;
-        ts[0] = split_prio;
-        ts[1] = split_chunk;
-        ts[2] = split_child;
+        ts[0] = RS(kRsSplitPrio);
+        ts[1] = sid < 0 ? -1.f : (float) (sid >> 3);
+        ts[2] = sid < 0 ? -1.f : (float) (sid & 7);
         float *tp = p.tg.to_sample + (size_t) idx * 3;
-        tp[0] = samp_prio;
-        tp[1] = samp_chunk;
-        tp[2] = samp_child;
+        tp[0] = RS(kRsSampPrio);
+        tp[1] = pid < 0 ? -1.f : (float) (pid >> 3);
+        tp[2] = pid < 0 ? -1.f : (float) (pid & 7);
     }
+#undef RS
+#undef RSI
     if (LOGV) {
         if (p.tg.visit_hash) p.tg.visit_hash[idx] = vhash;
         if (p.tg.visit_count) p.tg.visit_count[idx] = nvis;
@@ -405,7 +457,8 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
 __global__ void __launch_bounds__(kThreads, MNV_MIN_BLOCKS)
 render_voxels_kernel(const RenderParams p) {
-    extern __shared__ int32_t s_dyn[];  // [path_levels][kThreads] node path, then [TERMS][kThreads] basis
+    // [path_levels][kThreads] node path | [TERMS][kThreads] SH basis | [words][kThreads] ray state
+    extern __shared__ int32_t s_dyn[];
     const int bt = blockIdx.x;
     const int bty = bt / p.tiles_x, btx = bt - bty * p.tiles_x;
     if (p.tg.tile_mod > 1) {
@@ -418,7 +471,8 @@ render_voxels_kernel(const RenderParams p) {
     if (x >= p.cam.width || y >= p.cam.height) return;
     render_pixel<TERMS, TRACK, LOGV, VISIT>(
             p, x, y, s_dyn + threadIdx.x,
-            reinterpret_cast<float *>(s_dyn + p.path_levels * kThreads) + threadIdx.x);
+            reinterpret_cast<float *>(s_dyn + p.path_levels * kThreads) + threadIdx.x,
+            reinterpret_cast<float *>(s_dyn + (p.path_levels + TERMS) * kThreads) + threadIdx.x);
 }
 
 // query_single_from_root for arbitrary points (include/cuda/rt_core.cuh:117-159).
@@ -520,7 +574,9 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
     }
     const int terms = tree.format == MNV_FORMAT_SH ? tree.basis_dim : 0;
     const dim3 grid((unsigned) (p.tiles_x * tiles_y));
-    const size_t smem = (size_t) (p.path_levels + terms) * kThreads * sizeof(int32_t);
+    const size_t smem = (size_t) (p.path_levels +
+                                  (MNV_SMEM_STATE ? terms + (track ? kRsWordsTrack : kRsWordsBase) : 0)) *
+                        kThreads * sizeof(int32_t);
     switch (terms) {
         case 0: return dispatch<0>(p, track, logv, visit, grid, smem, stream);
         case 1: return dispatch<1>(p, track, logv, visit, grid, smem, stream);
