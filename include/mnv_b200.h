@@ -98,6 +98,38 @@ typedef struct mnv_tree_desc {
 typedef struct mnv_tree mnv_tree;   /* opaque device tree (SoA planes) */
 typedef struct mnv_model mnv_model; /* opaque Mega-NeRF MLP container */
 
+/* One Mega-NeRF sub-MLP, weights in PyTorch nn.Linear layout ([out][in], fp32, host).
+ * Stands in for one `sub_module_i` of the TorchScript container the reference
+ * loads in VolumeRenderer::load_model (src/renderer/cuda_renderer.cpp:518-543).
+ * The architecture is not part of the reference repository; shapes follow
+ * BASELINE.json / SURVEY.md §8 A9:
+ *   h0 = PE(xyz, pe_xyz_freqs)                       (3 + 6*freqs values, include-input)
+ *   h  = relu(trunk[l](l == skip_layer ? cat(h0, h) : h)),  l = 0 .. n_trunk_layers-1
+ *   sigma = act(sigma_w . h + sigma_b)
+ *   f  = final(h)                                    (width -> width, no activation)
+ *   g  = relu(head1(cat(f, [PE(dir, pe_dir_freqs)], [embedding[appearance index]])))
+ *   out = cat(head2(g), sigma)                       (out_rgb_dim + 1 columns)          */
+typedef struct mnv_mlp_desc {
+    int n_trunk_layers;   /* 8 */
+    int width;            /* 256 (the only supported width) */
+    int skip_layer;       /* 4 */
+    int pe_xyz_freqs;     /* 12 */
+    int pe_dir_freqs;     /* 4 */
+    int need_viewdir;     /* container attr need_viewdir, cuda_renderer.cpp:536 */
+    int appearance_dim;   /* 48; 0 = no appearance embedding */
+    int n_appearance;     /* rows of the embedding table */
+    int head_width;       /* 128 */
+    int out_rgb_dim;      /* 3 * basis_dim (27 for SH9), 3 for RGB */
+    int sigma_activation; /* 0 = ReLU, 1 = softplus */
+    const float *trunk_w[12];
+    const float *trunk_b[12];
+    const float *sigma_w, *sigma_b;
+    const float *final_w, *final_b;
+    const float *embedding; /* [n_appearance][appearance_dim] */
+    const float *head1_w, *head1_b;
+    const float *head2_w, *head2_b;
+} mnv_mlp_desc;
+
 /* Per-frame statistics the traversal kernel can produce (bench / roofline). */
 typedef struct mnv_frame_stats {
     uint64_t rays;
@@ -160,6 +192,21 @@ int mnv_render_voxels_logged(mnv_tree *tree, const mnv_camera *cam, const mnv_re
  * too (into tree-owned device buffers, see mnv_tree_trackers). */
 int mnv_render_frame_host(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
                           uint8_t *rgba_host, mnv_frame_stats *stats /* may be NULL */);
+
+/* ---- Mega-NeRF MLP: torch::jit::load + Module::forward, cuda_renderer.cpp:165-203,518-543
+ * Container attributes grid_dim / min_position / max_position (cluster rule,
+ * rt_core.cuh:541-549) travel with the model. x rows are
+ * [x, y, z, (dir x3 if need_viewdir), (appearance index as float if appearance_dim > 0)];
+ * out rows are [rgb / SH (out_rgb_dim), sigma] at stride out_stride floats.
+ * bf16 operands, fp32 accumulation in TMEM (tcgen05), fp32 bias / activations. */
+int mnv_model_create(mnv_model **out, int n_submodules, const mnv_mlp_desc *descs,
+                     const int32_t grid_dim[2], const float min_position[3],
+                     const float max_position[3], int device);
+int mnv_model_destroy(mnv_model *model);
+int mnv_model_info(const mnv_model *model, int *n_submodules, int *in_dim, int *out_dim,
+                   double *flops_per_row);
+int mnv_mlp_forward(mnv_model *model, int submodule, const float *x_dev, int64_t rows, int in_dim,
+                    float *out_dev, int out_stride, void *stream);
 
 /* Device pointers of the tree-owned candidate buffers filled by the host frame
  * calls when opt->use_splitting is set: f32 [P][3] each (valid until the next

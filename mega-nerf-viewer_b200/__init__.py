@@ -86,6 +86,23 @@ class FrameStats(C.Structure):
                 ("rays_hit", C.c_uint64)]
 
 
+class MlpDesc(C.Structure):
+    """mnv_mlp_desc (include/mnv_b200.h)."""
+
+    _fields_ = [
+        ("n_trunk_layers", C.c_int), ("width", C.c_int), ("skip_layer", C.c_int),
+        ("pe_xyz_freqs", C.c_int), ("pe_dir_freqs", C.c_int), ("need_viewdir", C.c_int),
+        ("appearance_dim", C.c_int), ("n_appearance", C.c_int), ("head_width", C.c_int),
+        ("out_rgb_dim", C.c_int), ("sigma_activation", C.c_int),
+        ("trunk_w", C.c_void_p * 12), ("trunk_b", C.c_void_p * 12),
+        ("sigma_w", C.c_void_p), ("sigma_b", C.c_void_p),
+        ("final_w", C.c_void_p), ("final_b", C.c_void_p),
+        ("embedding", C.c_void_p),
+        ("head1_w", C.c_void_p), ("head1_b", C.c_void_p),
+        ("head2_w", C.c_void_p), ("head2_b", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -132,6 +149,10 @@ def lib() -> C.CDLL:
     L.mnv_render_frame_host_bands.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp,
                                               i32, i32, i32, C.POINTER(FrameStats)]
     L.mnv_tree_trackers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
+    L.mnv_model_destroy.argtypes = [vp]
+    L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
+    L.mnv_mlp_forward.argtypes = [vp, i32, vp, i64, i32, vp, i32, vp]
     _lib = L
     return L
 
@@ -320,3 +341,73 @@ class DeviceTree:
             return rgba_host, dict(rays=st.rays, visits=st.visits, shaded_visits=st.shaded_visits,
                                    rays_hit=st.rays_hit)
         return rgba_host
+
+
+class MlpModel:
+    """Mega-NeRF sub-MLP container on the device (mnv_model_create / mnv_mlp_forward).
+
+    `submodules`: list of dicts with numpy fp32 arrays in nn.Linear layout:
+      trunk_w[i] [256, in], trunk_b[i], sigma_w [1,256], sigma_b [1], final_w/b,
+      embedding [n_app, app_dim] (optional), head1_w/b, head2_w/b, and the ints
+      skip_layer, pe_xyz_freqs, pe_dir_freqs, need_viewdir, sigma_activation.
+    """
+
+    def __init__(self, submodules, grid_dim=(1, 1), min_position=(0, 0, 0), max_position=(1, 1, 1),
+                 device: int = 0):
+        descs = (MlpDesc * len(submodules))()
+        keep = []
+
+        def ptr(a):
+            a = np.ascontiguousarray(a, np.float32)
+            keep.append(a)
+            return a.ctypes.data
+
+        for d, sm in zip(descs, submodules):
+            n = len(sm["trunk_w"])
+            d.n_trunk_layers, d.width = n, int(sm["trunk_w"][0].shape[0])
+            d.skip_layer = int(sm.get("skip_layer", 4))
+            d.pe_xyz_freqs = int(sm.get("pe_xyz_freqs", 12))
+            d.pe_dir_freqs = int(sm.get("pe_dir_freqs", 4))
+            d.need_viewdir = int(bool(sm.get("need_viewdir", False)))
+            emb = sm.get("embedding")
+            d.appearance_dim = 0 if emb is None else int(emb.shape[1])
+            d.n_appearance = 0 if emb is None else int(emb.shape[0])
+            d.head_width = int(sm["head1_w"].shape[0])
+            d.out_rgb_dim = int(sm["head2_w"].shape[0])
+            d.sigma_activation = int(sm.get("sigma_activation", 1))
+            for i in range(n):
+                d.trunk_w[i], d.trunk_b[i] = ptr(sm["trunk_w"][i]), ptr(sm["trunk_b"][i])
+            d.sigma_w, d.sigma_b = ptr(sm["sigma_w"]), ptr(sm["sigma_b"])
+            d.final_w, d.final_b = ptr(sm["final_w"]), ptr(sm["final_b"])
+            d.embedding = None if emb is None else ptr(emb)
+            d.head1_w, d.head1_b = ptr(sm["head1_w"]), ptr(sm["head1_b"])
+            d.head2_w, d.head2_b = ptr(sm["head2_w"]), ptr(sm["head2_b"])
+        gd = np.asarray(grid_dim, np.int32)
+        mn = np.asarray(min_position, np.float32)
+        mx = np.asarray(max_position, np.float32)
+        self._h = C.c_void_p()
+        self.device = device
+        _check(lib().mnv_model_create(C.byref(self._h), len(submodules), descs, gd.ctypes.data,
+                                      mn.ctypes.data, mx.ctypes.data, device))
+        n, i, o, f = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+        _check(lib().mnv_model_info(self._h, C.byref(n), C.byref(i), C.byref(o), C.byref(f)))
+        self.n_submodules, self.in_dim, self.out_dim, self.flops_per_row = n.value, i.value, o.value, f.value
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _lib is not None:
+            _lib.mnv_model_destroy(h)
+        self._h = None
+
+    __del__ = close
+
+    def forward(self, x, submodule: int = 0, out=None, stream=None):
+        """x: CUDA float32 [rows, in_dim] -> CUDA float32 [rows, out_dim]."""
+        torch = _torch()
+        x = x.contiguous()
+        assert x.dtype == torch.float32 and x.is_cuda and x.shape[1] == self.in_dim
+        if out is None:
+            out = torch.empty((x.shape[0], self.out_dim), dtype=torch.float32, device=x.device)
+        _check(lib().mnv_mlp_forward(self._h, submodule, _dptr(x), x.shape[0], x.shape[1], _dptr(out),
+                                     out.stride(0), _stream_ptr(stream)))
+        return out

@@ -8,6 +8,13 @@
 
 using namespace mnv;
 
+struct mnv_model {
+    std::vector<MlpModel *> subs;
+    int32_t grid_dim[2] = {1, 1};
+    float min_position[3] = {0, 0, 0}, max_position[3] = {1, 1, 1};
+    int device = 0;
+};
+
 struct mnv_tree {
     DeviceTree t;
     std::map<void *, cudaSurfaceObject_t> surfaces;  // cudaArray_t -> surface, created once
@@ -396,6 +403,63 @@ int mnv_render_frame_host_bands(mnv_tree *h, const mnv_camera *cam, const mnv_re
                                 mnv_frame_stats *stats) {
     if (band_mod < 1) return MNV_ERR_INVALID;
     return frame_host_impl(h, cam, opt, rgba_host, band_rows, band_mod, band_rem, stats);
+}
+
+int mnv_model_create(mnv_model **out, int n_submodules, const mnv_mlp_desc *descs,
+                     const int32_t grid_dim[2], const float min_position[3],
+                     const float max_position[3], int device) {
+    if (!out || !descs || n_submodules < 1) return MNV_ERR_INVALID;
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc != MNV_OK) return rc;
+    mnv_model *m = new (std::nothrow) mnv_model();
+    if (!m) return MNV_ERR_OOM;
+    m->device = device;
+    for (int i = 0; i < 2; ++i) m->grid_dim[i] = grid_dim ? grid_dim[i] : 1;
+    for (int i = 0; i < 3; ++i) {
+        m->min_position[i] = min_position ? min_position[i] : 0.f;
+        m->max_position[i] = max_position ? max_position[i] : 1.f;
+    }
+    for (int i = 0; i < n_submodules; ++i) {
+        MlpModel *sub = mlp_create(descs[i], device, &rc);
+        if (!sub) {
+            mnv_model_destroy(m);
+            return rc;
+        }
+        m->subs.push_back(sub);
+    }
+    *out = m;
+    return MNV_OK;
+}
+
+int mnv_model_destroy(mnv_model *m) {
+    if (!m) return MNV_OK;
+    cudaSetDevice(m->device);
+    for (MlpModel *s : m->subs) mlp_destroy(s);
+    delete m;
+    return MNV_OK;
+}
+
+int mnv_model_info(const mnv_model *m, int *n_submodules, int *in_dim, int *out_dim,
+                   double *flops_per_row) {
+    if (!m || m->subs.empty()) return MNV_ERR_INVALID;
+    if (n_submodules) *n_submodules = (int) m->subs.size();
+    if (in_dim) *in_dim = mlp_in_dim(m->subs[0]);
+    if (out_dim) *out_dim = mlp_out_dim(m->subs[0]);
+    if (flops_per_row) *flops_per_row = mlp_flops_per_row(m->subs[0]);
+    return MNV_OK;
+}
+
+int mnv_mlp_forward(mnv_model *m, int submodule, const float *x_dev, int64_t rows, int in_dim,
+                    float *out_dev, int out_stride, void *stream) {
+    if (!m || submodule < 0 || submodule >= (int) m->subs.size() ||
+        (rows > 0 && (!x_dev || !out_dev))) {
+        set_error("mnv_mlp_forward: bad arguments");
+        return MNV_ERR_INVALID;
+    }
+    MNV_CUDA(cudaSetDevice(m->device));
+    return mlp_forward(m->subs[submodule], x_dev, rows, in_dim, out_dev, out_stride,
+                       static_cast<cudaStream_t>(stream));
 }
 
 int mnv_tree_trackers(mnv_tree *h, float **to_split_dev, float **to_sample_dev) {

@@ -134,4 +134,14 @@ int build_device_tree(DeviceTree &t, const mnv_tree_desc &desc);
 int download_device_tree(const DeviceTree &t, int64_t first, int64_t count, uint16_t *data,
                          int32_t *child, int32_t *parent, int16_t *sample_counts);
 
+// ---- fused MLP (mnv_mlp.cu) -------------------------------------------------
+struct MlpModel;
+MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out);
+void mlp_destroy(MlpModel *m);
+int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim, float *out_dev,
+                int out_stride, cudaStream_t stream);
+double mlp_flops_per_row(const MlpModel *m);
+int mlp_in_dim(const MlpModel *m);
+int mlp_out_dim(const MlpModel *m);
+
 }  // namespace mnv

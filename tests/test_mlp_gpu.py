@@ -1,0 +1,64 @@
+"""GPU tests of the fused tcgen05 MLP against the PyTorch
+statement of the named shapes (tests/mlp_reference.py).  Tolerance from
+BASELINE.json: 1e-3 relative with bf16 operands / fp32 accumulation."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_err(a, b):
+    """max |a-b| relative to the output scale (per-column rms of the reference)."""
+    scale = np.sqrt((b.astype(np.float64) ** 2).mean(0)) + 1e-6
+    return float((np.abs(a - b) / scale).max())
+
+
+@pytest.mark.parametrize("need_viewdir,app_dim,basis,rows", [
+    (False, 48, 9, 128 * 5), (False, 48, 9, 1000), (True, 48, 9, 777), (False, 0, 1, 300), (True, 0, 4, 129)])
+def test_mlp_matches_torch_reference(need_viewdir, app_dim, basis, rows, mnv):
+    import torch
+    from mlp_reference import MegaNerfMLP, flops_per_row
+
+    torch.manual_seed(3)
+    ref = MegaNerfMLP(basis_dim=basis, appearance_dim=app_dim, need_viewdir=need_viewdir).cuda().eval()
+    model = mnv.MlpModel([ref.export()])
+    assert model.in_dim == 3 + 3 * need_viewdir + (app_dim > 0) and model.out_dim == 3 * basis + 1
+    assert model.flops_per_row == pytest.approx(flops_per_row(ref))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((rows, model.in_dim), device="cuda", generator=g) * 2 - 1
+    if need_viewdir:
+        x[:, 3:6] = torch.nn.functional.normalize(x[:, 3:6], dim=-1)
+    if app_dim > 0:
+        x[:, -1] = torch.randint(0, 4, (rows,), device="cuda", generator=g).float()
+    with torch.no_grad():
+        want_bf16 = ref(x, emulate_bf16=True).cpu().numpy()
+        want_fp32 = ref(x, emulate_bf16=False).cpu().numpy()
+    got = model.forward(x)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    assert np.isfinite(got).all()
+    # same roundings as the kernel (bf16 operands, fp32 accumulate): 1e-3 relative
+    assert _rel_err(got, want_bf16) < 1e-3, _rel_err(got, want_bf16)
+    # against pure fp32 the bf16 operand rounding itself shows (reported, loose bound)
+    assert _rel_err(got, want_fp32) < 3e-2, _rel_err(got, want_fp32)
+    model.close()
+
+
+def test_mlp_config4_shape_and_determinism(mnv):
+    """Config 4: 4096 splits x 8 children x 8 samples = 262144 rows per frame."""
+    import torch
+    from mlp_reference import MegaNerfMLP
+
+    torch.manual_seed(3)
+    ref = MegaNerfMLP().cuda().eval()
+    model = mnv.MlpModel([ref.export(), ref.export()])
+    x = torch.rand((262144, model.in_dim), device="cuda") * 2 - 1
+    x[:, -1] = 0
+    a = model.forward(x, submodule=0)
+    b = model.forward(x, submodule=1)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)  # identical weights, deterministic kernel
+    with torch.no_grad():
+        want = ref(x[:4096], emulate_bf16=True)
+    assert _rel_err(a[:4096].cpu().numpy(), want.cpu().numpy()) < 1e-3
+    model.close()
