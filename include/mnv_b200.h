@@ -193,6 +193,33 @@ int mnv_render_voxels_logged(mnv_tree *tree, const mnv_camera *cam, const mnv_re
 int mnv_render_frame_host(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
                           uint8_t *rgba_host, mnv_frame_stats *stats /* may be NULL */);
 
+/* ---- guided sampling: viewer::get_samples_from_voxels, src/cuda/renderer_kernel.cu:439-485
+ * (kernel :329-363, emitter include/cuda/rt_core.cuh:418-576) + the cumsum / mask
+ * compaction of cuda_renderer.cpp:116-120, in CSR form.  Outputs (device):
+ *   offsets_dev  i64 [P]  inclusive scan of per-ray sample counts (== torch::cumsum)
+ *   z_vals_dev   f32 [V]  row column 0 of the reference's guided_samples
+ *   rows_dev     f32 [V][row_stride]  MLP input rows: x,y,z,(view dir),(appearance index)
+ *   cluster_dev  i16 [V]  sub-module id, grid rule of rt_core.cuh:541-549
+ * V = *total_rows_host (written after the internal count pass; the call
+ * synchronises the stream once, like the reference). MNV_ERR_FULL if V exceeds
+ * capacity_rows. grid_dim / min_position / range are host pointers. */
+int mnv_guided_samples(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                       void *depth_arr, bool offscreen, const int32_t grid_dim[2],
+                       const float min_position[3], const float range[3], int64_t *offsets_dev,
+                       float *z_vals_dev, float *rows_dev, int row_stride, int16_t *cluster_dev,
+                       int64_t capacity_rows, int64_t *total_rows_host, float *to_split_dev,
+                       float *to_sample_dev, int32_t *visited_dev, bool track_visit, void *stream);
+
+/* ---- viewer::render_nerf_results, src/cuda/renderer_kernel.cu:365-394 (kernel :294-327,
+ * compositor rt_core.cuh:334-416). sample_values_dev f32 [V][value_stride] (MLP outputs),
+ * sigma_col < 0 keeps the reference's behaviour of reading sigma from column 3
+ * (rt_core.cuh:365) whatever the data format. */
+int mnv_render_nerf_results(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                            void *image_arr, uint8_t *image_linear_dev,
+                            const float *sample_values_dev, int value_stride, int sigma_col,
+                            const float *z_vals_dev, const int64_t *offsets_dev, bool offscreen,
+                            void *stream);
+
 /* ---- Mega-NeRF MLP: torch::jit::load + Module::forward, cuda_renderer.cpp:165-203,518-543
  * Container attributes grid_dim / min_position / max_position (cluster rule,
  * rt_core.cuh:541-549) travel with the model. x rows are

@@ -149,6 +149,10 @@ def lib() -> C.CDLL:
     L.mnv_render_frame_host_bands.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp,
                                               i32, i32, i32, C.POINTER(FrameStats)]
     L.mnv_tree_trackers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.mnv_guided_samples.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, C.c_bool, vp, vp, vp,
+                                     vp, vp, vp, i32, vp, i64, C.POINTER(i64), vp, vp, vp, C.c_bool, vp]
+    L.mnv_render_nerf_results.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, i32, i32,
+                                          vp, vp, C.c_bool, vp]
     L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
@@ -320,6 +324,42 @@ class DeviceTree:
         return dict(rgba=img.cpu().numpy(), hash=vh.cpu().numpy().view(np.uint64),
                     count=vc.cpu().numpy(), shaded=vs.cpu().numpy(),
                     log=None if vlog is None else vlog.cpu().numpy())
+
+    # ---- guided sampling (renderer_kernel.cu:439-485 + cuda_renderer.cpp:116-120) ----------
+    def guided_samples(self, cam, opt: RenderOptions, grid_dim, min_position, rng, capacity_rows: int,
+                       to_split=None, to_sample=None, stream=None):
+        """-> dict(total, offsets i64 [P], z_vals [V], rows [V, in_dim], cluster i16 [V]) on the device."""
+        torch = _torch()
+        cam = make_camera(cam)
+        dev = f"cuda:{self.device}"
+        P = cam.width * cam.height
+        in_dim = 3 + (3 if opt.need_viewdir else 0) + (1 if opt.appearance_embedding != -1 else 0)
+        offsets = torch.empty(P, dtype=torch.int64, device=dev)
+        z = torch.empty(capacity_rows, dtype=torch.float32, device=dev)
+        rows = torch.empty((capacity_rows, in_dim), dtype=torch.float32, device=dev)
+        cluster = torch.empty(capacity_rows, dtype=torch.int16, device=dev)
+        gd = np.ascontiguousarray(grid_dim, np.int32)
+        mp = np.ascontiguousarray(min_position, np.float32)
+        rg = np.ascontiguousarray(rng, np.float32)
+        total = C.c_int64(0)
+        _check(lib().mnv_guided_samples(self._h, C.byref(cam), C.byref(opt), None, True, gd.ctypes.data,
+                                        mp.ctypes.data, rg.ctypes.data, _dptr(offsets), _dptr(z), _dptr(rows),
+                                        in_dim, _dptr(cluster), capacity_rows, C.byref(total), _dptr(to_split),
+                                        _dptr(to_sample), None, False, _stream_ptr(stream)))
+        v = total.value
+        return dict(total=v, offsets=offsets, z_vals=z[:v], rows=rows[:v], cluster=cluster[:v])
+
+    def render_nerf_results(self, cam, opt: RenderOptions, values, z_vals, offsets, sigma_col: int = -1,
+                            out=None, stream=None):
+        """Composite MLP outputs (values f32 [V, stride]) per ray -> RGBA8 [H, W, 4] on the device."""
+        torch = _torch()
+        cam = make_camera(cam)
+        if out is None:
+            out = torch.empty((cam.height, cam.width, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+        _check(lib().mnv_render_nerf_results(self._h, C.byref(cam), C.byref(opt), None, _dptr(out), _dptr(values),
+                                             values.stride(0), sigma_col, _dptr(z_vals), _dptr(offsets), True,
+                                             _stream_ptr(stream)))
+        return out
 
     def render_frame_host(self, cam, opt, rgba_host=None, stats: bool = False, bands=None):
         """The per-frame call with HOST buffers (camera in, RGBA8 frame out).

@@ -210,6 +210,8 @@ int mnv_tree_destroy(mnv_tree *h) {
     cudaFree(t.payload);
     cudaFree(t.parent);
     cudaFree(t.sample_counts);
+    cudaFree(t.count_dev);
+    cudaFree(t.scan_tmp);
     cudaFree(t.frame_dev);
     cudaFree(t.split_dev);
     cudaFree(t.sample_dev);
@@ -403,6 +405,66 @@ int mnv_render_frame_host_bands(mnv_tree *h, const mnv_camera *cam, const mnv_re
                                 mnv_frame_stats *stats) {
     if (band_mod < 1) return MNV_ERR_INVALID;
     return frame_host_impl(h, cam, opt, rgba_host, band_rows, band_mod, band_rem, stats);
+}
+
+int mnv_guided_samples(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                       void *depth_arr, bool offscreen, const int32_t grid_dim[2],
+                       const float min_position[3], const float range[3], int64_t *offsets_dev,
+                       float *z_vals_dev, float *rows_dev, int row_stride, int16_t *cluster_dev,
+                       int64_t capacity_rows, int64_t *total_rows_host, float *to_split_dev,
+                       float *to_sample_dev, int32_t *visited_dev, bool track_visit, void *stream) {
+    if (!h || !cam || !opt || !grid_dim || !min_position || !range || !offsets_dev || !z_vals_dev ||
+        !rows_dev || !cluster_dev) {
+        set_error("mnv_guided_samples: missing argument");
+        return MNV_ERR_INVALID;
+    }
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    GuidedIO io;
+    io.offscreen = offscreen;
+    if (!offscreen) {
+        if (!depth_arr) {
+            set_error("offscreen == false needs the depth surface");
+            return MNV_ERR_INVALID;
+        }
+        int rc = surface_for(h, depth_arr, &io.depth_surf);
+        if (rc != MNV_OK) return rc;
+    }
+    io.offsets = offsets_dev;
+    io.z_vals = z_vals_dev;
+    io.rows = rows_dev;
+    io.cluster = cluster_dev;
+    io.row_stride = row_stride;
+    io.capacity_rows = capacity_rows;
+    io.total_rows = total_rows_host;
+    io.to_split = to_split_dev;
+    io.to_sample = to_sample_dev;
+    io.visited = visited_dev;
+    io.track_visit = track_visit;
+    for (int i = 0; i < 2; ++i) io.grid_dim[i] = grid_dim[i];
+    for (int i = 0; i < 3; ++i) {
+        io.min_position[i] = min_position[i];
+        io.range[i] = range[i];
+    }
+    return launch_guided_samples(h->t, *cam, *opt, io, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_nerf_results(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                            void *image_arr, uint8_t *image_linear_dev,
+                            const float *sample_values_dev, int value_stride, int sigma_col,
+                            const float *z_vals_dev, const int64_t *offsets_dev, bool offscreen,
+                            void *stream) {
+    if (!h || !cam || !opt || !offsets_dev) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    cudaSurfaceObject_t surf = 0;
+    int rc = surface_for(h, image_arr, &surf);
+    if (rc != MNV_OK) return rc;
+    if (!offscreen && !image_arr) {
+        set_error("offscreen == false needs the image surface");
+        return MNV_ERR_INVALID;
+    }
+    return launch_composite_nerf(h->t, *cam, *opt, image_linear_dev, surf, sample_values_dev,
+                                 value_stride, sigma_col, z_vals_dev, offsets_dev, offscreen,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 int mnv_model_create(mnv_model **out, int n_submodules, const mnv_mlp_desc *descs,

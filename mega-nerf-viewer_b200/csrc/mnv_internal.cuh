@@ -60,6 +60,10 @@ struct DeviceTree {
     int device = 0;
     int max_leaf_depth = 1;  // deepest leaf (reference counting: root's children are depth 1)
     // scratch for mnv_render_frame_host
+    int32_t *count_dev = nullptr;  // [P] per-ray sample counts (guided sampling)
+    int64_t count_cap = 0;
+    void *scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
     uint8_t *frame_dev = nullptr;
     float *split_dev = nullptr, *sample_dev = nullptr;
     size_t frame_bytes = 0;
@@ -133,6 +137,31 @@ const char *last_error_cstr();
 int build_device_tree(DeviceTree &t, const mnv_tree_desc &desc);
 int download_device_tree(const DeviceTree &t, int64_t first, int64_t count, uint16_t *data,
                          int32_t *child, int32_t *parent, int16_t *sample_counts);
+
+// ---- guided sampling (mnv_guided.cu) ------------------------------------------
+struct GuidedIO {
+    cudaSurfaceObject_t depth_surf = 0;
+    bool offscreen = true;
+    int64_t *offsets = nullptr;   // [P] inclusive scan of per-ray sample counts (out)
+    float *z_vals = nullptr;      // [capacity_rows]
+    float *rows = nullptr;        // [capacity_rows][row_stride]
+    int16_t *cluster = nullptr;   // [capacity_rows]
+    int row_stride = 0;
+    int64_t capacity_rows = 0;
+    int64_t *total_rows = nullptr;  // host, out
+    float *to_split = nullptr, *to_sample = nullptr;
+    int32_t *visited = nullptr;
+    bool track_visit = false;
+    int32_t grid_dim[2] = {1, 1};
+    float min_position[3] = {0, 0, 0}, range[3] = {1, 1, 1};
+};
+int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_render_options &opt,
+                          const GuidedIO &io, cudaStream_t stream);
+int launch_composite_nerf(const DeviceTree &tree, const mnv_camera &cam,
+                          const mnv_render_options &opt, uint8_t *image_linear,
+                          cudaSurfaceObject_t image_surf, const float *values, int value_stride,
+                          int sigma_col, const float *z_vals, const int64_t *offsets, bool offscreen,
+                          cudaStream_t stream);
 
 // ---- fused MLP (mnv_mlp.cu) -------------------------------------------------
 struct MlpModel;

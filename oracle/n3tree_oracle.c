@@ -586,3 +586,229 @@ int oracle_render_voxels(const mnv_tree_desc *tree, const mnv_camera *cam,
     pfor(render_rows, &c, nrows, 1, nthreads);
     return MNV_OK;
 }
+
+/* ===================================================================== A7 ==
+ * include/cuda/rt_core.cuh:418-576 get_samples_trace_ray +
+ * src/cuda/renderer_kernel.cu:329-363 get_samples_from_voxels_kernel, dense
+ * outputs exactly like the reference (only sensible at test sizes):
+ *   num_samples i16 [P]; samples f32 [P][S][sd]; cluster_indices i16 [P][S]
+ * sd = 4 + 3*need_viewdir + (appearance_embedding != -1).
+ */
+typedef struct {
+    const mnv_tree_desc *tree;
+    const mnv_camera *cam;
+    const mnv_render_options *opt;
+    const int32_t *grid_dim;
+    const float *min_position, *range;
+    int16_t *num_samples;
+    float *samples;
+    int16_t *cluster;
+    float *to_split, *to_sample;
+    int S, sd;
+} samples_ctx;
+
+static void samples_rows(void *vctx, int64_t rb, int64_t re) {
+    samples_ctx *c = (samples_ctx *) vctx;
+    const mnv_tree_desc *tree = c->tree;
+    const mnv_render_options *opt = c->opt;
+    const int W = c->cam->width, N3 = 8, D = tree->data_dim;
+    for (int64_t y = rb; y < re; ++y) {
+        for (int x = 0; x < W; ++x) {
+            const int64_t idx = y * W + x;
+            float true_dir[3], true_cen[3];
+            screen2worlddir(x, (int) y, c->cam, true_dir, true_cen);
+            float vdir[3] = {true_dir[0], true_dir[1], true_dir[2]};
+            rodrigues(opt->rot_dirs, vdir);
+            float dummy_a[3], dummy_b[3];
+            float *split = c->to_split ? c->to_split + idx * 3 : dummy_a;
+            float *sample = c->to_sample ? c->to_sample + idx * 3 : dummy_b;
+            split[0] = (float) (opt->max_depth + 1);
+            sample[0] = (float) (opt->max_sample_count + 1);
+            float cen[3], dir[3];
+            for (int i = 0; i < 3; ++i) cen[i] = fmaf(tree->scale[i], true_cen[i], tree->offset[i]);
+            for (int i = 0; i < 3; ++i) dir[i] = true_dir[i] * tree->scale[i];
+            const float delta_scale = 1.f / norm3(dir);
+            for (int i = 0; i < 3; ++i) dir[i] *= delta_scale;
+            const float tmax_bg = 1e9f / delta_scale;
+            float invdir[3];
+            for (int i = 0; i < 3; ++i) invdir[i] = (float) (1.0 / ((double) dir[i] + 1e-9));
+            float tmin = 0.f, tmax = 1e4f;
+            for (int i = 0; i < 3; ++i) {
+                const float t1 = (float) ((((double) opt->render_bbox[i] + 1e-6) - (double) cen[i]) *
+                                          (double) invdir[i]);
+                const float t2 = (float) ((((double) opt->render_bbox[i + 3] - 1e-6) - (double) cen[i]) *
+                                          (double) invdir[i]);
+                tmin = fmax_c(tmin, fmin_c(t1, t2));
+                tmax = fmin_c(tmax, fmax_c(t1, t2));
+            }
+            tmax = fmin_c(tmax, tmax_bg);
+            int16_t *ns = c->num_samples + idx;
+            if (tmax < 0 || tmin > tmax) continue;
+            float light_intensity = 1.f, t = tmin, max_weight = -1.f, max_sample_weight = -1.f;
+            float pos[3];
+            int32_t chunk_idx, child_idx;
+            while (t < tmax) {
+                for (int i = 0; i < 3; ++i) pos[i] = fmaf(t, dir[i], cen[i]);
+                const int depth = query_single_from_root(tree, NULL, pos, &chunk_idx, &child_idx, 0);
+                const float cube_size = powf((float) tree->N, (float) depth);
+                float tm = 1e4f;
+                for (int i = 0; i < 3; ++i) {
+                    const float t1 = -pos[i] * invdir[i];
+                    const float t2 = t1 + invdir[i];
+                    tm = fmin_c(tm, fmax_c(t1, t2));
+                }
+                const float delta_t = tm / cube_size + opt->step_size;
+                const int64_t leaf = (int64_t) chunk_idx * N3 + child_idx;
+                const float sigma = half_to_float(tree->data[leaf * D + D - 1]);
+                const int16_t sc = tree->sample_counts ? tree->sample_counts[leaf] : 8;
+                if (sigma > opt->sigma_thresh) {
+                    const float att = expf((-delta_t * delta_scale) * sigma);
+                    const float weight = light_intensity * (1.f - att);
+                    if (weight > max_weight && depth < opt->max_depth) {
+                        split[1] = (float) chunk_idx;
+                        split[2] = (float) child_idx;
+                        split[0] = (float) depth;
+                        max_weight = weight;
+                    }
+                    if (weight > max_sample_weight && sc < opt->max_sample_count) {
+                        sample[1] = (float) chunk_idx;
+                        sample[2] = (float) child_idx;
+                        sample[0] = (float) sc;
+                        max_sample_weight = weight;
+                    }
+                    if (*ns < opt->max_guided_samples) {
+                        float *row = c->samples + ((int64_t) idx * c->S + *ns) * c->sd;
+                        float tz[3];
+                        for (int i = 0; i < 3; ++i) tz[i] = (t * dir[i]) / tree->scale[i];
+                        row[0] = norm3(tz);
+                        for (int i = 0; i < 3; ++i) row[1 + i] = fmaf(true_dir[i], row[0], true_cen[i]);
+                        if (opt->need_viewdir) {
+                            row[4] = vdir[0];
+                            row[5] = vdir[1];
+                            row[6] = vdir[2];
+                            if (opt->appearance_embedding != -1) row[7] = (float) opt->appearance_embedding;
+                        } else if (opt->appearance_embedding != -1) {
+                            row[4] = (float) opt->appearance_embedding;
+                        }
+                        const float g0 = (float) c->grid_dim[0], g1 = (float) c->grid_dim[1];
+                        const int a = (int) fmax_c(
+                                fmin_c((row[2] - c->min_position[1]) / c->range[1] * g0, g0 - 1.0f), 0.0f);
+                        const int b = (int) fmax_c(
+                                fmin_c((row[3] - c->min_position[2]) / c->range[2] * g1, g1 - 1.0f), 0.0f);
+                        c->cluster[(int64_t) idx * c->S + *ns] = (int16_t) (a * c->grid_dim[1] + b);
+                        *ns += 1;
+                    }
+                    light_intensity *= att;
+                    if (light_intensity < opt->stop_thresh) break;
+                } else {
+                    if (max_weight == -1 && depth < opt->max_depth) {
+                        split[1] = (float) chunk_idx;
+                        split[2] = (float) child_idx;
+                        split[0] = (float) depth;
+                    }
+                    if (max_sample_weight == -1 && sc < opt->max_sample_count) {
+                        sample[1] = (float) chunk_idx;
+                        sample[2] = (float) child_idx;
+                        sample[0] = (float) sc;
+                    }
+                }
+                t += delta_t;
+            }
+        }
+    }
+}
+
+int oracle_get_samples(const mnv_tree_desc *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                       const int32_t *grid_dim, const float *min_position, const float *range,
+                       int16_t *num_samples, float *samples, int16_t *cluster, int S, int sd,
+                       float *to_split, float *to_sample, int nthreads) {
+    if (!tree || !cam || !opt || !num_samples || !samples || !cluster) return MNV_ERR_INVALID;
+    samples_ctx c = {tree, cam, opt, grid_dim, min_position, range, num_samples,
+                     samples, cluster, to_split, to_sample, S, sd};
+    pfor(samples_rows, &c, cam->height, 1, nthreads);
+    return MNV_OK;
+}
+
+/* ===================================================================== A8 ==
+ * include/cuda/rt_core.cuh:334-416 composite_nerf_results +
+ * src/cuda/renderer_kernel.cu:294-327 render_nerf_results_kernel (offscreen).
+ * sample_values f32 [V][stride]; sigma is read from column `sigma_col`
+ * (the reference always uses 3, rt_core.cuh:365).
+ */
+int oracle_composite_nerf(int format, int basis_dim, const mnv_camera *cam,
+                          const mnv_render_options *opt, const float *sample_values, int stride,
+                          int sigma_col, const float *z_vals, const int64_t *offsets, uint8_t *rgba) {
+    const int W = cam->width, H = cam->height;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int64_t idx = (int64_t) y * W + x;
+            float out[3] = {0.f, 0.f, 0.f};
+            const int64_t start = idx == 0 ? 0 : offsets[idx - 1], end = offsets[idx];
+            if (start != end) {
+                float dir[3], cen[3];
+                screen2worlddir(x, y, cam, dir, cen);
+                rodrigues(opt->rot_dirs, dir);
+                float basis_fn[MNV_GLOBAL_BASIS_MAX];
+                memset(basis_fn, 0, sizeof(basis_fn));
+                precalc_basis(format, basis_dim, dir, basis_fn);
+                for (int i = 0; i < opt->basis_minmax[0] && i < MNV_GLOBAL_BASIS_MAX; ++i) basis_fn[i] = 0.f;
+                for (int i = opt->basis_minmax[1] + 1; i < MNV_GLOBAL_BASIS_MAX; ++i)
+                    if (i >= 0) basis_fn[i] = 0.f;
+                float ti = 1.f, wc = 0.f;
+                for (int64_t i = start; i < end; ++i) {
+                    const float *sv = sample_values + i * stride;
+                    float weight;
+                    if (i < end - 1) {
+                        const float delta = z_vals[i + 1] - z_vals[i];
+                        wc = expf(-sv[sigma_col] * delta);
+                        weight = ti * (1.0f - wc);
+                    } else {
+                        weight = ti;
+                    }
+                    if (opt->render_depth) {
+                        out[0] = fmaf(ti, weight, out[0]);
+                    } else if (basis_dim >= 0) {
+                        for (int ch = 0; ch < 3; ++ch) {
+                            const float *c = sv + ch * basis_dim;
+                            float tmp = basis_fn[0] * c[0];
+                            if (basis_dim == 25) {
+                                float s = basis_fn[17] * c[17];
+                                s = fmaf(basis_fn[16], c[16], s);
+                                for (int k = 18; k <= 24; ++k) s = fmaf(basis_fn[k], c[k], s);
+                                tmp = tmp + s;
+                            }
+                            if (basis_dim == 25 || basis_dim == 16) {
+                                float s = basis_fn[10] * c[10];
+                                s = fmaf(basis_fn[9], c[9], s);
+                                for (int k = 11; k <= 15; ++k) s = fmaf(basis_fn[k], c[k], s);
+                                tmp = tmp + s;
+                            }
+                            if (basis_dim == 25 || basis_dim == 16 || basis_dim == 9) {
+                                float s = basis_fn[5] * c[5];
+                                s = fmaf(basis_fn[4], c[4], s);
+                                for (int k = 6; k <= 8; ++k) s = fmaf(basis_fn[k], c[k], s);
+                                tmp = tmp + s;
+                            }
+                            if (basis_dim == 25 || basis_dim == 16 || basis_dim == 9 || basis_dim == 4) {
+                                float s = basis_fn[2] * c[2];
+                                s = fmaf(basis_fn[1], c[1], s);
+                                s = fmaf(basis_fn[3], c[3], s);
+                                tmp = tmp + s;
+                            }
+                            out[ch] += weight / (1.f + expf(-tmp));
+                        }
+                    } else {
+                        for (int j = 0; j < 3; ++j) out[j] = fmaf(weight, sv[j], out[j]);
+                    }
+                    ti *= wc;
+                }
+                if (opt->render_depth) out[0] = out[1] = out[2] = fmin_c(out[0] * 0.3f, 1.0f);
+            }
+            uint8_t *px = rgba + idx * 4;
+            px[0] = to_u8(out[0]);
+            px[1] = to_u8(out[1]);
+            px[2] = to_u8(out[2]);
+            px[3] = 255;
+        }
+    return MNV_OK;
+}

@@ -149,6 +149,13 @@ def lib():
             C.c_int, C.c_int, C.c_int, C.c_int,
         ]
         _lib.oracle_num_threads.restype = C.c_int
+        _lib.oracle_get_samples.restype = C.c_int
+        _lib.oracle_get_samples.argtypes = [C.POINTER(TreeDesc), C.POINTER(Camera), C.POINTER(RenderOptions),
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.oracle_composite_nerf.restype = C.c_int
+        _lib.oracle_composite_nerf.argtypes = [C.c_int, C.c_int, C.POINTER(Camera), C.POINTER(RenderOptions),
+                                               C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -185,6 +192,55 @@ def render_voxels(tree, cam: dict, opt: RenderOptions, *, trackers=False, log_ca
         y0, H if y1 is None else y1, row_step, nthreads)
     assert rc == 0, rc
     return dict(rgba=rgba, to_split=split, to_sample=sample, hash=vh, count=vc, shaded=vs, log=vlog)
+
+
+def sample_dim(opt: RenderOptions) -> int:
+    """cuda_renderer.cpp:478-489: z + xyz (+ view dir) (+ appearance index)."""
+    return 4 + (3 if opt.need_viewdir else 0) + (1 if opt.appearance_embedding != -1 else 0)
+
+
+def compact_samples(num_samples, samples, cluster):
+    """The reference's mask compaction + cumsum (cuda_renderer.cpp:116-120) on host arrays:
+    -> offsets i64 [P], z_vals [V], rows [V, sd-1], cluster [V]."""
+    P, S, sd = samples.shape
+    flat = samples.reshape(-1, sd)
+    valid = flat[:, 0] >= 0
+    offsets = np.cumsum(num_samples.astype(np.int64))
+    return offsets, flat[valid, 0].copy(), flat[valid, 1:].copy(), cluster.reshape(-1)[valid].copy()
+
+
+def get_samples(tree, cam: dict, opt: RenderOptions, grid_dim, min_position, rng, nthreads=0):
+    """CPU oracle of get_samples_from_voxels with the reference's dense outputs."""
+    desc, keep = make_tree_desc(tree)
+    c = make_camera(cam)
+    P, S, sd = c.width * c.height, opt.max_guided_samples, sample_dim(opt)
+    ns = np.zeros(P, np.int16)
+    samples = np.full((P, S, sd), -1, np.float32)
+    cluster = np.zeros((P, S), np.int16)
+    split = np.full((P, 3), -1, np.float32)
+    samp = np.full((P, 3), -1, np.float32)
+    gd = np.ascontiguousarray(grid_dim, np.int32)
+    mp = np.ascontiguousarray(min_position, np.float32)
+    rg = np.ascontiguousarray(rng, np.float32)
+    rc = lib().oracle_get_samples(C.byref(desc), C.byref(c), C.byref(opt), gd.ctypes.data, mp.ctypes.data,
+                                  rg.ctypes.data, ns.ctypes.data, samples.ctypes.data, cluster.ctypes.data,
+                                  S, sd, split.ctypes.data, samp.ctypes.data, nthreads)
+    assert rc == 0, rc
+    return dict(num_samples=ns, samples=samples, cluster=cluster, to_split=split, to_sample=samp)
+
+
+def composite_nerf(tree, cam: dict, opt: RenderOptions, values, z_vals, offsets, sigma_col=3):
+    c = make_camera(cam)
+    values = np.ascontiguousarray(values, np.float32)
+    z_vals = np.ascontiguousarray(z_vals, np.float32)
+    offsets = np.ascontiguousarray(offsets, np.int64)
+    rgba = np.zeros((c.height, c.width, 4), np.uint8)
+    fmt = 1 if tree.data_format.upper().startswith("SH") else 0
+    rc = lib().oracle_composite_nerf(fmt, tree.basis_dim, C.byref(c), C.byref(opt), values.ctypes.data,
+                                     values.shape[1], sigma_col, z_vals.ctypes.data, offsets.ctypes.data,
+                                     rgba.ctypes.data)
+    assert rc == 0, rc
+    return rgba
 
 
 # ---------------------------------------------------------------------------
@@ -269,6 +325,39 @@ class RefRenderer:
         w, h, intr, c2w = self._cam_args(cam)
         rc = self.L.ref_render_frame_host(self.h, w, h, intr.ctypes.data, c2w.ctypes.data,
                                           C.byref(opt), C.sizeof(opt), rgba.ctypes.data)
+        assert rc == 0, rc
+        return rgba
+
+    def get_samples(self, cam: dict, opt: RenderOptions, grid_dim, min_position, rng):
+        w, h, intr, c2w = self._cam_args(cam)
+        P, S, sd = w * h, opt.max_guided_samples, sample_dim(opt)
+        ns = np.zeros(P, np.int16)
+        samples = np.zeros((P, S, sd), np.float32)
+        cluster = np.zeros((P, S), np.int16)
+        split = np.zeros((P, 3), np.float32)
+        samp = np.zeros((P, 3), np.float32)
+        gd = np.ascontiguousarray(grid_dim, np.int32)
+        mp = np.ascontiguousarray(min_position, np.float32)
+        rg = np.ascontiguousarray(rng, np.float32)
+        self.L.ref_get_samples.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + [C.c_int] + \
+            [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 5
+        rc = self.L.ref_get_samples(self.h, w, h, intr.ctypes.data, c2w.ctypes.data, C.byref(opt), C.sizeof(opt),
+                                    gd.ctypes.data, mp.ctypes.data, rg.ctypes.data, S, sd, ns.ctypes.data,
+                                    samples.ctypes.data, cluster.ctypes.data, split.ctypes.data, samp.ctypes.data)
+        assert rc == 0, rc
+        return dict(num_samples=ns, samples=samples, cluster=cluster, to_split=split, to_sample=samp)
+
+    def render_nerf_results(self, cam: dict, opt: RenderOptions, values, z_vals, offsets):
+        w, h, intr, c2w = self._cam_args(cam)
+        values = np.ascontiguousarray(values, np.float32)
+        z_vals = np.ascontiguousarray(z_vals, np.float32)
+        offsets = np.ascontiguousarray(offsets, np.int64)
+        rgba = np.zeros((h, w, 4), np.uint8)
+        self.L.ref_render_nerf_results.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 3 + \
+            [C.c_int, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.L.ref_render_nerf_results(self.h, w, h, intr.ctypes.data, c2w.ctypes.data, C.byref(opt),
+                                            C.sizeof(opt), values.ctypes.data, values.shape[0], values.shape[1],
+                                            z_vals.ctypes.data, offsets.ctypes.data, rgba.ctypes.data)
         assert rc == 0, rc
         return rgba
 

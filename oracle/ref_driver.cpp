@@ -200,6 +200,72 @@ int ref_render_frame_host(void *ctx, int w, int h, const float *intr, const floa
     return cudaStreamSynchronize(c->stream) == cudaSuccess ? 0 : 2;
 }
 
+// viewer::get_samples_from_voxels (src/cuda/renderer_kernel.cu:439-485), offscreen, with the
+// dense buffers of Impl::init_sample_tensor / init_split_tracker (cuda_renderer.cpp:460-496):
+// guided_samples [P][S][sd] pre-filled with -1 in column 0 (:110), num_samples zeroed (:109).
+int ref_get_samples(void *ctx, int w, int h, const float *intr, const float *c2w, const void *opt_pod,
+                    int opt_size, const int *grid_dim, const float *min_position, const float *range,
+                    int S, int sd, short *num_samples_out, float *samples_out, short *cluster_out,
+                    float *split_out, float *sample_out) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    ensure_target(c, w, h);
+    set_camera(c, w, h, intr, c2w);
+    const long P = (long) w * h;
+    auto cuda = torch::TensorOptions().device(torch::kCUDA);
+    torch::Tensor num_samples = torch::zeros({P}, cuda.dtype(torch::kInt16));
+    torch::Tensor samples = torch::ones({P, S, sd}, cuda.dtype(torch::kFloat32)) * -1;
+    torch::Tensor cluster = torch::zeros({P, S}, cuda.dtype(torch::kInt16));
+    torch::Tensor gd = torch::from_blob((void *) grid_dim, {2}, torch::kInt32).clone().to(torch::kCUDA);
+    torch::Tensor mp = torch::from_blob((void *) min_position, {3}, torch::kFloat32).clone().to(torch::kCUDA);
+    torch::Tensor rg = torch::from_blob((void *) range, {3}, torch::kFloat32).clone().to(torch::kCUDA);
+    c->split.fill_(-1);
+    c->sample.fill_(-1);
+    viewer::get_samples_from_voxels(c->tree, *c->cam, opt, c->depth, c->stream, c->split, c->sample,
+                                    c->visited, /*track_visit=*/false, /*offscreen=*/true,
+                                    num_samples, samples, cluster, gd, mp, rg);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+    auto ns = num_samples.cpu();
+    std::memcpy(num_samples_out, ns.data_ptr(), P * 2);
+    auto sm = samples.cpu();
+    std::memcpy(samples_out, sm.data_ptr(), (size_t) P * S * sd * 4);
+    auto cl = cluster.cpu();
+    std::memcpy(cluster_out, cl.data_ptr(), (size_t) P * S * 2);
+    if (split_out) {
+        auto t = c->split.cpu();
+        std::memcpy(split_out, t.data_ptr(), t.numel() * 4);
+    }
+    if (sample_out) {
+        auto t = c->sample.cpu();
+        std::memcpy(sample_out, t.data_ptr(), t.numel() * 4);
+    }
+    return 0;
+}
+
+// viewer::render_nerf_results (src/cuda/renderer_kernel.cu:365-394), offscreen.
+int ref_render_nerf_results(void *ctx, int w, int h, const float *intr, const float *c2w,
+                            const void *opt_pod, int opt_size, const float *sample_values, long V,
+                            int vdim, const float *z_vals, const long *offsets,
+                            unsigned char *rgba_out) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    ensure_target(c, w, h);
+    set_camera(c, w, h, intr, c2w);
+    const long P = (long) w * h;
+    torch::Tensor sv = torch::from_blob((void *) sample_values, {V, vdim}, torch::kFloat32).clone().to(torch::kCUDA);
+    torch::Tensor zv = torch::from_blob((void *) z_vals, {V}, torch::kFloat32).clone().to(torch::kCUDA);
+    torch::Tensor of = torch::from_blob((void *) offsets, {P}, torch::kInt64).clone().to(torch::kCUDA);
+    viewer::render_nerf_results(c->tree, *c->cam, opt, c->img, c->stream, sv, zv, of, /*offscreen=*/true);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+    cudaMemcpy2DFromArray(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h,
+                          cudaMemcpyDeviceToHost);
+    return 0;
+}
+
 #ifdef REF_VISIT_LOG
 // Instrumented build only: one render with per-ray visit hash / count / log.
 int ref_render_voxels_logged(void *ctx, int w, int h, const float *intr, const float *c2w,
