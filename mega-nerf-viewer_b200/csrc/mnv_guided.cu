@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const Guid
         float T = 1.f, t = r.tmin;
         MarchState ms;
         while (t < r.tmax) {
-            const Leaf lf = march_step<VISIT>(p.tree.cell, p.max_level, r, t, opt.step_size, ms, path,
+            const Leaf lf = march_step<VISIT, /*FUSED_POS=*/false>(p.tree.cell, p.max_level, r, t, opt.step_size, ms, path,
                                               kGThreads, p.visited);
             const float sigma = leaf_sigma(lf.cw);
             const int scount = leaf_sample_count(lf.cw);

@@ -94,15 +94,21 @@ struct Leaf {
 // One iteration of the reference's while (t < tmax) loop up to and including
 // delta_t (rt_core.cuh:221-230): locate the leaf of pos = cen + t*dir and the
 // distance to its exit.  s_path: this thread's column of the shared node path.
-template <bool VISIT>
+// FUSED_POS: pos = FFMA(t, dir, cen) as in the reference's render_voxels_kernel; false:
+// pos = FADD(cen, FMUL(t, dir)), which is what its get_samples_from_voxels_kernel executes
+// (t*dir is reused for the sample's z there, so nvcc does not contract the add).
+template <bool VISIT, bool FUSED_POS>
 __device__ __forceinline__ Leaf march_step(const uint32_t *__restrict__ cells, const int max_level,
                                            const Ray &r, const float t, const float step_size,
                                            MarchState &ms, int32_t *__restrict__ s_path,
                                            const int path_stride, int32_t *visited) {
     const float clamp_hi = f_from_bits(0x3F7FFFEFu);
-    const float px = fminf(__saturatef(__fmaf_rn(t, r.d0, r.c0)), clamp_hi);
-    const float py = fminf(__saturatef(__fmaf_rn(t, r.d1, r.c1)), clamp_hi);
-    const float pz = fminf(__saturatef(__fmaf_rn(t, r.d2, r.c2)), clamp_hi);
+    const float rx = FUSED_POS ? __fmaf_rn(t, r.d0, r.c0) : __fadd_rn(r.c0, __fmul_rn(t, r.d0));
+    const float ry = FUSED_POS ? __fmaf_rn(t, r.d1, r.c1) : __fadd_rn(r.c1, __fmul_rn(t, r.d1));
+    const float rz = FUSED_POS ? __fmaf_rn(t, r.d2, r.c2) : __fadd_rn(r.c2, __fmul_rn(t, r.d2));
+    const float px = fminf(__saturatef(rx), clamp_hi);
+    const float py = fminf(__saturatef(ry), clamp_hi);
+    const float pz = fminf(__saturatef(rz), clamp_hi);
     const uint32_t qx = __float_as_uint(__fmaf_rd(px, 8388608.f, 8388608.f));
     const uint32_t qy = __float_as_uint(__fmaf_rd(py, 8388608.f, 8388608.f));
     const uint32_t qz = __float_as_uint(__fmaf_rd(pz, 8388608.f, 8388608.f));

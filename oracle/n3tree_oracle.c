@@ -648,7 +648,9 @@ static void samples_rows(void *vctx, int64_t rb, int64_t re) {
             float pos[3];
             int32_t chunk_idx, child_idx;
             while (t < tmax) {
-                for (int i = 0; i < 3; ++i) pos[i] = fmaf(t, dir[i], cen[i]);
+                /* NOT fused here: the reference's get_samples kernel executes FMUL + FADD
+                 * (t*dir is reused for true_z), unlike its render kernel's FFMA */
+                for (int i = 0; i < 3; ++i) pos[i] = cen[i] + t * dir[i];
                 const int depth = query_single_from_root(tree, NULL, pos, &chunk_idx, &child_idx, 0);
                 const float cube_size = powf((float) tree->N, (float) depth);
                 float tm = 1e4f;

@@ -358,6 +358,8 @@ class RefRenderer:
         rc = self.L.ref_render_nerf_results(self.h, w, h, intr.ctypes.data, c2w.ctypes.data, C.byref(opt),
                                             C.sizeof(opt), values.ctypes.data, values.shape[0], values.shape[1],
                                             z_vals.ctypes.data, offsets.ctypes.data, rgba.ctypes.data)
+        if rc == 3:  # the reference's own launch fails on this GPU (168 regs x 512 threads)
+            return None
         assert rc == 0, rc
         return rgba
 

@@ -259,7 +259,12 @@ int ref_render_nerf_results(void *ctx, int w, int h, const float *intr, const fl
     torch::Tensor sv = torch::from_blob((void *) sample_values, {V, vdim}, torch::kFloat32).clone().to(torch::kCUDA);
     torch::Tensor zv = torch::from_blob((void *) z_vals, {V}, torch::kFloat32).clone().to(torch::kCUDA);
     torch::Tensor of = torch::from_blob((void *) offsets, {P}, torch::kInt64).clone().to(torch::kCUDA);
+    cudaGetLastError();
     viewer::render_nerf_results(c->tree, *c->cam, opt, c->img, c->stream, sv, zv, of, /*offscreen=*/true);
+    // The reference never checks its launches.  Rebuilt for sm_100 this kernel needs 168
+    // registers x 512 threads per block (auto_cuda_threads, renderer_kernel.cu:14-28) = 86016
+    // > 65536 registers per SM: the launch fails with "too many resources requested".
+    if (cudaGetLastError() != cudaSuccess) return 3;
     if (cudaDeviceSynchronize() != cudaSuccess) return 2;
     cudaMemcpy2DFromArray(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h,
                           cudaMemcpyDeviceToHost);

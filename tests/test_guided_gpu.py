@@ -37,7 +37,11 @@ def test_guided_samples_match_oracle_and_reference(okw, mnv, oracle, tmp_path):
     assert np.array_equal(g["offsets"].cpu().numpy(), off)
     assert np.array_equal(g["cluster"].cpu().numpy(), cl)
     assert np.array_equal(g["z_vals"].cpu().numpy(), z)          # same fp32 ops -> bit-exact
-    assert np.array_equal(g["rows"].cpu().numpy(), rows)
+    if "rot_dirs" in okw:  # rotated view dirs go through sinf/cosf: CPU libm vs CUDA differ by an ulp
+        assert np.allclose(g["rows"].cpu().numpy(), rows, rtol=0, atol=3e-7)
+        assert np.array_equal(g["rows"].cpu().numpy()[:, :3], rows[:, :3])
+    else:
+        assert np.array_equal(g["rows"].cpu().numpy(), rows)
     assert np.array_equal(ts.cpu().numpy(), o["to_split"]) and np.array_equal(tp.cpu().numpy(), o["to_sample"])
     assert int(o["num_samples"].max()) <= mopt.max_guided_samples
     if oracle.ref_available():
@@ -90,6 +94,9 @@ def test_composite_matches_oracle_and_reference(fmt, render_depth, mnv, oracle, 
         tree.save_npz(npz)
         ref = oracle.RefRenderer(npz)
         rimg = ref.render_nerf_results(cam, oopt, values, z, off)
-        assert np.array_equal(img, rimg), np.abs(img.astype(int) - rimg.astype(int)).max()
+        # None: the reference's render_nerf_results_kernel cannot launch on sm_100 as built
+        # (168 registers x 512 threads per block > 64 K registers); the oracle is then the check
+        if rimg is not None:
+            assert np.array_equal(img, rimg), np.abs(img.astype(int) - rimg.astype(int)).max()
         ref.close()
     dt.close()
