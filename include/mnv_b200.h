@@ -220,6 +220,42 @@ int mnv_render_nerf_results(mnv_tree *tree, const mnv_camera *cam, const mnv_ren
                             const float *z_vals_dev, const int64_t *offsets_dev, bool offscreen,
                             void *stream);
 
+/* ---- dynamic refinement --------------------------------------------------------------
+ * viewer::add_children_and_generate_samples, src/cuda/renderer_kernel.cu:487-511 (kernel
+ * :170-198): link 8 children under each of the n chosen leaves (parent_nodes_dev i32 [n][2] =
+ * chunk, child) at node indices capacity .. capacity+n-1, and turn the U[0,1) numbers in
+ * samples_dev (f32 [n*8][samples_per_corner][rand_dim], rand_dim = 3 + 3*need_viewdir +
+ * (appearance_embedding != -1)) into world-space sample rows; cluster_dev i16
+ * [n*8][samples_per_corner].  The children become visible to the march at once (sigma 0)
+ * and count towards capacity after mnv_tree_commit_children.  MNV_ERR_FULL when the tree
+ * cannot take n more nodes ("Full", cuda_renderer.cpp:228-231). */
+int mnv_add_children_and_generate_samples(mnv_tree *tree, const mnv_render_options *opt,
+                                          const int32_t *parent_nodes_dev, int n, float *samples_dev,
+                                          int16_t *cluster_dev, int32_t *visited_dev,
+                                          const int32_t grid_dim[2], const float min_position[3],
+                                          const float range[3], void *stream);
+/* Impl::expand_voxels tail, cuda_renderer.cpp:266-275: leaf payload = mean over the
+ * samples_per_corner MLP outputs (results_dev f32 [n*8][samples_per_corner][result_stride],
+ * first data_dim columns used) rounded to fp16, sample_counts = samples_per_corner,
+ * capacity += n. */
+int mnv_tree_commit_children(mnv_tree *tree, const mnv_render_options *opt, int n,
+                             const float *results_dev, int result_stride, void *stream);
+/* viewer::generate_samples, renderer_kernel.cu:513-535 (kernel :200-213): sample rows for m
+ * existing leaves (nodes_dev i32 [m][2]). */
+int mnv_generate_samples(mnv_tree *tree, const mnv_render_options *opt, const int32_t *nodes_dev, int m,
+                         float *samples_dev, int16_t *cluster_dev, const int32_t grid_dim[2],
+                         const float min_position[3], const float range[3], void *stream);
+/* Impl::get_more_samples tail, cuda_renderer.cpp:318-339: running-mean update of the m leaves
+ * with samples_per_corner new MLP outputs each; sample_counts += samples_per_corner. */
+int mnv_tree_update_samples(mnv_tree *tree, const mnv_render_options *opt, const int32_t *nodes_dev,
+                            int m, const float *results_dev, int result_stride, void *stream);
+/* Impl::prune_tree, cuda_renderer.cpp:343-381 + viewer::adjust_parents_and_children,
+ * renderer_kernel.cu:537-550 (kernel :63-86): to_delete_dev u8 [capacity] (1 = drop node),
+ * index_shifts_dev i32 [capacity] = inclusive cumsum of to_delete, num_deleted = its last
+ * element.  Fixes child / parent links, compacts every plane in place, capacity -= num_deleted. */
+int mnv_tree_prune(mnv_tree *tree, const uint8_t *to_delete_dev, const int32_t *index_shifts_dev,
+                   int first_shift_index, int64_t num_deleted, void *stream);
+
 /* ---- Mega-NeRF MLP: torch::jit::load + Module::forward, cuda_renderer.cpp:165-203,518-543
  * Container attributes grid_dim / min_position / max_position (cluster rule,
  * rt_core.cuh:541-549) travel with the model. x rows are

@@ -153,6 +153,11 @@ def lib() -> C.CDLL:
                                      vp, vp, vp, i32, vp, i64, C.POINTER(i64), vp, vp, vp, C.c_bool, vp]
     L.mnv_render_nerf_results.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, i32, i32,
                                           vp, vp, C.c_bool, vp]
+    L.mnv_add_children_and_generate_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.mnv_tree_commit_children.argtypes = [vp, C.POINTER(RenderOptions), i32, vp, i32, vp]
+    L.mnv_generate_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, vp, vp, vp, vp, vp]
+    L.mnv_tree_update_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, i32, vp]
+    L.mnv_tree_prune.argtypes = [vp, vp, vp, i32, i64, vp]
     L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
@@ -360,6 +365,45 @@ class DeviceTree:
                                              values.stride(0), sigma_col, _dptr(z_vals), _dptr(offsets), True,
                                              _stream_ptr(stream)))
         return out
+
+    # ---- refinement (renderer_kernel.cu:63-213, cuda_renderer.cpp:205-381) --------------------
+    @staticmethod
+    def _grid_args(grid_dim, min_position, rng):
+        a = (np.ascontiguousarray(grid_dim, np.int32), np.ascontiguousarray(min_position, np.float32),
+             np.ascontiguousarray(rng, np.float32))
+        return a, [C.c_void_p(x.ctypes.data) for x in a]
+
+    def add_children(self, opt, parent_nodes, samples, cluster, grid_dim, min_position, rng, visited=None,
+                     stream=None):
+        keep, g = self._grid_args(grid_dim, min_position, rng)
+        _check(lib().mnv_add_children_and_generate_samples(
+            self._h, C.byref(opt), _dptr(parent_nodes), parent_nodes.shape[0], _dptr(samples), _dptr(cluster),
+            _dptr(visited), g[0], g[1], g[2], _stream_ptr(stream)))
+
+    def commit_children(self, opt, n, results, stream=None):
+        _check(lib().mnv_tree_commit_children(self._h, C.byref(opt), n, _dptr(results), results.shape[-1],
+                                              _stream_ptr(stream)))
+
+    def generate_samples(self, opt, nodes, samples, cluster, grid_dim, min_position, rng, stream=None):
+        keep, g = self._grid_args(grid_dim, min_position, rng)
+        _check(lib().mnv_generate_samples(self._h, C.byref(opt), _dptr(nodes), nodes.shape[0], _dptr(samples),
+                                          _dptr(cluster), g[0], g[1], g[2], _stream_ptr(stream)))
+
+    def update_samples(self, opt, nodes, results, stream=None):
+        _check(lib().mnv_tree_update_samples(self._h, C.byref(opt), _dptr(nodes), nodes.shape[0],
+                                             _dptr(results), results.shape[-1], _stream_ptr(stream)))
+
+    def prune(self, to_delete, stream=None):
+        """to_delete: CUDA bool/uint8 [capacity]. Mirrors Impl::prune_tree (cumsum on the device)."""
+        torch = _torch()
+        td = to_delete.to(torch.uint8).contiguous()
+        shifts = torch.cumsum(td, 0, dtype=torch.int32)
+        num = int(shifts[-1].item())
+        if num == 0:
+            return 0
+        first = int(torch.argmin(shifts).item())  # cuda_renderer.cpp:357
+        _check(lib().mnv_tree_prune(self._h, _dptr(td), _dptr(shifts), first, num, _stream_ptr(stream)))
+        return num
 
     def render_frame_host(self, cam, opt, rgba_host=None, stats: bool = False, bands=None):
         """The per-frame call with HOST buffers (camera in, RGBA8 frame out).

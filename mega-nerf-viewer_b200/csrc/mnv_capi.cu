@@ -467,6 +467,52 @@ int mnv_render_nerf_results(mnv_tree *h, const mnv_camera *cam, const mnv_render
                                  static_cast<cudaStream_t>(stream));
 }
 
+int mnv_add_children_and_generate_samples(mnv_tree *h, const mnv_render_options *opt,
+                                          const int32_t *parent_nodes_dev, int n, float *samples_dev,
+                                          int16_t *cluster_dev, int32_t *visited_dev,
+                                          const int32_t grid_dim[2], const float min_position[3],
+                                          const float range[3], void *stream) {
+    if (!h || !opt || (n > 0 && (!parent_nodes_dev || !samples_dev || !cluster_dev))) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return refine_add_children(h->t, *opt, parent_nodes_dev, n, samples_dev, cluster_dev, visited_dev,
+                               grid_dim, min_position, range, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_tree_commit_children(mnv_tree *h, const mnv_render_options *opt, int n, const float *results_dev,
+                             int result_stride, void *stream) {
+    if (!h || !opt || (n > 0 && !results_dev) || result_stride < h->t.data_dim) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return refine_commit_children(h->t, *opt, n, results_dev, result_stride, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_generate_samples(mnv_tree *h, const mnv_render_options *opt, const int32_t *nodes_dev, int m,
+                         float *samples_dev, int16_t *cluster_dev, const int32_t grid_dim[2],
+                         const float min_position[3], const float range[3], void *stream) {
+    if (!h || !opt || (m > 0 && (!nodes_dev || !samples_dev || !cluster_dev))) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return refine_generate_samples(h->t, *opt, nodes_dev, m, samples_dev, cluster_dev, grid_dim,
+                                   min_position, range, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_tree_update_samples(mnv_tree *h, const mnv_render_options *opt, const int32_t *nodes_dev, int m,
+                            const float *results_dev, int result_stride, void *stream) {
+    if (!h || !opt || (m > 0 && (!nodes_dev || !results_dev)) || result_stride < h->t.data_dim)
+        return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return refine_update_samples(h->t, *opt, nodes_dev, m, results_dev, result_stride,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int mnv_tree_prune(mnv_tree *h, const uint8_t *to_delete_dev, const int32_t *index_shifts_dev,
+                   int first_shift_index, int64_t num_deleted, void *stream) {
+    if (!h || !to_delete_dev || !index_shifts_dev || first_shift_index < 0 || num_deleted < 0 ||
+        num_deleted >= h->t.capacity)
+        return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return refine_prune(h->t, to_delete_dev, index_shifts_dev, first_shift_index, num_deleted,
+                        static_cast<cudaStream_t>(stream));
+}
+
 int mnv_model_create(mnv_model **out, int n_submodules, const mnv_mlp_desc *descs,
                      const int32_t grid_dim[2], const float min_position[3],
                      const float max_position[3], int device) {

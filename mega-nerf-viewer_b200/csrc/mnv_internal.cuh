@@ -58,6 +58,7 @@ struct DeviceTree {
     float scale[3] = {1, 1, 1};
     float offset[3] = {0, 0, 0};
     int device = 0;
+    int pending_children = 0;  // nodes linked by add_children, not yet committed
     int max_leaf_depth = 1;  // deepest leaf (reference counting: root's children are depth 1)
     // scratch for mnv_render_frame_host
     int32_t *count_dev = nullptr;  // [P] per-ray sample counts (guided sampling)
@@ -162,6 +163,21 @@ int launch_composite_nerf(const DeviceTree &tree, const mnv_camera &cam,
                           cudaSurfaceObject_t image_surf, const float *values, int value_stride,
                           int sigma_col, const float *z_vals, const int64_t *offsets, bool offscreen,
                           cudaStream_t stream);
+
+// ---- refinement (mnv_refine.cu) -------------------------------------------------
+int refine_add_children(DeviceTree &t, const mnv_render_options &opt, const int32_t *parent_nodes_dev,
+                        int n, float *samples_dev, int16_t *cluster_dev, int32_t *visited_dev,
+                        const int32_t *grid_dim, const float *min_position, const float *range,
+                        cudaStream_t stream);
+int refine_commit_children(DeviceTree &t, const mnv_render_options &opt, int n, const float *results_dev,
+                           int result_stride, cudaStream_t stream);
+int refine_generate_samples(DeviceTree &t, const mnv_render_options &opt, const int32_t *nodes_dev, int m,
+                            float *samples_dev, int16_t *cluster_dev, const int32_t *grid_dim,
+                            const float *min_position, const float *range, cudaStream_t stream);
+int refine_update_samples(DeviceTree &t, const mnv_render_options &opt, const int32_t *nodes_dev, int m,
+                          const float *results_dev, int result_stride, cudaStream_t stream);
+int refine_prune(DeviceTree &t, const uint8_t *to_delete_dev, const int32_t *index_shifts_dev,
+                 int first_shift_index, int64_t num_deleted, cudaStream_t stream);
 
 // ---- fused MLP (mnv_mlp.cu) -------------------------------------------------
 struct MlpModel;

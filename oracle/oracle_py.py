@@ -363,6 +363,41 @@ class RefRenderer:
         assert rc == 0, rc
         return rgba
 
+    def add_children(self, opt: RenderOptions, parent_nodes, samples, grid_dim, min_position, rng):
+        pn = np.ascontiguousarray(parent_nodes, np.int32)
+        sm = np.ascontiguousarray(samples, np.float32).copy()
+        n, spc, rd = pn.shape[0], sm.shape[1], sm.shape[2]
+        cl = np.zeros((n * 8, spc), np.int16)
+        gd, mp, rg = (np.ascontiguousarray(grid_dim, np.int32), np.ascontiguousarray(min_position, np.float32),
+                      np.ascontiguousarray(rng, np.float32))
+        self.L.ref_add_children.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.L.ref_add_children(self.h, C.byref(opt), C.sizeof(opt), pn.ctypes.data, n, sm.ctypes.data, spc,
+                                     rd, cl.ctypes.data, gd.ctypes.data, mp.ctypes.data, rg.ctypes.data)
+        assert rc == 0, rc
+        return sm, cl
+
+    def generate_samples(self, opt: RenderOptions, nodes, samples, grid_dim, min_position, rng):
+        nd = np.ascontiguousarray(nodes, np.int32)
+        sm = np.ascontiguousarray(samples, np.float32).copy()
+        m, spc, rd = nd.shape[0], sm.shape[1], sm.shape[2]
+        cl = np.zeros((m, spc), np.int16)
+        gd, mp, rg = (np.ascontiguousarray(grid_dim, np.int32), np.ascontiguousarray(min_position, np.float32),
+                      np.ascontiguousarray(rng, np.float32))
+        self.L.ref_generate_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        rc = self.L.ref_generate_samples(self.h, C.byref(opt), C.sizeof(opt), nd.ctypes.data, m, sm.ctypes.data,
+                                         spc, rd, cl.ctypes.data, gd.ctypes.data, mp.ctypes.data, rg.ctypes.data)
+        assert rc == 0, rc
+        return sm, cl
+
+    def prune(self, to_delete):
+        td = np.ascontiguousarray(to_delete, np.uint8)
+        self.L.ref_prune.argtypes = [C.c_void_p, C.c_void_p]
+        rc = self.L.ref_prune(self.h, td.ctypes.data)
+        assert rc >= 0, rc
+        return rc
+
     def render_logged(self, cam: dict, opt: RenderOptions, log_cap: int = 0):
         assert self.instr
         w, h, intr, c2w = self._cam_args(cam)

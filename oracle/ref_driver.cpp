@@ -271,6 +271,84 @@ int ref_render_nerf_results(void *ctx, int w, int h, const float *intr, const fl
     return 0;
 }
 
+// ---- refinement launchers (include/cuda/renderer_kernel.hpp:49-79) -------------------------
+static void cluster_tensors(const int *grid_dim, const float *min_position, const float *range,
+                            torch::Tensor &gd, torch::Tensor &mp, torch::Tensor &rg) {
+    gd = torch::from_blob((void *) grid_dim, {2}, torch::kInt32).clone().to(torch::kCUDA);
+    mp = torch::from_blob((void *) min_position, {3}, torch::kFloat32).clone().to(torch::kCUDA);
+    rg = torch::from_blob((void *) range, {3}, torch::kFloat32).clone().to(torch::kCUDA);
+}
+
+// viewer::add_children_and_generate_samples; then capacity += n like expand_voxels
+// (cuda_renderer.cpp:275).  samples: in = U[0,1) numbers, out = world-space rows.
+int ref_add_children(void *ctx, const void *opt_pod, int opt_size, const int *parent_nodes, int n,
+                     float *samples, int spc, int rand_dim, short *cluster_out, const int *grid_dim,
+                     const float *min_position, const float *range) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    if (c->tree.capacity + n > c->max_cap) return 4;
+    auto cuda = torch::TensorOptions().device(torch::kCUDA);
+    torch::Tensor pn = torch::from_blob((void *) parent_nodes, {n, 2}, torch::kInt32).clone().to(torch::kCUDA);
+    torch::Tensor sm = torch::from_blob(samples, {(long) n * 8, spc, rand_dim}, torch::kFloat32).clone().to(torch::kCUDA);
+    torch::Tensor cl = torch::zeros({(long) n * 8, spc}, cuda.dtype(torch::kInt16));
+    torch::Tensor gd, mp, rg;
+    cluster_tensors(grid_dim, min_position, range, gd, mp, rg);
+    viewer::add_children_and_generate_samples(c->tree, opt, pn, sm, cl, c->visited, gd, mp, rg);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+    c->tree.capacity += n;
+    auto smc = sm.cpu();
+    std::memcpy(samples, smc.data_ptr(), smc.numel() * 4);
+    auto clc = cl.cpu();
+    std::memcpy(cluster_out, clc.data_ptr(), clc.numel() * 2);
+    return 0;
+}
+
+// viewer::generate_samples for existing leaves.
+int ref_generate_samples(void *ctx, const void *opt_pod, int opt_size, const int *nodes, int m,
+                         float *samples, int spc, int rand_dim, short *cluster_out,
+                         const int *grid_dim, const float *min_position, const float *range) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    auto cuda = torch::TensorOptions().device(torch::kCUDA);
+    torch::Tensor nd = torch::from_blob((void *) nodes, {m, 2}, torch::kInt32).clone().to(torch::kCUDA);
+    torch::Tensor sm = torch::from_blob(samples, {m, spc, rand_dim}, torch::kFloat32).clone().to(torch::kCUDA);
+    torch::Tensor cl = torch::zeros({m, spc}, cuda.dtype(torch::kInt16));
+    torch::Tensor gd, mp, rg;
+    cluster_tensors(grid_dim, min_position, range, gd, mp, rg);
+    viewer::generate_samples(c->tree, opt, nd, sm, cl, gd, mp, rg);
+    if (cudaDeviceSynchronize() != cudaSuccess) return 2;
+    auto smc = sm.cpu();
+    std::memcpy(samples, smc.data_ptr(), smc.numel() * 4);
+    auto clc = cl.cpu();
+    std::memcpy(cluster_out, clc.data_ptr(), clc.numel() * 2);
+    return 0;
+}
+
+// Impl::prune_tree (cuda_renderer.cpp:343-381) on host-provided marks: cumsum, argmin,
+// viewer::adjust_parents_and_children, then the chunked gather of data/child/parent.
+int ref_prune(void *ctx, const unsigned char *to_delete_host) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    const long cap = c->tree.capacity;
+    torch::Tensor to_delete = torch::from_blob((void *) to_delete_host, {cap}, torch::kUInt8).clone().to(torch::kCUDA).to(torch::kBool);
+    int num_to_delete = to_delete.sum().item().toInt();
+    if (num_to_delete == 0) return 0;
+    torch::Tensor index_shifts = torch::cumsum(to_delete, 0, torch::kInt32);
+    int first_shift_index = index_shifts.argmin().item().toInt();
+    viewer::adjust_parents_and_children(c->tree, first_shift_index, to_delete, index_shifts);
+    torch::Tensor keep = torch::arange(first_shift_index, cap, torch::TensorOptions().device(torch::kCUDA))
+                                 .index({to_delete.slice(0, first_shift_index, cap) == false});
+    const long kept = keep.size(0);
+    c->tree.data.slice(0, first_shift_index, first_shift_index + kept) = c->tree.data.index({keep}).clone();
+    c->tree.child.slice(0, first_shift_index, first_shift_index + kept) = c->tree.child.index({keep}).clone();
+    c->tree.parent.slice(0, first_shift_index, first_shift_index + kept) = c->tree.parent.index({keep}).clone();
+    c->tree.capacity -= num_to_delete;
+    return cudaDeviceSynchronize() == cudaSuccess ? num_to_delete : -2;
+}
+
 #ifdef REF_VISIT_LOG
 // Instrumented build only: one render with per-ray visit hash / count / log.
 int ref_render_voxels_logged(void *ctx, int w, int h, const float *intr, const float *c2w,
