@@ -271,6 +271,23 @@ int mnv_model_info(const mnv_model *model, int *n_submodules, int *in_dim, int *
 int mnv_mlp_forward(mnv_model *model, int submodule, const float *x_dev, int64_t rows, int in_dim,
                     float *out_dev, int out_stride, void *stream);
 
+/* Impl::query_submodules, cuda_renderer.cpp:165-203: evaluate rows_dev f32 [V][in_dim] with
+ * the sub-module named by cluster_dev i16 [V]; out_dev f32 [V][out_stride] receives
+ * [rgb / SH, sigma] in the first out_dim columns of each row (scatter_ semantics). */
+int mnv_query_submodules(mnv_model *model, const int16_t *cluster_dev, const float *rows_dev, int in_dim,
+                         int64_t rows, float *out_dev, int out_stride, void *stream);
+
+/* Candidate selection of Impl::expand_voxels (cuda_renderer.cpp:205-226): unique tracker rows
+ * with their vote counts, keep rows voted by >= 2 rays, order by (-count, depth, chunk, child),
+ * take the first max_n -> nodes_dev i32 [max_n][2] = (chunk, child).  *n_selected rows are
+ * valid; *n_candidates is the reference's "Split candidates" count. */
+int mnv_select_split_candidates(const float *to_split_dev, int64_t n_rays, int max_n, int32_t *nodes_dev,
+                                int *n_selected, int *n_candidates, void *stream);
+/* Impl::get_more_samples (cuda_renderer.cpp:281-293): unique rows ordered by
+ * (sample count, chunk, child), first max_n. */
+int mnv_select_sample_candidates(const float *to_sample_dev, int64_t n_rays, int max_n,
+                                 int32_t *nodes_dev, int *n_selected, int *n_candidates, void *stream);
+
 /* Device pointers of the tree-owned candidate buffers filled by the host frame
  * calls when opt->use_splitting is set: f32 [P][3] each (valid until the next
  * frame call with a different size). */

@@ -158,6 +158,9 @@ def lib() -> C.CDLL:
     L.mnv_generate_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, vp, vp, vp, vp, vp]
     L.mnv_tree_update_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, i32, vp]
     L.mnv_tree_prune.argtypes = [vp, vp, vp, i32, i64, vp]
+    L.mnv_query_submodules.argtypes = [vp, vp, vp, i32, i64, vp, i32, vp]
+    L.mnv_select_split_candidates.argtypes = [vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
+    L.mnv_select_sample_candidates.argtypes = [vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
     L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
@@ -427,6 +430,16 @@ class DeviceTree:
         return rgba_host
 
 
+def select_candidates(tracker, max_n: int, kind: str = "split", stream=None):
+    """tracker: CUDA f32 [P, 3] = (priority, chunk, child) -> (nodes i32 [n, 2] on device, n_candidates)."""
+    torch = _torch()
+    nodes = torch.empty((max_n, 2), dtype=torch.int32, device=tracker.device)
+    n, nc = C.c_int(0), C.c_int(0)
+    fn = lib().mnv_select_split_candidates if kind == "split" else lib().mnv_select_sample_candidates
+    _check(fn(_dptr(tracker), tracker.shape[0], max_n, _dptr(nodes), C.byref(n), C.byref(nc), _stream_ptr(stream)))
+    return nodes[: n.value], nc.value
+
+
 class MlpModel:
     """Mega-NeRF sub-MLP container on the device (mnv_model_create / mnv_mlp_forward).
 
@@ -484,6 +497,12 @@ class MlpModel:
         self._h = None
 
     __del__ = close
+
+    def query_submodules(self, cluster, rows, out, stream=None):
+        """cluster i16 [V], rows f32 [V, in_dim], out f32 [V, >= out_dim] (all CUDA)."""
+        _check(lib().mnv_query_submodules(self._h, _dptr(cluster), _dptr(rows), rows.shape[1], rows.shape[0],
+                                          _dptr(out), out.stride(0), _stream_ptr(stream)))
+        return out
 
     def forward(self, x, submodule: int = 0, out=None, stream=None):
         """x: CUDA float32 [rows, in_dim] -> CUDA float32 [rows, out_dim]."""

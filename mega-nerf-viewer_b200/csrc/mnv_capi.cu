@@ -570,6 +570,28 @@ int mnv_mlp_forward(mnv_model *m, int submodule, const float *x_dev, int64_t row
                        static_cast<cudaStream_t>(stream));
 }
 
+int mnv_query_submodules(mnv_model *m, const int16_t *cluster_dev, const float *rows_dev, int in_dim,
+                         int64_t rows, float *out_dev, int out_stride, void *stream) {
+    if (!m || m->subs.empty() || (rows > 0 && (!cluster_dev || !rows_dev || !out_dev))) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(m->device));
+    return query_submodules(m->subs.data(), (int) m->subs.size(), cluster_dev, rows_dev, in_dim, rows, out_dev,
+                            out_stride, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_select_split_candidates(const float *to_split_dev, int64_t n_rays, int max_n, int32_t *nodes_dev,
+                                int *n_selected, int *n_candidates, void *stream) {
+    if (!to_split_dev || !nodes_dev || n_rays <= 0 || max_n <= 0) return MNV_ERR_INVALID;
+    return select_split_candidates(to_split_dev, n_rays, max_n, nodes_dev, n_selected, n_candidates,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int mnv_select_sample_candidates(const float *to_sample_dev, int64_t n_rays, int max_n,
+                                 int32_t *nodes_dev, int *n_selected, int *n_candidates, void *stream) {
+    if (!to_sample_dev || !nodes_dev || n_rays <= 0 || max_n <= 0) return MNV_ERR_INVALID;
+    return select_sample_candidates(to_sample_dev, n_rays, max_n, nodes_dev, n_selected, n_candidates,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 int mnv_tree_trackers(mnv_tree *h, float **to_split_dev, float **to_sample_dev) {
     if (!h) return MNV_ERR_INVALID;
     if (to_split_dev) *to_split_dev = h->t.split_dev;

@@ -185,8 +185,18 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out);
 void mlp_destroy(MlpModel *m);
 int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim, float *out_dev,
                 int out_stride, cudaStream_t stream);
+int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, int64_t rows,
+                        int in_dim, float *out_dev, int out_stride, cudaStream_t stream);
 double mlp_flops_per_row(const MlpModel *m);
 int mlp_in_dim(const MlpModel *m);
 int mlp_out_dim(const MlpModel *m);
+
+// ---- candidate selection / sub-module dispatch (mnv_select.cu) ------------------
+int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
+                            int *n_selected, int *n_candidates, cudaStream_t stream);
+int select_sample_candidates(const float *to_sample_dev, int64_t P, int max_n, int32_t *nodes_dev,
+                             int *n_selected, int *n_candidates, cudaStream_t stream);
+int query_submodules(MlpModel *const *subs, int n_subs, const int16_t *cluster_dev, const float *rows_dev,
+                     int in_dim, int64_t V, float *out_dev, int out_stride, cudaStream_t stream);
 
 }  // namespace mnv

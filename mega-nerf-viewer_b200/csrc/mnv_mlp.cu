@@ -77,6 +77,7 @@ struct MlpParams {
     const MlpSchedule *__restrict__ sched;
     const float *__restrict__ x;           // [rows][in_dim]
     float *__restrict__ out;               // [rows][out_stride]
+    const int32_t *__restrict__ row_index; // optional: logical row i reads x / writes out at row_index[i]
     int64_t rows;
     int in_dim, out_stride;
     int n_tiles;
@@ -293,8 +294,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
         uint32_t acc_uses = 0;
         const float *bias = p.biases;
         for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int64_t grow = (int64_t) tile * kTileM + row;
-            const bool valid = grow < p.rows;
+            const int64_t lrow = (int64_t) tile * kTileM + row;
+            const bool valid = lrow < p.rows;
+            const int64_t grow = (valid && p.row_index) ? (int64_t) p.row_index[lrow] : lrow;
             // ---- inputs: positional encodings + appearance embedding -> A buffers ----
             float xin[8];
 #pragma unroll
@@ -573,6 +575,11 @@ void mlp_destroy(MlpModel *m) {
 
 int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim, float *out_dev,
                 int out_stride, cudaStream_t stream) {
+    return mlp_forward_indexed(m, x_dev, nullptr, rows, in_dim, out_dev, out_stride, stream);
+}
+
+int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, int64_t rows,
+                        int in_dim, float *out_dev, int out_stride, cudaStream_t stream) {
     if (rows <= 0) return MNV_OK;
     if (in_dim != m->in_dim) {
         set_error("mlp_forward: in_dim %d, model expects %d", in_dim, m->in_dim);
@@ -589,6 +596,7 @@ int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim,
     p.sched = m->sched_dev;
     p.x = x_dev;
     p.out = out_dev;
+    p.row_index = row_index_dev;
     p.rows = rows;
     p.in_dim = in_dim;
     p.out_stride = out_stride;
