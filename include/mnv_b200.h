@@ -144,6 +144,17 @@ const char *mnv_last_error(void); /* thread-local message of the last failure */
 int mnv_device_count(int *count);
 void mnv_render_options_default(mnv_render_options *opt); /* render_options.hpp defaults */
 
+/* ---- device memory helpers for host code that does not include CUDA headers ---------- */
+int mnv_malloc(void **ptr_dev, size_t bytes, int device);
+int mnv_free(void *ptr_dev);
+int mnv_memset(void *ptr_dev, int value, size_t bytes, void *stream);
+int mnv_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int mnv_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream); /* synchronises */
+int mnv_fill_f32(float *ptr_dev, float value, int64_t n, void *stream);
+int mnv_fill_i32(int32_t *ptr_dev, int32_t value, int64_t n, void *stream);
+/* U[0,1) numbers (counter-based hash generator; stands in for torch::rand, cuda_renderer.cpp:250) */
+int mnv_fill_uniform(float *ptr_dev, int64_t n, uint64_t seed, void *stream);
+
 /* ---- tree: N3Tree::move_to_device, src/n3tree/n3tree.cpp:207-246 --------- */
 int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *desc, int64_t max_capacity, int device);
 int mnv_tree_destroy(mnv_tree *tree);
@@ -255,6 +266,11 @@ int mnv_tree_update_samples(mnv_tree *tree, const mnv_render_options *opt, const
  * element.  Fixes child / parent links, compacts every plane in place, capacity -= num_deleted. */
 int mnv_tree_prune(mnv_tree *tree, const uint8_t *to_delete_dev, const int32_t *index_shifts_dev,
                    int first_shift_index, int64_t num_deleted, void *stream);
+
+/* The whole of Impl::prune_tree (cuda_renderer.cpp:343-381): drop every node whose
+ * visited_dev[node] == 0 (node 0 is always kept), then zero visited_dev[1..max_capacity).
+ * *num_deleted_host receives the number of reclaimed nodes (0: "Nothing can be pruned"). */
+int mnv_tree_prune_unvisited(mnv_tree *tree, int32_t *visited_dev, int64_t *num_deleted_host, void *stream);
 
 /* ---- Mega-NeRF MLP: torch::jit::load + Module::forward, cuda_renderer.cpp:165-203,518-543
  * Container attributes grid_dim / min_position / max_position (cluster rule,

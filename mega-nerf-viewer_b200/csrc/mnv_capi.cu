@@ -107,6 +107,41 @@ int mnv_device_count(int *count) {
     return MNV_OK;
 }
 
+int mnv_malloc(void **ptr_dev, size_t bytes, int device) {
+    if (!ptr_dev) return MNV_ERR_INVALID;
+    int rc = check_device(device);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaSetDevice(device));
+    MNV_CUDA(cudaMalloc(ptr_dev, bytes ? bytes : 1));
+    return MNV_OK;
+}
+int mnv_free(void *ptr_dev) {
+    if (ptr_dev) MNV_CUDA(cudaFree(ptr_dev));
+    return MNV_OK;
+}
+int mnv_memset(void *ptr_dev, int value, size_t bytes, void *stream) {
+    MNV_CUDA(cudaMemsetAsync(ptr_dev, value, bytes, static_cast<cudaStream_t>(stream)));
+    return MNV_OK;
+}
+int mnv_memcpy_h2d(void *dst_dev, const void *src_host, size_t bytes, void *stream) {
+    MNV_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return MNV_OK;
+}
+int mnv_memcpy_d2h(void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    MNV_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    MNV_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return MNV_OK;
+}
+int mnv_fill_f32(float *ptr_dev, float value, int64_t n, void *stream) {
+    return fill_f32(ptr_dev, value, n, static_cast<cudaStream_t>(stream));
+}
+int mnv_fill_i32(int32_t *ptr_dev, int32_t value, int64_t n, void *stream) {
+    return fill_i32(ptr_dev, value, n, static_cast<cudaStream_t>(stream));
+}
+int mnv_fill_uniform(float *ptr_dev, int64_t n, uint64_t seed, void *stream) {
+    return fill_uniform(ptr_dev, n, seed, static_cast<cudaStream_t>(stream));
+}
+
 void mnv_render_options_default(mnv_render_options *o) {
     if (!o) return;
     std::memset(o, 0, sizeof(*o));
@@ -511,6 +546,12 @@ int mnv_tree_prune(mnv_tree *h, const uint8_t *to_delete_dev, const int32_t *ind
     MNV_CUDA(cudaSetDevice(h->t.device));
     return refine_prune(h->t, to_delete_dev, index_shifts_dev, first_shift_index, num_deleted,
                         static_cast<cudaStream_t>(stream));
+}
+
+int mnv_tree_prune_unvisited(mnv_tree *h, int32_t *visited_dev, int64_t *num_deleted_host, void *stream) {
+    if (!h || !visited_dev) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return prune_unvisited(h->t, visited_dev, num_deleted_host, static_cast<cudaStream_t>(stream));
 }
 
 int mnv_model_create(mnv_model **out, int n_submodules, const mnv_mlp_desc *descs,

@@ -191,6 +191,11 @@ double mlp_flops_per_row(const MlpModel *m);
 int mlp_in_dim(const MlpModel *m);
 int mlp_out_dim(const MlpModel *m);
 
+int fill_uniform(float *ptr, int64_t n, uint64_t seed, cudaStream_t stream);
+int fill_f32(float *ptr, float v, int64_t n, cudaStream_t stream);
+int fill_i32(int32_t *ptr, int32_t v, int64_t n, cudaStream_t stream);
+int prune_unvisited(DeviceTree &t, int32_t *visited_dev, int64_t *num_deleted, cudaStream_t stream);
+
 // ---- candidate selection / sub-module dispatch (mnv_select.cu) ------------------
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
                             int *n_selected, int *n_candidates, cudaStream_t stream);

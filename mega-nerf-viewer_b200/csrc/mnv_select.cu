@@ -20,6 +20,8 @@
 #include <thrust/binary_search.h>
 #include <thrust/unique.h>
 #include <thrust/transform.h>
+#include <thrust/scan.h>
+#include <thrust/functional.h>
 
 #include <algorithm>
 #include <vector>
@@ -66,7 +68,80 @@ __global__ void write_nodes_kernel(const unsigned long long *ranked, int n, int 
     nodes[2 * i + 1] = (int32_t) (id & 7);
 }
 
+template <typename T>
+__global__ void fill_kernel(T *p, T v, int64_t n) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// splitmix64 finaliser as a counter-based generator: 24 random bits -> [0, 1)
+__global__ void uniform_kernel(float *p, int64_t n, unsigned long long seed) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long) (i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    p[i] = (float) (z >> 40) * (1.0f / 16777216.0f);
+}
+struct NotVisited {
+    const int32_t *visited;
+    __device__ uint8_t operator()(long long i) const { return (i > 0 && visited[i] == 0) ? 1 : 0; }
+};
+
 }  // namespace
+
+int fill_uniform(float *ptr, int64_t n, uint64_t seed, cudaStream_t stream) {
+    if (n <= 0) return MNV_OK;
+    uniform_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(ptr, n, (unsigned long long) seed);
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+int fill_f32(float *ptr, float v, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return MNV_OK;
+    fill_kernel<float><<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(ptr, v, n);
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+int fill_i32(int32_t *ptr, int32_t v, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return MNV_OK;
+    fill_kernel<int32_t><<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(ptr, v, n);
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+
+// Impl::prune_tree, cuda_renderer.cpp:343-381.
+int prune_unvisited(DeviceTree &t, int32_t *visited_dev, int64_t *num_deleted, cudaStream_t stream) {
+    auto pol = thrust::cuda::par.on(stream);
+    const int64_t cap = t.capacity;
+    uint8_t *del = nullptr;
+    int32_t *shifts = nullptr;
+    MNV_CUDA(cudaMalloc(&del, cap));
+    MNV_CUDA(cudaMalloc(&shifts, cap * sizeof(int32_t)));
+    int rc = MNV_OK;
+    int64_t num = 0;
+    try {
+        thrust::device_ptr<uint8_t> d(del);
+        thrust::device_ptr<int32_t> sh(shifts);
+        thrust::transform(pol, thrust::counting_iterator<long long>(0), thrust::counting_iterator<long long>(cap), d,
+                          NotVisited{visited_dev});
+        thrust::inclusive_scan(pol, d, d + cap, sh, thrust::plus<int32_t>());
+        int32_t last = 0;
+        MNV_CUDA(cudaMemcpyAsync(&last, shifts + cap - 1, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        MNV_CUDA(cudaStreamSynchronize(stream));
+        num = last;
+        if (num > 0) rc = refine_prune(t, del, shifts, 0, num, stream);
+        if (rc == MNV_OK && t.max_capacity > 1)  // visit_tracker.slice(0, 1, max).zero_()
+            MNV_CUDA(cudaMemsetAsync(visited_dev + 1, 0, (size_t) (t.max_capacity - 1) * sizeof(int32_t), stream));
+    } catch (const std::exception &e) {
+        set_error("prune_unvisited: %s", e.what());
+        cudaGetLastError();
+        rc = MNV_ERR_CUDA;
+    }
+    cudaFree(del);
+    cudaFree(shifts);
+    if (num_deleted) *num_deleted = num;
+    return rc;
+}
 
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
                             int *n_selected, int *n_candidates, cudaStream_t stream) {

@@ -1,0 +1,204 @@
+#include "n3tree.hpp"
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+
+#include "../../../include/mnv_b200.h"
+#include "npz.hpp"
+
+namespace viewer {
+
+N3Tree::N3Tree() {}
+N3Tree::N3Tree(const std::string &path) { open(path); }
+N3Tree::~N3Tree() {
+    if (device_tree) mnv_tree_destroy(device_tree);
+}
+
+// Keys and conversions of N3Tree::load_npz (src/n3tree/n3tree.cpp:28-205).  Like the
+// reference: a missing file prints a message and leaves the tree empty (:19-22); schema
+// violations throw std::runtime_error (:114,121,180,196,200).  The VQ-compressed variant
+// (quant_colors / quant_map, :109-175) is not supported and is reported as such.
+void N3Tree::open(const std::string &path) {
+    if (!std::ifstream(path)) {
+        std::printf("Can't load because file does not exist: %s\n", path.c_str());
+        return;
+    }
+    npz::Archive z = npz::load(path);
+    auto need = [&](const char *key) -> const npz::Array & {
+        auto it = z.find(key);
+        if (it == z.end()) throw std::runtime_error(std::string("npz key missing: ") + key);
+        return it->second;
+    };
+    {
+        const npz::Array &a = need("data_dim");
+        data_dim = a.word_size == 8 ? (int) *a.data<int64_t>() : (int) *a.data<int32_t>();
+    }
+    {
+        const npz::Array &a = need("data_format");  // '<U*': UCS-4 code points
+        std::string s;
+        if (a.kind == 'U')
+            for (size_t i = 0; i + 3 < a.bytes.size(); i += 4) {
+                if (a.bytes[i] == 0) break;
+                s.push_back((char) a.bytes[i]);
+            }
+        else
+            s.assign(reinterpret_cast<const char *>(a.bytes.data()), a.bytes.size());
+        data_format.parse(s);
+    }
+    scale.shape = offset.shape = {3};
+    scale.v.resize(3);
+    offset.v.resize(3);
+    if (z.count("invradius3")) {
+        const float *p = need("invradius3").data<float>();
+        for (int i = 0; i < 3; ++i) scale.v[i] = p[i];
+    } else {
+        const npz::Array &a = need("invradius");
+        const float s = a.word_size == 8 ? (float) *a.data<double>() : *a.data<float>();
+        scale.v = {s, s, s};
+    }
+    {
+        const float *p = need("offset").data<float>();
+        for (int i = 0; i < 3; ++i) offset.v[i] = p[i];
+    }
+    const npz::Array &ch = need("child");
+    if (ch.shape.size() != 4 || ch.word_size != 4) throw std::runtime_error("child must be int32 [cap,N,N,N]");
+    N = (int) ch.shape[1];
+    if (N != 2) std::printf("WARNING: N != 2 probably doesn't work.\n");
+    N2_ = N * N;
+    N3_ = N * N * N;
+    const int64_t cap = (int64_t) ch.shape[0];
+    child.shape = {cap, N3_};
+    child.v.assign(ch.data<int32_t>(), ch.data<int32_t>() + cap * N3_);
+    const npz::Array &pd = need("parent_depth");
+    if (pd.word_size != 4 || pd.shape.size() != 2 || pd.shape[1] != 2)
+        throw std::runtime_error("parent_depth must be int32 [cap,2]");
+    parent.shape = {(int64_t) pd.shape[0]};
+    parent.v.resize(pd.shape[0]);
+    for (size_t i = 0; i < pd.shape[0]; ++i) parent.v[i] = pd.data<int32_t>()[2 * i];
+    if (z.count("quant_colors"))
+        throw std::runtime_error("VQ-compressed trees (quant_colors/quant_map) are not supported yet");
+    const npz::Array &dn = need("data");
+    if (dn.word_size != 2) throw std::runtime_error("data must be stored in half precision");
+    const int64_t dcap = (int64_t) dn.shape[0];
+    if ((int64_t) dn.num_vals() != dcap * N3_ * data_dim) throw std::runtime_error("data shape does not match data_dim");
+    data.shape = {dcap, N3_, data_dim};
+    data.v.assign(dn.data<uint16_t>(), dn.data<uint16_t>() + dn.num_vals());
+    sample_counts.shape = {dcap, N3_};
+    sample_counts.v.assign((size_t) dcap * N3_, (int16_t) 8);  // n3tree.cpp:191-193
+    if (dcap != parent.size(0)) throw std::runtime_error("data and parent sizes not aligned");
+    if (dcap != child.size(0)) throw std::runtime_error("data and child sizes not aligned");
+    capacity = (int) dcap;
+    std::printf("Data format %s, data size: %d\n", data_format.to_string().c_str(), capacity);
+}
+
+void N3Tree::move_to_device(long max_capacity, bool /*need_parent*/, bool /*need_sample_counts*/) {
+    if (device_tree) {
+        mnv_tree_destroy(device_tree);
+        device_tree = nullptr;
+    }
+    const int64_t cap = child.size(0);  // honours --bounds_only style edits of the host arrays
+    mnv_tree_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.N = N;
+    d.data_dim = data_dim;
+    d.format = data_format.format == DataFormat::SH ? MNV_FORMAT_SH : MNV_FORMAT_RGBA;
+    d.basis_dim = data_format.basis_dim;
+    d.capacity = cap;
+    d.data = data.data_ptr();
+    d.child = child.data_ptr();
+    d.parent = parent.numel() >= cap ? parent.data_ptr() : nullptr;
+    d.sample_counts = sample_counts.numel() >= cap * 8 ? sample_counts.data_ptr() : nullptr;
+    for (int i = 0; i < 3; ++i) {
+        d.scale[i] = scale.v[i];
+        d.offset[i] = offset.v[i];
+    }
+    if (mnv_tree_create(&device_tree, &d, max_capacity, 0) != MNV_OK)
+        throw std::runtime_error(std::string("move_to_device: ") + mnv_last_error());
+    capacity = (int) cap;
+}
+
+void N3Tree::sync_capacity() {
+    if (!device_tree) return;
+    int64_t c = 0, m = 0;
+    mnv_tree_capacity(device_tree, &c, &m);
+    capacity = (int) c;
+}
+
+void N3Tree::download() {
+    if (!device_tree) return;
+    sync_capacity();
+    const int64_t cap = capacity;
+    data.shape = {cap, 8, data_dim};
+    data.v.resize((size_t) cap * 8 * data_dim);
+    child.shape = {cap, 8};
+    child.v.resize((size_t) cap * 8);
+    parent.shape = {cap};
+    parent.v.resize((size_t) cap);
+    sample_counts.shape = {cap, 8};
+    sample_counts.v.resize((size_t) cap * 8);
+    if (mnv_tree_download(device_tree, 0, cap, data.data_ptr(), child.data_ptr(), parent.data_ptr(),
+                          sample_counts.data_ptr()) != MNV_OK)
+        throw std::runtime_error(std::string("download: ") + mnv_last_error());
+}
+
+namespace {
+// 12 edges of an axis-aligned box as line vertices: position(3) colour(3) normal(3)
+// (layout of Mesh.vert, src/n3tree/n3tree.cpp:249-274).
+void push_box(const float bb[6], std::vector<float> &out) {
+    auto vert = [&](int i, int j, int k) {
+        const float v[9] = {bb[i * 3], bb[j * 3 + 1], bb[k * 3 + 2], 0, 0, 0, 0, 0, 1};
+        out.insert(out.end(), v, v + 9);
+    };
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            vert(0, i, j);
+            vert(1, i, j);
+            vert(i, 0, j);
+            vert(i, 1, j);
+            vert(i, j, 0);
+            vert(i, j, 1);
+        }
+}
+void wire_rec(const N3Tree &t, int32_t node, size_t xi, size_t yi, size_t zi, int depth, size_t grid,
+              int max_depth, std::vector<float> &out) {
+    int cnt = 0;
+    for (size_t i = xi * 2; i < (xi + 1) * 2; ++i)
+        for (size_t j = yi * 2; j < (yi + 1) * 2; ++j)
+            for (size_t k = zi * 2; k < (zi + 1) * 2; ++k, ++cnt) {
+                const int32_t c = t.child.v[(size_t) node * 8 + cnt];
+                if (c == 0 || depth >= max_depth) {
+                    const size_t ijk[3] = {i, j, k};
+                    float bb[6];
+                    for (int a = 0; a < 3; ++a) {
+                        bb[a] = ((float) ijk[a] / grid - t.offset.v[a]) / t.scale.v[a];
+                        bb[a + 3] = ((float) (ijk[a] + 1) / grid - t.offset.v[a]) / t.scale.v[a];
+                    }
+                    push_box(bb, out);
+                } else {
+                    wire_rec(t, node + c, i, j, k, depth + 1, grid * 2, max_depth, out);
+                }
+            }
+}
+}  // namespace
+
+std::vector<float> N3Tree::gen_wireframe(int max_depth) const {
+    std::vector<float> verts;
+    if (N == 2 && child.numel() >= 8) wire_rec(*this, 0, 0, 0, 0, 0, (size_t) N, max_depth, verts);
+    return verts;
+}
+
+int64_t N3Tree::pack_index(int nd, int i, int j, int k) { return (int64_t) nd * N3_ + i * N2_ + j * N + k; }
+
+std::tuple<int, int, int, int> N3Tree::unpack_index(int64_t packed) {
+    const int k = (int) (packed % N);
+    packed /= N;
+    const int j = (int) (packed % N);
+    packed /= N;
+    const int i = (int) (packed % N);
+    packed /= N;
+    return std::tuple<int, int, int, int>{(int) packed, i, j, k};
+}
+
+}  // namespace viewer

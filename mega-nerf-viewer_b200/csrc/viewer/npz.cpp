@@ -1,0 +1,166 @@
+#include "npz.hpp"
+
+#include <zlib.h>
+
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+
+namespace viewer::npz {
+namespace {
+
+uint16_t rd16(const uint8_t *p) { return (uint16_t) (p[0] | (p[1] << 8)); }
+uint32_t rd32(const uint8_t *p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t) p[3] << 24); }
+uint64_t rd64(const uint8_t *p) { return (uint64_t) rd32(p) | ((uint64_t) rd32(p + 4) << 32); }
+
+[[noreturn]] void fail(const std::string &m) { throw std::runtime_error("npz: " + m); }
+
+std::vector<uint8_t> inflate_raw(const uint8_t *src, size_t n_src, size_t n_dst) {
+    std::vector<uint8_t> out(n_dst);
+    z_stream zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -MAX_WBITS) != Z_OK) fail("inflateInit2");
+    size_t done_in = 0, done_out = 0;
+    int rc = Z_OK;
+    while (rc != Z_STREAM_END && done_out < n_dst) {  // zlib counters are 32-bit: feed in slices
+        const size_t in_now = std::min<size_t>(n_src - done_in, 1u << 30);
+        const size_t out_now = std::min<size_t>(n_dst - done_out, 1u << 30);
+        zs.next_in = const_cast<Bytef *>(src + done_in);
+        zs.avail_in = (uInt) in_now;
+        zs.next_out = out.data() + done_out;
+        zs.avail_out = (uInt) out_now;
+        rc = inflate(&zs, Z_NO_FLUSH);
+        if (rc != Z_OK && rc != Z_STREAM_END && rc != Z_BUF_ERROR) {
+            inflateEnd(&zs);
+            fail("inflate failed");
+        }
+        done_in += in_now - zs.avail_in;
+        done_out += out_now - zs.avail_out;
+        if (rc == Z_BUF_ERROR && zs.avail_in == 0 && done_in >= n_src) break;
+    }
+    inflateEnd(&zs);
+    if (done_out != n_dst) fail("inflate: short output");
+    return out;
+}
+
+}  // namespace
+
+Array parse_npy(const uint8_t *buf, size_t len) {
+    if (len < 10 || std::memcmp(buf, "\x93NUMPY", 6) != 0) fail("bad npy magic");
+    const int major = buf[6];
+    size_t hlen, hoff;
+    if (major == 1) {
+        hlen = rd16(buf + 8);
+        hoff = 10;
+    } else {
+        if (len < 12) fail("truncated npy header");
+        hlen = rd32(buf + 8);
+        hoff = 12;
+    }
+    if (hoff + hlen > len) fail("truncated npy header");
+    const std::string h(reinterpret_cast<const char *>(buf + hoff), hlen);
+    Array a;
+    // 'descr': '<f4'
+    size_t p = h.find("'descr'");
+    if (p == std::string::npos) fail("npy header without descr");
+    p = h.find('\'', h.find(':', p));
+    const size_t q = h.find('\'', p + 1);
+    const std::string descr = h.substr(p + 1, q - p - 1);
+    if (descr.size() < 2) fail("bad descr " + descr);
+    size_t t = (descr[0] == '<' || descr[0] == '>' || descr[0] == '|' || descr[0] == '=') ? 1 : 0;
+    if (descr[0] == '>') fail("big-endian arrays are not supported");
+    a.kind = descr[t];
+    a.word_size = (size_t) std::atoi(descr.c_str() + t + 1);
+    if (a.kind == 'U') a.word_size *= 4;  // UCS-4 (the reference patches cnpy the same way, cnpy.cpp:113)
+    if (a.kind == '?') a.word_size = 1;
+    // 'fortran_order': False
+    p = h.find("'fortran_order'");
+    a.fortran_order = p != std::string::npos && h.compare(h.find(':', p) + 1 + (h[h.find(':', p) + 1] == ' '), 4, "True") == 0;
+    // 'shape': (a, b, ...)
+    p = h.find("'shape'");
+    if (p == std::string::npos) fail("npy header without shape");
+    p = h.find('(', p);
+    const size_t e = h.find(')', p);
+    std::string dims = h.substr(p + 1, e - p - 1);
+    size_t pos = 0;
+    while (pos < dims.size()) {
+        while (pos < dims.size() && (dims[pos] == ' ' || dims[pos] == ',')) ++pos;
+        if (pos >= dims.size()) break;
+        size_t end = pos;
+        while (end < dims.size() && std::isdigit(static_cast<unsigned char>(dims[end]))) ++end;
+        if (end == pos) fail("bad shape " + dims);
+        a.shape.push_back((size_t) std::stoull(dims.substr(pos, end - pos)));  // 64-bit dims
+        pos = end;
+    }
+    const size_t nbytes = a.num_vals() * a.word_size;
+    if (hoff + hlen + nbytes > len) fail("npy payload shorter than its shape");
+    a.bytes.assign(buf + hoff + hlen, buf + hoff + hlen + nbytes);
+    return a;
+}
+
+Archive load(const std::string &path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) fail("cannot open " + path);
+    const size_t size = (size_t) f.tellg();
+    std::vector<uint8_t> buf(size);
+    f.seekg(0);
+    f.read(reinterpret_cast<char *>(buf.data()), (std::streamsize) size);
+    if (!f) fail("short read " + path);
+    // end of central directory (search backwards over a possible comment)
+    if (size < 22) fail("not a zip file");
+    size_t eocd = std::string::npos;
+    for (size_t i = size - 22;; --i) {
+        if (rd32(&buf[i]) == 0x06054b50) {
+            eocd = i;
+            break;
+        }
+        if (i == 0 || size - i > 22 + 65535) break;
+    }
+    if (eocd == std::string::npos) fail("no end-of-central-directory record");
+    uint64_t n_entries = rd16(&buf[eocd + 10]), cd_off = rd32(&buf[eocd + 16]);
+    if (eocd >= 20 && rd32(&buf[eocd - 20]) == 0x07064b50) {  // ZIP64 locator
+        const uint64_t z64 = rd64(&buf[eocd - 20 + 8]);
+        if (z64 + 56 > size || rd32(&buf[z64]) != 0x06064b50) fail("bad ZIP64 end record");
+        n_entries = rd64(&buf[z64 + 32]);
+        cd_off = rd64(&buf[z64 + 48]);
+    }
+    Archive out;
+    size_t p = (size_t) cd_off;
+    for (uint64_t i = 0; i < n_entries; ++i) {
+        if (p + 46 > size || rd32(&buf[p]) != 0x02014b50) fail("bad central directory entry");
+        const uint16_t method = rd16(&buf[p + 10]);
+        uint64_t csize = rd32(&buf[p + 20]), usize = rd32(&buf[p + 24]);
+        const uint16_t nlen = rd16(&buf[p + 28]), xlen = rd16(&buf[p + 30]), clen = rd16(&buf[p + 32]);
+        uint64_t lho = rd32(&buf[p + 42]);
+        std::string name(reinterpret_cast<const char *>(&buf[p + 46]), nlen);
+        // ZIP64 extended information (header id 0x0001): present fields in fixed order
+        size_t x = p + 46 + nlen;
+        const size_t xend = x + xlen;
+        while (x + 4 <= xend) {
+            const uint16_t id = rd16(&buf[x]), sz = rd16(&buf[x + 2]);
+            if (id == 0x0001) {
+                size_t y = x + 4;
+                if (usize == 0xffffffffu) { usize = rd64(&buf[y]); y += 8; }
+                if (csize == 0xffffffffu) { csize = rd64(&buf[y]); y += 8; }
+                if (lho == 0xffffffffu) { lho = rd64(&buf[y]); }
+            }
+            x += 4 + sz;
+        }
+        p = xend + clen;
+        if (lho + 30 > size || rd32(&buf[lho]) != 0x04034b50) fail("bad local header for " + name);
+        const size_t data = (size_t) lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
+        if (data + csize > size) fail("member " + name + " runs past the end of the file");
+        if (name.size() > 4 && name.compare(name.size() - 4, 4, ".npy") == 0) name.resize(name.size() - 4);
+        if (method == 0) {
+            out[name] = parse_npy(&buf[data], (size_t) usize);
+        } else if (method == 8) {
+            const std::vector<uint8_t> raw = inflate_raw(&buf[data], (size_t) csize, (size_t) usize);
+            out[name] = parse_npy(raw.data(), raw.size());
+        } else {
+            fail("unsupported compression method in " + name);
+        }
+    }
+    return out;
+}
+
+}  // namespace viewer::npz

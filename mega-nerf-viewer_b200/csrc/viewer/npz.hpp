@@ -1,0 +1,35 @@
+// Minimal .npy/.npz reader for the keys N3Tree::load_npz reads (the reference vendors a
+// patched cnpy, 3rdparty/cnpy/cnpy.cpp:303-369).  Entries are located through the ZIP
+// central directory (so data descriptors and ZIP64 sizes are handled uniformly), stored
+// and raw-deflate members are supported, npy format versions 1-3.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace viewer::npz {
+
+struct Array {
+    std::vector<size_t> shape;
+    size_t word_size = 0;  // bytes per element ('U' = 4 per character)
+    char kind = 0;         // numpy type char: f, i, u, b, U, ...
+    bool fortran_order = false;
+    std::vector<uint8_t> bytes;
+
+    size_t num_vals() const {
+        size_t n = 1;
+        for (size_t s : shape) n *= s;
+        return n;
+    }
+    template <typename T>
+    const T *data() const { return reinterpret_cast<const T *>(bytes.data()); }
+};
+
+using Archive = std::map<std::string, Array>;
+
+// Throws std::runtime_error on malformed input.
+Archive load(const std::string &path);
+Array parse_npy(const uint8_t *buf, size_t len);
+
+}  // namespace viewer::npz
