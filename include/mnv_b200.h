@@ -154,6 +154,12 @@ int mnv_fill_f32(float *ptr_dev, float value, int64_t n, void *stream);
 int mnv_fill_i32(int32_t *ptr_dev, int32_t value, int64_t n, void *stream);
 /* U[0,1) numbers (counter-based hash generator; stands in for torch::rand, cuda_renderer.cpp:250) */
 int mnv_fill_uniform(float *ptr_dev, int64_t n, uint64_t seed, void *stream);
+int mnv_malloc_host(void **ptr_host, size_t bytes); /* pinned (cudaHostAlloc) */
+int mnv_free_host(void *ptr_host);
+int mnv_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int mnv_stream_create(void **stream, int device); /* non-blocking cudaStream_t */
+int mnv_stream_destroy(void *stream);
+int mnv_stream_synchronize(void *stream);
 
 /* ---- tree: N3Tree::move_to_device, src/n3tree/n3tree.cpp:207-246 --------- */
 int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *desc, int64_t max_capacity, int device);

@@ -514,3 +514,49 @@ class MlpModel:
         _check(lib().mnv_mlp_forward(self._h, submodule, _dptr(x), x.shape[0], x.shape[1], _dptr(out),
                                      out.stride(0), _stream_ptr(stream)))
         return out
+
+
+def save_model_container(path: str, submodules, grid_dim=(1, 1), min_position=(0, 0, 0),
+                         max_position=(1, 1, 1), centroids=None, need_viewdir: bool | None = None,
+                         need_appearance_embedding: bool | None = None, compressed: bool = False) -> None:
+    """Write the Mega-NeRF sub-module container the C++ viewer::VolumeRenderer::load_model reads
+    (csrc/viewer/model.hpp): the attributes the reference pulls out of its TorchScript archive
+    (cuda_renderer.cpp:518-543) plus the flat fp32 weights of every sub_module_<i>.
+    `submodules`: the dicts MlpModel takes (tests/mlp_reference.MegaNerfMLP.export())."""
+    n = len(submodules)
+    if centroids is None:
+        centroids = np.zeros((n, 3), np.float32)
+    if need_viewdir is None:
+        need_viewdir = bool(submodules[0].get("need_viewdir", False))
+    if need_appearance_embedding is None:
+        need_appearance_embedding = submodules[0].get("embedding") is not None
+    arrays = dict(grid_dim=np.asarray(grid_dim, np.int32), min_position=np.asarray(min_position, np.float32),
+                  max_position=np.asarray(max_position, np.float32),
+                  centroids=np.asarray(centroids, np.float32).reshape(n, 3),
+                  need_viewdir=np.array(bool(need_viewdir)),
+                  need_appearance_embedding=np.array(bool(need_appearance_embedding)))
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    for i, sm in enumerate(submodules):
+        p = f"sub_module_{i}/"
+        nt = len(sm["trunk_w"])
+        arrays[p + "config"] = np.asarray([nt, sm.get("skip_layer", 4), sm.get("pe_xyz_freqs", 12),
+                                           sm.get("pe_dir_freqs", 4), sm.get("sigma_activation", 1)], np.int32)
+        for l in range(nt):
+            arrays[p + f"trunk_w_{l}"] = f(sm["trunk_w"][l])
+            arrays[p + f"trunk_b_{l}"] = f(sm["trunk_b"][l])
+        for k in ("sigma_w", "sigma_b", "final_w", "final_b", "head1_w", "head1_b", "head2_w", "head2_b"):
+            arrays[p + k] = f(sm[k])
+        if sm.get("embedding") is not None:
+            arrays[p + "embedding"] = f(sm["embedding"])
+    (np.savez_compressed if compressed else np.savez)(path, **arrays)
+
+
+HEADLESS_BIN = os.path.join(_HERE, "bin", "mnv_headless")
+
+
+def bytes_checksum(a: np.ndarray) -> str:
+    """The 64-bit position-weighted byte sum `mnv_headless --selftest-*` prints."""
+    b = np.ascontiguousarray(a).view(np.uint8).ravel().astype(np.uint64)
+    i = np.arange(b.size, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return f"{int(((b + np.uint64(1)) * (i * np.uint64(2654435761) + np.uint64(1))).sum(dtype=np.uint64)):016x}"

@@ -142,6 +142,40 @@ int mnv_fill_uniform(float *ptr_dev, int64_t n, uint64_t seed, void *stream) {
     return fill_uniform(ptr_dev, n, seed, static_cast<cudaStream_t>(stream));
 }
 
+int mnv_malloc_host(void **ptr_host, size_t bytes) {
+    if (!ptr_host) return MNV_ERR_INVALID;
+    int rc = check_device(0);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaHostAlloc(ptr_host, bytes ? bytes : 1, cudaHostAllocDefault));
+    return MNV_OK;
+}
+int mnv_free_host(void *ptr_host) {
+    if (ptr_host) MNV_CUDA(cudaFreeHost(ptr_host));
+    return MNV_OK;
+}
+int mnv_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    MNV_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return MNV_OK;
+}
+int mnv_stream_create(void **stream, int device) {
+    if (!stream) return MNV_ERR_INVALID;
+    int rc = check_device(device);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    MNV_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return MNV_OK;
+}
+int mnv_stream_destroy(void *stream) {
+    if (stream) MNV_CUDA(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+    return MNV_OK;
+}
+int mnv_stream_synchronize(void *stream) {
+    MNV_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return MNV_OK;
+}
+
 void mnv_render_options_default(mnv_render_options *o) {
     if (!o) return;
     std::memset(o, 0, sizeof(*o));

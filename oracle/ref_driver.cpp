@@ -398,4 +398,38 @@ int ref_render_voxels_logged(void *ctx, int w, int h, const float *intr, const f
 }
 #endif
 
+// Camera parity: runs the script of `mnv_headless --selftest-camera` on the reference's own
+// viewer::Camera (src/camera.cpp) and dumps, per step, transform (12), K (16), w2c (16),
+// fx, fy, cx, cy -> out[3][48].  Needs a CUDA device (the constructor cudaMallocs).
+int ref_camera_trace(int w, int h, float fx, float *out) {
+    viewer::Camera c(w, h, fx);
+    auto dump = [&](int step) {
+        float *o = out + step * 48;
+        int k = 0;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 3; ++j) o[k++] = c.transform[i][j];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) o[k++] = c.K[i][j];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) o[k++] = c.w2c[i][j];
+        o[k++] = c.fx;
+        o[k++] = c.fy;
+        o[k++] = c.cx;
+        o[k++] = c.cy;
+    };
+    dump(0);
+    c.begin_drag(100.f, 120.f, false, false);
+    c.drag_update(260.f, 90.f);
+    c.end_drag();
+    c._update();
+    dump(1);
+    c.begin_drag(10.f, 10.f, true, false);
+    c.drag_update(40.f, 70.f);
+    c.end_drag();
+    c.move(glm::vec3(0.1f, -0.2f, 0.3f));
+    c._update();
+    dump(2);
+    return 0;
+}
+
 }  // extern "C"
