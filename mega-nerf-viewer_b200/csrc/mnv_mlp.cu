@@ -9,20 +9,32 @@
 // feature Linear 256 -> 256; head Linear(256 [+27 dir PE] [+48 appearance]) -> 128 +
 // ReLU; Linear 128 -> 3*basis.  Output row = [rgb / SH coefficients, sigma].
 //
-// One CTA owns a 128-row tile and keeps its activations on chip across all 11
-// GEMMs:  A (activations, bf16) lives in shared memory in the UMMA K-major
-// no-swizzle core-matrix layout, B (weights, bf16, pre-packed on the host into the
-// same layout) is streamed from L2 by 1-D bulk TMA copies (cp.async.bulk ->
-// UBLKCP) through a 3-stage mbarrier ring, D accumulates in TMEM (128 lanes x
-// N<=256 fp32 columns) via tcgen05.mma issued by one thread, and the epilogue
-// warps read D back with tcgen05.ld, add bias, apply ReLU, round to bf16 and write
-// the next layer's A operand in place.
-//   warps 0-3 : positional encoding, epilogues (warp w owns TMEM lanes 32w..32w+31)
-//   warp  4   : TMA producer (one elected lane)
-//   warp  5   : TMEM allocation + MMA issue (one elected lane)
+// One CTA owns TWO 128-row tiles and ping-pongs them through the 11 GEMMs so that the
+// tensor pipe works on one tile while the epilogue warps drain the other:
+//     tensor pipe : T0.L0  T1.L0  T0.L1  T1.L1  T0.L2 ...
+//     epilogue    :        T0.L0  T1.L0  T0.L1  T1.L1 ...
+// A (activations, bf16) lives in shared memory in the UMMA K-major no-swizzle core-matrix
+// layout and is rewritten in place by the epilogue; B (weights, bf16, pre-packed on the
+// host into the same layout, 16 K-columns = 8 KiB per chunk) is streamed from L2 by 1-D
+// bulk TMA copies (cp.async.bulk -> UBLKCP) through a 5-stage mbarrier ring; D accumulates
+// in TMEM (2 x 256 fp32 columns = all 512) via tcgen05.mma issued by one thread (M=128,
+// N<=256, K=16: 128 clk each, measured); the epilogue reads D back with tcgen05.ld, applies
+// ReLU while packing to bf16 (cvt.rn.relu.bf16x2.f32) and writes the next layer's A operand.
+//   warps 0-7 : epilogue of whichever tile completed — warp w owns TMEM lanes
+//               32(w%4)..+31 (the hardware's lane-quarter rule) and column half w/4;
+//               also the positional encodings of the next 256 rows
+//   warp  8   : TMA producer (one elected lane)
+//   warp  9   : TMEM allocation + MMA issue (one elected lane)
+// Biases ride in the GEMM: the PE operand carries two columns of ones, the weights there
+// hold bf16 hi + lo parts of the fp32 bias (error <= 2^-17 |b|), so the epilogue is
+// load -> convert -> store.  The appearance embedding enters head 1 as a per-index fp32
+// bias row (W_app . emb[i] + b, tabulated at model load with bf16-rounded operands)
+// instead of 48 more K columns.
 #include <cuda_bf16.h>
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -31,38 +43,41 @@
 namespace mnv {
 namespace {
 
-constexpr int kMlpThreads = 192;
+constexpr int kMlpThreads = 320;
+constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
-constexpr int kStages = 3;
-constexpr int kChunkK = 64;
+constexpr int kTiles = 2;  // row tiles per CTA
+constexpr int kStages = 5;
+constexpr int kChunkK = 16;
 constexpr int kMaxN = 256;
-constexpr int kStageBytes = kMaxN * kChunkK * 2;  // 32 KiB
-constexpr int kActK = 256, kSideK = 80;
-constexpr int kActBytes = kTileM * kActK * 2;    // 64 KiB
-constexpr int kSideBytes = kTileM * kSideK * 2;  // 20 KiB
-constexpr int kActSBO = (kActK / 8) * 128, kSideSBO = (kSideK / 8) * 128;
-constexpr int kTmemCols = 256;
-constexpr int kMaxLayers = 16, kMaxChunks = 64;
+constexpr int kStageBytes = kMaxN * kChunkK * 2;  // 8 KiB
+constexpr int kActK = 256, kPeK = 80, kDirK = 32;
+constexpr int kActBytes = kTileM * kActK * 2;  // 64 KiB
+constexpr int kPeBytes = kTileM * kPeK * 2;    // 20 KiB
+constexpr int kDirBytes = kTileM * kDirK * 2;  // 8 KiB
+constexpr int kActSBO = (kActK / 8) * 128, kPeSBO = (kPeK / 8) * 128, kDirSBO = (kDirK / 8) * 128;
+constexpr int kTmemCols = 512;
+constexpr int kMaxLayers = 16, kMaxChunks = 224;  // smem copy of the schedule: 12 B per chunk
 
-enum { kEpiReluAct = 0, kEpiReluActSigma = 1, kEpiLinearAct = 2, kEpiOut = 3 };
-enum { kSrcAct = 0, kSrcPE = 1, kSrcAux = 2 };
+enum { kEpiReluAct = 0, kEpiReluActSigma = 1, kEpiLinearAct = 2, kEpiOut = 3, kEpiReluActApp = 4 };
+enum { kSrcAct = 0, kSrcPE = 1, kSrcDir = 2 };
 
 struct ChunkDesc {
     uint32_t gmem_off;  // byte offset of the packed chunk in the weight blob
-    uint32_t bytes;
-    uint16_t n;     // padded N of the layer
-    uint16_t kc;    // K of this chunk (multiple of 16, <= kChunkK)
-    uint16_t a_src; // which A buffer
-    uint16_t a_k0;  // first K column inside that buffer
-    uint8_t first, last, layer, pad;
+    uint16_t n;         // padded N of the layer
+    uint16_t a_src;     // which A buffer
+    uint16_t a_k0;      // first K column inside that buffer
+    uint16_t pad;
 };
 
 struct LayerDesc {
-    uint16_t n;       // padded N
-    uint16_t n_real;  // real output width
-    uint32_t bias_off;  // float offset into the bias blob
+    uint16_t n;        // padded N (multiple of 32)
+    uint16_t n_real;   // real output width
+    uint16_t chunk_begin, chunk_end;
     uint32_t epilogue;
+    uint32_t bias_off;  // float offset of an fp32 bias row the epilogue adds; kNoBias: the bias rides in the GEMM
 };
+constexpr uint32_t kNoBias = 0xffffffffu;
 
 struct MlpSchedule {
     int n_layers, n_chunks;
@@ -71,21 +86,22 @@ struct MlpSchedule {
 };
 
 struct MlpParams {
-    const uint8_t *__restrict__ weights;   // packed bf16 chunks
-    const float *__restrict__ biases;      // fp32 biases, then sigma head weights + bias
-    const float *__restrict__ embedding;   // [n_appearance][app_dim] fp32 (may be null)
+    const uint8_t *__restrict__ weights;   // packed bf16 chunks, schedule order
+    const float *__restrict__ sigma_w;     // [256] sigma head weights, then its bias
+    const float *__restrict__ biases;      // fp32 bias rows added by the epilogue (layers with bias_off != kNoBias)
+    const float *__restrict__ app_bias;    // [n_appearance][head_n] head-1 bias rows incl. appearance term (may be null)
     const MlpSchedule *__restrict__ sched;
     const float *__restrict__ x;           // [rows][in_dim]
     float *__restrict__ out;               // [rows][out_stride]
     const int32_t *__restrict__ row_index; // optional: logical row i reads x / writes out at row_index[i]
     int64_t rows;
     int in_dim, out_stride;
-    int n_tiles;
-    int pe_xyz_freqs, pe_dir_freqs;
-    int need_viewdir, app_dim, n_appearance, app_col;  // app_col: column of x holding the index (-1: none)
-    int sigma_w_off, sigma_b_off;  // float offsets into biases
+    int n_groups;  // groups of kTiles * kTileM rows
+    int pe_xyz_freqs, pe_dir_freqs, ones_col;
+    int need_viewdir, n_appearance, app_col, head_n;  // app_col: column of x holding the index (-1: none)
     int sigma_activation;          // 0 = ReLU, 1 = softplus
     int out_real;                  // 3 * basis
+    long long *dbg;                // dev: per-CTA cycle counters (MNV_MLP_DEBUG=1), else null
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -161,6 +177,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+// asynchronous: the registers are valid after tmem_wait()
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -173,12 +190,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
               "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
               "=r"(r[31])
             : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&v);
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {  // a -> low half
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {  // max(x, 0) fused into the conversion
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
 }
 
 // Byte offset of element (row, k) in an A buffer with K-major core-matrix layout.
@@ -186,212 +209,327 @@ __device__ __forceinline__ uint32_t a_off(int row, int k, int sbo) {
     return (uint32_t) ((row >> 3) * sbo + (k >> 3) * 128 + (row & 7) * 16 + (k & 7) * 2);
 }
 
-// Positional encoding of v[3] with `freqs` octaves into `feat` (3 + 6*freqs values):
-// [v, sin(2^0 v), cos(2^0 v), sin(2^1 v), cos(2^1 v), ...] (NeRF "Embedding", include-input).
-__device__ __forceinline__ void write_pe(uint8_t *buf, int row, int k0, int sbo, const float *v,
-                                         int freqs, int k_pad_end) {
-    auto put = [&](int k, float val) {
-        *reinterpret_cast<__nv_bfloat16 *>(buf + a_off(row, k, sbo)) = __float2bfloat16_rn(val);
-    };
-    int k = k0;
-    for (int c = 0; c < 3; ++c) put(k++, v[c]);
-    float f = 1.f;
-    for (int o = 0; o < freqs; ++o) {
-        float s[3], cs[3];
-        for (int c = 0; c < 3; ++c) sincosf(f * v[c], &s[c], &cs[c]);
-        for (int c = 0; c < 3; ++c) put(k++, s[c]);
-        for (int c = 0; c < 3; ++c) put(k++, cs[c]);
+// sin / cos of a = 2^o * v: two-constant Cody-Waite reduction to [-pi, pi] (a is exact, the
+// reduction error is ~1e-11 * |a|), then the SFU approximations (abs error 2^-21.4 there) —
+// two orders below the bf16 rounding the value goes through next.
+__device__ __forceinline__ void sincos_reduced(float a, float &s, float &c) {
+    const float k = rintf(a * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, a);
+    r = fmaf(k, 1.7484555e-07f, r);
+    s = __sinf(r);
+    c = __cosf(r);
+}
+
+__device__ __forceinline__ void put_bf16(uint8_t *buf, int row, int k, int sbo, float val) {
+    *reinterpret_cast<__nv_bfloat16 *>(buf + a_off(row, k, sbo)) = __float2bfloat16_rn(val);
+}
+
+// Octaves [o0, o1) of the positional encoding of v[3] (NeRF "Embedding", include-input:
+// [v, sin(2^0 v), cos(2^0 v), sin(2^1 v), cos(2^1 v), ...]) into columns 3 + 6*o ... of `buf`.
+__device__ __forceinline__ void write_pe_octaves(uint8_t *buf, int row, int sbo, const float *v, int o0, int o1) {
+    float f = exp2f((float) o0);
+    for (int o = o0; o < o1; ++o) {
+        const int k = 3 + 6 * o;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float sn, cs;
+            sincos_reduced(f * v[c], sn, cs);
+            put_bf16(buf, row, k + c, sbo, sn);
+            put_bf16(buf, row, k + 3 + c, sbo, cs);
+        }
         f *= 2.f;
     }
-    for (; k < k_pad_end; ++k) put(k, 0.f);
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *s_act = smem;
-    uint8_t *s_pe = s_act + kActBytes;
-    uint8_t *s_aux = s_pe + kSideBytes;
-    uint8_t *s_stage = s_aux + kSideBytes;
+    uint8_t *s_act = smem;                           // [kTiles][kActBytes]
+    uint8_t *s_pe = s_act + kTiles * kActBytes;      // [kTiles][kPeBytes]
+    uint8_t *s_dir = s_pe + kTiles * kPeBytes;       // [kTiles][kDirBytes]
+    uint8_t *s_stage = s_dir + kTiles * kDirBytes;   // [kStages][kStageBytes]
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_stage + kStages * kStageBytes);
-    uint64_t *bar_full = bars;                 // [kStages] weights landed
-    uint64_t *bar_empty = bars + kStages;      // [kStages] weights consumed
-    uint64_t *bar_acc = bars + 2 * kStages;    // accumulator of the current layer complete
-    uint64_t *bar_act = bars + 2 * kStages + 1;  // A operand of the next layer written (128 arrivals)
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2);
+    uint64_t *bar_full = bars;                       // [kStages] weights landed
+    uint64_t *bar_empty = bars + kStages;            // [kStages] weights consumed
+    uint64_t *bar_acc = bars + 2 * kStages;          // [kTiles] accumulator of the current layer complete
+    uint64_t *bar_act = bars + 2 * kStages + kTiles; // [kTiles] A operand of the next layer written (256 arrivals)
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kTiles);
+    // issuer-side schedule, 3 words per chunk: low word of tile 0's A descriptor;
+    // (tile stride >> 4) | (SBO >> 4) << 16; instruction descriptor.  Then one word per layer:
+    // chunk_begin | chunk_end << 16.
+    uint32_t *s_sched = s_tmem + 4;
+    uint32_t *s_layer = s_sched + 3 * kMaxChunks;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MlpSchedule &S = *p.sched;
+    const int n_layers = S.n_layers;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + s, 1);
             mbar_init(bar_empty + s, 1);
         }
-        mbar_init(bar_acc, 1);
-        mbar_init(bar_act, kTileM);
+        for (int t = 0; t < kTiles; ++t) {
+            mbar_init(bar_acc + t, 1);
+            mbar_init(bar_act + t, kEpiThreads);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                              smem_u32(s_tmem)),
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    for (int c = threadIdx.x; c < S.n_chunks; c += kMlpThreads) {
+        const ChunkDesc cd = S.chunks[c];
+        const uint8_t *abuf = cd.a_src == kSrcAct ? s_act : (cd.a_src == kSrcPE ? s_pe : s_dir);
+        const uint32_t sbo = cd.a_src == kSrcAct ? kActSBO : (cd.a_src == kSrcPE ? kPeSBO : kDirSBO);
+        const uint32_t stride = cd.a_src == kSrcAct ? kActBytes : (cd.a_src == kSrcPE ? kPeBytes : kDirBytes);
+        s_sched[3 * c + 0] = (((smem_u32(abuf) + (cd.a_k0 >> 3) * 128) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
+        s_sched[3 * c + 1] = (stride >> 4) | ((sbo >> 4) << 16);
+        s_sched[3 * c + 2] = umma_idesc(kTileM, cd.n);
+    }
+    if (threadIdx.x < n_layers)
+        s_layer[threadIdx.x] = (uint32_t) S.layers[threadIdx.x].chunk_begin | ((uint32_t) S.layers[threadIdx.x].chunk_end << 16);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================== TMA producer =====================
+        // every layer's chunks are streamed twice in a row (tile 0, then tile 1): the second pass hits L2
         if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < S.n_chunks; ++c, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(bar_empty + s, ((it / kStages) & 1) ^ 1);
-                    const ChunkDesc cd = S.chunks[c];
-                    mbar_expect_tx(bar_full + s, cd.bytes);
-                    tma_bulk_g2s(s_stage + s * kStageBytes, p.weights + cd.gmem_off, cd.bytes,
-                                 bar_full + s);
+            uint32_t s = 0, ph = 1;
+            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+                const uint8_t *layer_src = p.weights;
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint32_t lw = s_layer[l];
+                    const uint8_t *src = layer_src;
+                    for (int t = 0; t < kTiles; ++t) {
+                        src = layer_src;
+                        for (uint32_t c = lw & 0xffffu; c < (lw >> 16); ++c) {
+                            const uint32_t bytes = ((s_sched[3 * c + 2] >> 17) & 0x3fu) * (8u * kChunkK * 2u);  // N * 16 * 2
+                            const long long t0 = p.dbg ? clock64() : 0;
+                            mbar_wait(bar_empty + s, ph);
+                            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += clock64() - t0;
+                            mbar_expect_tx(bar_full + s, bytes);
+                            tma_bulk_g2s(s_stage + s * kStageBytes, src, bytes, bar_full + s);
+                            src += bytes;
+                            if (++s == kStages) {
+                                s = 0;
+                                ph ^= 1;
+                            }
+                        }
+                    }
+                    layer_src = src;
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================== MMA issuer =====================
+        // One thread feeds the tensor pipe: everything per chunk comes from the smem schedule
+        // (3 LDS), descriptors are integer adds — the loop must stay well under the 128 clk an
+        // M=128 x N=256 x K=16 MMA takes.
         if (lane == 0) {
-            uint32_t it = 0, act_uses = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int c = 0; c < S.n_chunks; ++c, ++it) {
-                    const ChunkDesc cd = S.chunks[c];
-                    if (cd.first) {  // A operand of this layer ready, TMEM drained
-                        mbar_wait(bar_act, act_uses & 1);
-                        ++act_uses;
-                        tc_fence_after();
+            const uint32_t b_lo0 = ((smem_u32(s_stage) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
+            const uint32_t b_hi = ((kChunkK / 8 * 128u) >> 4) | (1u << 14);
+            uint32_t s = 0, ph = 0, act_ph = 0;
+            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint32_t lw = s_layer[l];
+                    for (int t = 0; t < kTiles; ++t) {
+                        long long t0 = p.dbg ? clock64() : 0;
+                        mbar_wait(bar_act + t, act_ph);  // A operand of tile t ready, its accumulator drained
+                        if (p.dbg) p.dbg[blockIdx.x * 8 + 1] += clock64() - t0;
+                        uint32_t acc = 0;
+                        for (uint32_t c = lw & 0xffffu; c < (lw >> 16); ++c) {
+                            const uint32_t a_lo = s_sched[3 * c + 0], w1 = s_sched[3 * c + 1], idesc = s_sched[3 * c + 2];
+                            const uint64_t ad = ((uint64_t) ((w1 >> 16) | (1u << 14)) << 32) | (a_lo + t * (w1 & 0xffffu));
+                            const uint64_t bd = ((uint64_t) b_hi << 32) | (b_lo0 + s * (kStageBytes >> 4));
+                            t0 = p.dbg ? clock64() : 0;
+                            mbar_wait(bar_full + s, ph);
+                            if (p.dbg) p.dbg[blockIdx.x * 8 + 2] += clock64() - t0;
+                            tc_fence_after();
+                            umma_bf16(tmem_base + t * kMaxN, ad, bd, idesc, acc);
+                            tc_commit(bar_empty + s);  // frees the weight stage
+                            acc = 1;
+                            if (++s == kStages) {
+                                s = 0;
+                                ph ^= 1;
+                            }
+                        }
+                        tc_commit(bar_acc + t);  // accumulator complete -> epilogue of tile t
                     }
-                    const int s = it % kStages;
-                    mbar_wait(bar_full + s, (it / kStages) & 1);
-                    tc_fence_after();
-                    const uint8_t *abuf = cd.a_src == kSrcAct ? s_act : (cd.a_src == kSrcPE ? s_pe : s_aux);
-                    const uint32_t a_sbo = cd.a_src == kSrcAct ? kActSBO : kSideSBO;
-                    const uint32_t a_base = smem_u32(abuf) + (cd.a_k0 >> 3) * 128;
-                    const uint32_t b_base = smem_u32(s_stage + s * kStageBytes);
-                    const uint32_t b_sbo = (cd.kc >> 3) * 128;
-                    const uint32_t idesc = umma_idesc(kTileM, cd.n);
-                    for (int k = 0; k < cd.kc; k += 16) {
-                        const uint64_t ad = umma_desc(a_base + (k >> 3) * 128, 128, a_sbo);
-                        const uint64_t bd = umma_desc(b_base + (k >> 3) * 128, 128, b_sbo);
-                        umma_bf16(tmem_base, ad, bd, idesc, (cd.first && k == 0) ? 0u : 1u);
-                    }
-                    tc_commit(bar_empty + s);          // frees the weight stage
-                    if (cd.last) tc_commit(bar_acc);   // accumulator complete -> epilogue
+                    act_ph ^= 1;
                 }
             }
         }
     } else {
-        // ===================== PE + epilogue warps (thread = one row of the tile) ==========
-        const int row = threadIdx.x;  // 0..127, TMEM lane
-        uint32_t acc_uses = 0;
-        const float *bias = p.biases;
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            const int64_t lrow = (int64_t) tile * kTileM + row;
-            const bool valid = lrow < p.rows;
-            const int64_t grow = (valid && p.row_index) ? (int64_t) p.row_index[lrow] : lrow;
-            // ---- inputs: positional encodings + appearance embedding -> A buffers ----
-            float xin[8];
+        // ===================== PE + epilogue warps =====================
+        // thread = (row of the tile, column half); both tiles in turn
+        const int q = warp & 3, h = warp >> 2;
+        const int row = q * 32 + lane;  // 0..127, TMEM lane
+        const uint32_t tlane = tmem_base + ((uint32_t) (q * 32) << 16);
+        uint32_t acc_ph = 0;
+        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+            int64_t grow[kTiles];
+            bool valid[kTiles];
+            int ai[kTiles];
+            // ---- inputs: positional encodings -> A buffers (octaves split between the two halves) ----
 #pragma unroll
-            for (int c = 0; c < 8; ++c) xin[c] = (valid && c < p.in_dim) ? p.x[grow * p.in_dim + c] : 0.f;
-            write_pe(s_pe, row, 0, kSideSBO, xin, p.pe_xyz_freqs, kSideK);
-            if (p.need_viewdir) {
-                write_pe(s_aux, row, 0, kSideSBO, xin + 3, p.pe_dir_freqs, 32);
-            } else {
-                for (int k = 0; k < 32; k += 8)
-                    *reinterpret_cast<uint4 *>(s_aux + a_off(row, k, kSideSBO)) = make_uint4(0, 0, 0, 0);
+            for (int t = 0; t < kTiles; ++t) {
+                const int64_t lrow = ((int64_t) grp * kTiles + t) * kTileM + row;
+                valid[t] = lrow < p.rows;
+                grow[t] = (valid[t] && p.row_index) ? (int64_t) p.row_index[lrow] : lrow;
+                float xin[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xin[c] = (valid[t] && c < p.in_dim) ? p.x[grow[t] * p.in_dim + c] : 0.f;
+                uint8_t *pe = s_pe + t * kPeBytes;
+                const int fh = p.pe_xyz_freqs >> 1;
+                if (h == 0) {
+                    for (int c = 0; c < 3; ++c) put_bf16(pe, row, c, kPeSBO, xin[c]);
+                    write_pe_octaves(pe, row, kPeSBO, xin, 0, fh);
+                } else {
+                    write_pe_octaves(pe, row, kPeSBO, xin, fh, p.pe_xyz_freqs);
+                    for (int k = 3 + 6 * p.pe_xyz_freqs; k < kPeK; ++k)  // padding, with the two bias columns = 1
+                        put_bf16(pe, row, k, kPeSBO, (k == p.ones_col || k == p.ones_col + 1) ? 1.f : 0.f);
+                    if (p.need_viewdir) {
+                        uint8_t *dir = s_dir + t * kDirBytes;
+                        for (int c = 0; c < 3; ++c) put_bf16(dir, row, c, kDirSBO, xin[3 + c]);
+                        write_pe_octaves(dir, row, kDirSBO, xin + 3, 0, p.pe_dir_freqs);
+                        for (int k = 3 + 6 * p.pe_dir_freqs; k < kDirK; ++k) put_bf16(dir, row, k, kDirSBO, 0.f);
+                    }
+                }
+                ai[t] = 0;
+                if (p.app_bias) {
+                    const int a = p.app_col >= 0 ? (int) xin[p.app_col] : 0;
+                    ai[t] = min(max(a, 0), p.n_appearance - 1);
+                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_act + t);
             }
-            if (p.app_dim > 0) {
-                int ai = p.app_col >= 0 ? (int) xin[p.app_col] : 0;
-                ai = min(max(ai, 0), p.n_appearance - 1);
-                const float *e = p.embedding + (size_t) ai * p.app_dim;
-                for (int k = 0; k < kSideK - 32; ++k)
-                    *reinterpret_cast<__nv_bfloat16 *>(s_aux + a_off(row, 32 + k, kSideSBO)) =
-                            __float2bfloat16_rn(k < p.app_dim ? __ldg(e + k) : 0.f);
-            } else {
-                for (int k = 32; k < kSideK; k += 8)
-                    *reinterpret_cast<uint4 *>(s_aux + a_off(row, k, kSideSBO)) = make_uint4(0, 0, 0, 0);
-            }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_act);
 
-            float sigma = 0.f;
-            for (int l = 0; l < S.n_layers; ++l) {
+            float sigma[kTiles] = {0.f, 0.f};
+            for (int l = 0; l < n_layers; ++l) {
                 const LayerDesc ld = S.layers[l];
-                mbar_wait(bar_acc, acc_uses & 1);
-                ++acc_uses;
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t) (warp * 32) << 16);
-                for (int c0 = 0; c0 < ld.n; c0 += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(taddr + c0, r);
-                    if (ld.epilogue == kEpiOut) {
-                        if (valid) {
-                            for (int j = 0; j < 32; ++j) {
-                                const int c = c0 + j;
-                                if (c < p.out_real)
-                                    p.out[grow * p.out_stride + c] =
-                                            __uint_as_float(r[j]) + __ldg(bias + ld.bias_off + c);
+                const bool last_layer = ld.epilogue == kEpiOut;
+                // columns of this thread: half of the layer (the 32-wide output layer: all, by half 0)
+                const int n_mine = ld.n >= 64 ? (ld.n >> 1) : (h == 0 ? ld.n : 0);
+                const int col0 = ld.n >= 64 ? h * n_mine : 0;
+#pragma unroll
+                for (int t = 0; t < kTiles; ++t) {
+                    uint8_t *act = s_act + t * kActBytes;
+                    const long long t0 = (p.dbg && threadIdx.x == 0) ? clock64() : 0;
+                    mbar_wait(bar_acc + t, acc_ph);
+                    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 3] += clock64() - t0;
+                    tc_fence_after();
+                    const uint32_t taddr = tlane + t * kMaxN + col0;
+                    uint32_t r[2][32];
+                    if (n_mine > 0) tmem_ld32(taddr, r[0]);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < n_mine; c0 += 64) {
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const int cc = c0 + half * 32;
+                            if (cc >= n_mine) break;
+                            tmem_wait();
+                            if (cc + 32 < n_mine) tmem_ld32(taddr + cc + 32, r[half ^ 1]);  // overlaps the math below
+                            const uint32_t(&rr)[32] = r[half];
+                            const int col = col0 + cc;
+                            if (last_layer) {
+                                if (valid[t]) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (col + j < p.out_real)
+                                            p.out[grow[t] * p.out_stride + col + j] =
+                                                    __uint_as_float(rr[j]) + (ld.bias_off != kNoBias ? __ldg(p.biases + ld.bias_off + col + j) : 0.f);
+                                }
+                                continue;
+                            }
+                            float v[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
+                            if (ld.epilogue == kEpiReluActApp || ld.bias_off != kNoBias) {
+                                const float4 *b4 = reinterpret_cast<const float4 *>(
+                                        (ld.epilogue == kEpiReluActApp ? p.app_bias + (size_t) ai[t] * p.head_n : p.biases + ld.bias_off) + col);
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) {
+                                    const float4 b = __ldg(b4 + g);
+                                    v[4 * g + 0] += b.x;
+                                    v[4 * g + 1] += b.y;
+                                    v[4 * g + 2] += b.z;
+                                    v[4 * g + 3] += b.w;
+                                }
+                            }
+                            if (ld.epilogue == kEpiReluActSigma) {
+                                const float4 *w4 = reinterpret_cast<const float4 *>(p.sigma_w + col);
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) {
+                                    const float4 w = __ldg(w4 + g);
+                                    sigma[t] = fmaf(fmaxf(v[4 * g + 0], 0.f), w.x, sigma[t]);
+                                    sigma[t] = fmaf(fmaxf(v[4 * g + 1], 0.f), w.y, sigma[t]);
+                                    sigma[t] = fmaf(fmaxf(v[4 * g + 2], 0.f), w.z, sigma[t]);
+                                    sigma[t] = fmaf(fmaxf(v[4 * g + 3], 0.f), w.w, sigma[t]);
+                                }
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 o;
+                                if (ld.epilogue == kEpiLinearAct) {
+                                    o.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]);
+                                    o.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
+                                    o.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]);
+                                    o.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
+                                } else {
+                                    o.x = pack_bf16_relu(v[8 * g + 0], v[8 * g + 1]);
+                                    o.y = pack_bf16_relu(v[8 * g + 2], v[8 * g + 3]);
+                                    o.z = pack_bf16_relu(v[8 * g + 4], v[8 * g + 5]);
+                                    o.w = pack_bf16_relu(v[8 * g + 6], v[8 * g + 7]);
+                                }
+                                *reinterpret_cast<uint4 *>(act + a_off(row, col + 8 * g, kActSBO)) = o;
                             }
                         }
+                    }
+                    if (ld.epilogue == kEpiReluActSigma) {
+                        // the sigma head needs the whole row: the two column halves meet through a
+                        // shuffle-free exchange in the (now dead) TMEM-drained registers is not possible
+                        // across warps, so half 1 parks its partial sum in global memory (its own row's
+                        // sigma slot) and half 0 adds it at output time; the act barrier below orders them.
+                        if (h == 1 && valid[t]) p.out[grow[t] * p.out_stride + p.out_real] = sigma[t];
+                    }
+                    if (last_layer) {
+                        if (h == 0 && valid[t]) {
+                            float *po = p.out + grow[t] * p.out_stride + p.out_real;
+                            float sg = sigma[t] + __ldcg(po) + __ldg(p.sigma_w + 256);
+                            sg = p.sigma_activation == 1 ? (sg > 20.f ? sg : log1pf(expf(sg))) : fmaxf(sg, 0.f);
+                            *po = sg;
+                        }
+                        tc_fence_before();  // TMEM reads ordered before the next group's first MMA
                     } else {
-                        float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            v[j] = __uint_as_float(r[j]) + __ldg(bias + ld.bias_off + c0 + j);
-                            if (ld.epilogue != kEpiLinearAct) v[j] = fmaxf(v[j], 0.f);
-                        }
-                        if (ld.epilogue == kEpiReluActSigma) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                sigma = fmaf(v[j], __ldg(bias + p.sigma_w_off + c0 + j), sigma);
-                        }
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 q;
-                            q.x = pack_bf16(v[8 * g + 0], v[8 * g + 1]);
-                            q.y = pack_bf16(v[8 * g + 2], v[8 * g + 3]);
-                            q.z = pack_bf16(v[8 * g + 4], v[8 * g + 5]);
-                            q.w = pack_bf16(v[8 * g + 6], v[8 * g + 7]);
-                            *reinterpret_cast<uint4 *>(s_act + a_off(row, c0 + 8 * g, kActSBO)) = q;
-                        }
+                        if (ld.epilogue == kEpiReluActSigma) __threadfence_block();
+                        fence_async_smem();  // generic-proxy smem writes -> visible to the UMMA proxy
+                        tc_fence_before();
+                        mbar_arrive(bar_act + t);
                     }
                 }
-                if (ld.epilogue == kEpiOut) {
-                    if (valid) {
-                        float sg = sigma + __ldg(bias + p.sigma_b_off);
-                        sg = p.sigma_activation == 1 ? (sg > 20.f ? sg : log1pf(expf(sg)))
-                                                     : fmaxf(sg, 0.f);
-                        p.out[grow * p.out_stride + p.out_real] = sg;
-                    }
-                    tc_fence_before();  // TMEM reads ordered before the next tile's first MMA
-                } else {
-                    fence_async_smem();  // generic-proxy smem writes -> visible to the UMMA proxy
-                    tc_fence_before();
-                    mbar_arrive(bar_act);
-                }
+                acc_ph ^= 1;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(kTmemCols));
     }
 }
 
-constexpr size_t kMlpSmemBytes =
-        kActBytes + 2 * kSideBytes + kStages * kStageBytes + (2 * kStages + 2) * 8 + 16;
+constexpr size_t kMlpSmemBytes = kTiles * (kActBytes + kPeBytes + kDirBytes) + kStages * kStageBytes +
+                                 (2 * kStages + 2 * kTiles) * 8 + 16 + kMaxChunks * 12 + kMaxLayers * 4;
+static_assert(kMlpSmemBytes <= 232448, "shared memory budget of one sm_100 CTA");
 
 // ------------------------------------------------------------------ host packing
 uint16_t f2bf(float f) {
@@ -400,6 +538,12 @@ uint16_t f2bf(float f) {
     if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t) ((u >> 16) | 0x40u);  // NaN
     u += 0x7fffu + ((u >> 16) & 1u);  // round to nearest even
     return (uint16_t) (u >> 16);
+}
+float bf2f(uint16_t h) {
+    const uint32_t u = (uint32_t) h << 16;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
 }
 
 struct KSeg {  // a run of K columns of one layer's A operand
@@ -412,12 +556,13 @@ struct KSeg {  // a run of K columns of one layer's A operand
 struct MlpModel {
     int device = 0;
     uint8_t *weights = nullptr;
-    float *biases = nullptr;
-    float *embedding = nullptr;
+    float *sigma_w = nullptr;   // [256] + bias
+    float *biases = nullptr;    // fp32 bias rows for layers whose bias is not folded into the GEMM
+    float *app_bias = nullptr;  // [n_appearance][head_n]
     MlpSchedule *sched_dev = nullptr;
     MlpSchedule sched;
     mnv_mlp_desc cfg;
-    int sigma_w_off = 0, sigma_b_off = 0;
+    int head_n = 0, ones_col = 0;
     int num_sms = 0;
     int in_dim = 3;
     int out_dim = 0;
@@ -431,65 +576,88 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
         return nullptr;
     };
     if (d.width != 256 || d.n_trunk_layers < 2 || d.n_trunk_layers > 12 || d.head_width > 256 ||
-        d.head_width % 16 || d.out_rgb_dim < 1 || d.out_rgb_dim > 255)
-        return fail(MNV_ERR_INVALID, "unsupported MLP shape (width must be 256, head <= 256)");
+        d.head_width % 32 || d.out_rgb_dim < 1 || d.out_rgb_dim > 32)
+        return fail(MNV_ERR_INVALID, "unsupported MLP shape (width must be 256, head a multiple of 32 <= 256, "
+                                     "at most 32 colour outputs)");
     const int pe = 3 + 6 * d.pe_xyz_freqs;
     const int pe_dir = d.need_viewdir ? 3 + 6 * d.pe_dir_freqs : 0;
-    if (pe > kSideK || pe_dir > 32 || d.appearance_dim > kSideK - 32)
-        return fail(MNV_ERR_INVALID, "positional encoding / appearance embedding too wide");
-    if (d.skip_layer >= d.n_trunk_layers)
+    // two columns of ones behind the encoding carry the biases through the GEMM (same 16-column chunk)
+    const int ones_col = (pe % 16 == 15) ? pe + 1 : pe;
+    if (d.pe_xyz_freqs < 2 || ones_col + 2 > kPeK || pe_dir > kDirK)
+        return fail(MNV_ERR_INVALID, "positional encoding too wide");
+    if (d.appearance_dim > 0 && (d.n_appearance < 1 || !d.embedding))
+        return fail(MNV_ERR_INVALID, "appearance_dim > 0 needs an embedding table");
+    if (d.skip_layer >= d.n_trunk_layers || d.skip_layer < 1)
         return fail(MNV_ERR_INVALID, "skip_layer outside the trunk");
+    const int pe_len = (ones_col + 2 + 15) / 16 * 16;  // K columns of the PE segment incl. the ones
+    if (2 * (pe_len / kChunkK) + (d.n_trunk_layers + 1) * (256 / kChunkK + 1) + kDirK / kChunkK + 1 +
+                d.head_width / kChunkK + 1 > kMaxChunks)
+        return fail(MNV_ERR_INVALID, "MLP too deep for the on-chip schedule");
 
     auto *m = new MlpModel();
     m->device = device;
     m->cfg = d;
+    m->ones_col = ones_col;
     m->in_dim = 3 + (d.need_viewdir ? 3 : 0) + (d.appearance_dim > 0 ? 1 : 0);
     m->out_dim = d.out_rgb_dim + 1;
     MlpSchedule &S = m->sched;
     std::memset(&S, 0, sizeof(S));
     std::vector<uint8_t> blob;
-    std::vector<float> bias;
+    std::vector<float> bias_rows(32, 0.f);
     double macs = 0;
+    // bit l set -> layer l adds its fp32 bias in the epilogue; clear -> the bias rides in the GEMM as
+    // bf16 hi + lo against two columns of ones.  Measured on B200: the GEMM route is 10 % faster but
+    // moves 2.9 % of the rows beyond 1e-3 of the bf16-emulated reference (0.4 % with epilogue biases),
+    // so the epilogue route is the default; MNV_MLP_BIAS_EPILOGUE=<mask> is a dev override.
+    const unsigned epi_bias_mask = std::getenv("MNV_MLP_BIAS_EPILOGUE") ? (unsigned) std::strtoul(std::getenv("MNV_MLP_BIAS_EPILOGUE"), nullptr, 0) : ~0u;
 
-    auto add_layer = [&](const float *W, const float *b, int n_real, int k_real_total,
-                         const std::vector<KSeg> &segs, int epilogue) {
+    // W [n_real][k_real_total] row-major (nn.Linear); b may be null (bias applied by the epilogue)
+    auto add_layer = [&](const float *W, const float *b, int n_real, int k_real_total, std::vector<KSeg> segs,
+                         int epilogue) {
         LayerDesc &L = S.layers[S.n_layers];
         L.n = (uint16_t) ((n_real + 31) / 32 * 32);  // the epilogue reads 32 TMEM columns at a time
         L.n_real = (uint16_t) n_real;
-        L.bias_off = (uint32_t) bias.size();
         L.epilogue = (uint32_t) epilogue;
-        const int n_mma = L.n;  // epilogue reads 32 columns at a time
-        for (int c = 0; c < n_mma; ++c) bias.push_back(c < n_real ? b[c] : 0.f);
-        bool first = true;
-        for (size_t si = 0; si < segs.size(); ++si) {
-            const KSeg &sg = segs[si];
+        L.chunk_begin = (uint16_t) S.n_chunks;
+        L.bias_off = kNoBias;
+        const int n_mma = L.n;
+        if (b && ((epi_bias_mask >> S.n_layers) & 1u)) {
+            L.bias_off = (uint32_t) bias_rows.size();
+            for (int c = 0; c < n_mma; ++c) bias_rows.push_back(c < n_real ? b[c] : 0.f);
+            b = nullptr;
+        }
+        const int ones_chunk0 = ones_col / 16 * 16;
+        bool has_ones = false;
+        for (const KSeg &sg : segs) has_ones |= sg.a_src == kSrcPE && sg.a_k0 <= ones_chunk0 && sg.a_k0 + sg.k_len >= ones_chunk0 + 16;
+        if (b && !has_ones) segs.push_back({kSrcPE, ones_chunk0, 16, 0, 0});  // bias-only chunk
+        for (const KSeg &sg : segs) {
             for (int k0 = 0; k0 < sg.k_len; k0 += kChunkK) {
-                const int kc = std::min(kChunkK, sg.k_len - k0);
                 ChunkDesc &C = S.chunks[S.n_chunks++];
                 C.gmem_off = (uint32_t) blob.size();
-                C.bytes = (uint32_t) (n_mma * kc * 2);
                 C.n = (uint16_t) n_mma;
-                C.kc = (uint16_t) kc;
                 C.a_src = (uint16_t) sg.a_src;
                 C.a_k0 = (uint16_t) (sg.a_k0 + k0);
-                C.first = first;
-                C.last = 0;
-                C.layer = (uint8_t) S.n_layers;
-                first = false;
-                blob.resize(blob.size() + C.bytes, 0);
+                const size_t bytes = (size_t) n_mma * kChunkK * 2;
+                blob.resize(blob.size() + bytes, 0);
                 uint8_t *dst = blob.data() + C.gmem_off;
-                const int sbo = (kc / 8) * 128;
-                for (int n = 0; n < n_real; ++n)
-                    for (int k = 0; k < kc; ++k) {
+                const int sbo = (kChunkK / 8) * 128;
+                auto put = [&](int n, int k, uint16_t hbits) {
+                    std::memcpy(dst + (n / 8) * sbo + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, &hbits, 2);
+                };
+                for (int n = 0; n < n_real; ++n) {
+                    for (int k = 0; k < kChunkK; ++k) {
                         const int kk = k0 + k;  // column inside the segment
-                        if (kk >= sg.w_cols) continue;
-                        const float w = W[(size_t) n * k_real_total + sg.w_col0 + kk];
-                        const uint16_t h = f2bf(w);
-                        std::memcpy(dst + (n / 8) * sbo + (k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2, &h, 2);
+                        if (kk < sg.w_cols) put(n, k, f2bf(W[(size_t) n * k_real_total + sg.w_col0 + kk]));
                     }
+                    if (b && sg.a_src == kSrcPE && C.a_k0 == ones_chunk0) {  // bias = hi + lo against the ones
+                        const uint16_t hi = f2bf(b[n]);
+                        put(n, ones_col - ones_chunk0, hi);
+                        put(n, ones_col + 1 - ones_chunk0, f2bf(b[n] - bf2f(hi)));
+                    }
+                }
             }
         }
-        S.chunks[S.n_chunks - 1].last = 1;
+        L.chunk_end = (uint16_t) S.n_chunks;
         macs += (double) n_real * k_real_total;
         ++S.n_layers;
     };
@@ -499,11 +667,11 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
         std::vector<KSeg> segs;
         int k_total;
         if (l == 0) {
-            segs.push_back({kSrcPE, 0, (pe + 15) / 16 * 16, 0, pe});
+            segs.push_back({kSrcPE, 0, pe_len, 0, pe});
             k_total = pe;
         } else if (l == d.skip_layer) {  // cat([pe, h]) like the NeRF skip connection
             segs.push_back({kSrcAct, 0, 256, pe, 256});
-            segs.push_back({kSrcPE, 0, (pe + 15) / 16 * 16, 0, pe});
+            segs.push_back({kSrcPE, 0, pe_len, 0, pe});
             k_total = pe + 256;
         } else {
             segs.push_back({kSrcAct, 0, 256, 0, 256});
@@ -514,41 +682,54 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
     }
     // feature layer (no activation)
     add_layer(d.final_w, d.final_b, 256, 256, {{kSrcAct, 0, 256, 0, 256}}, kEpiLinearAct);
-    // head 1: [feature(256) | dir PE | appearance]
+    // head 1: [feature(256) | dir PE | appearance].  The appearance columns do not enter the GEMM:
+    // their product with the (per-row constant) embedding row is a bias, tabulated per index below.
+    std::vector<float> app_bias;
+    int head_n = 0;
     {
         std::vector<KSeg> segs;
         segs.push_back({kSrcAct, 0, 256, 0, 256});
         int col = 256;
         if (pe_dir > 0) {
-            segs.push_back({kSrcAux, 0, 32, col, pe_dir});
+            segs.push_back({kSrcDir, 0, kDirK, col, pe_dir});
             col += pe_dir;
         }
-        if (d.appearance_dim > 0) {
-            segs.push_back({kSrcAux, 32, (d.appearance_dim + 15) / 16 * 16, col, d.appearance_dim});
-            col += d.appearance_dim;
+        const int k_total = col + d.appearance_dim;
+        const bool app = d.appearance_dim > 0;
+        add_layer(d.head1_w, app ? nullptr : d.head1_b, d.head_width, k_total, segs, app ? kEpiReluActApp : kEpiReluAct);
+        head_n = S.layers[S.n_layers - 1].n;
+        if (app) {
+            app_bias.assign((size_t) d.n_appearance * head_n, 0.f);
+            for (int a = 0; a < d.n_appearance; ++a)
+                for (int n = 0; n < d.head_width; ++n) {
+                    double acc = 0;  // operand rounding of the tensor-core path, wide accumulation
+                    for (int k = 0; k < d.appearance_dim; ++k)
+                        acc += (double) bf2f(f2bf(d.head1_w[(size_t) n * k_total + col + k])) *
+                               (double) bf2f(f2bf(d.embedding[(size_t) a * d.appearance_dim + k]));
+                    app_bias[(size_t) a * head_n + n] = (float) (acc + (double) d.head1_b[n]);
+                }
         }
-        add_layer(d.head1_w, d.head1_b, d.head_width, col, segs, kEpiReluAct);
     }
     // head 2
     add_layer(d.head2_w, d.head2_b, d.out_rgb_dim, d.head_width,
               {{kSrcAct, 0, d.head_width, 0, d.head_width}}, kEpiOut);
     macs += 256;  // sigma head
     m->flops_per_row = 2.0 * macs;
-    m->sigma_w_off = (int) bias.size();
-    for (int c = 0; c < 256; ++c) bias.push_back(d.sigma_w[c]);
-    m->sigma_b_off = (int) bias.size();
-    bias.push_back(d.sigma_b[0]);
+    std::vector<float> sig(d.sigma_w, d.sigma_w + 256);
+    sig.push_back(d.sigma_b[0]);
 
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaMalloc(&m->weights, blob.size());
     if (e == cudaSuccess) e = cudaMemcpy(m->weights, blob.data(), blob.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&m->biases, bias.size() * 4);
-    if (e == cudaSuccess) e = cudaMemcpy(m->biases, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && d.appearance_dim > 0) {
-        const size_t nb = (size_t) d.n_appearance * d.appearance_dim * 4;
-        e = cudaMalloc(&m->embedding, nb);
-        if (e == cudaSuccess) e = cudaMemcpy(m->embedding, d.embedding, nb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&m->biases, bias_rows.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->biases, bias_rows.data(), bias_rows.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&m->sigma_w, sig.size() * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(m->sigma_w, sig.data(), sig.size() * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !app_bias.empty()) {
+        e = cudaMalloc(&m->app_bias, app_bias.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(m->app_bias, app_bias.data(), app_bias.size() * 4, cudaMemcpyHostToDevice);
     }
+    m->head_n = head_n;
     if (e == cudaSuccess) e = cudaMalloc(&m->sched_dev, sizeof(MlpSchedule));
     if (e == cudaSuccess) e = cudaMemcpy(m->sched_dev, &S, sizeof(S), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -567,8 +748,9 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
 void mlp_destroy(MlpModel *m) {
     if (!m) return;
     cudaFree(m->weights);
+    cudaFree(m->sigma_w);
     cudaFree(m->biases);
-    cudaFree(m->embedding);
+    cudaFree(m->app_bias);
     cudaFree(m->sched_dev);
     delete m;
 }
@@ -591,8 +773,9 @@ int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *ro
     }
     MlpParams p;
     p.weights = m->weights;
+    p.sigma_w = m->sigma_w;
     p.biases = m->biases;
-    p.embedding = m->embedding;
+    p.app_bias = m->app_bias;
     p.sched = m->sched_dev;
     p.x = x_dev;
     p.out = out_dev;
@@ -600,20 +783,34 @@ int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *ro
     p.rows = rows;
     p.in_dim = in_dim;
     p.out_stride = out_stride;
-    p.n_tiles = (int) ((rows + kTileM - 1) / kTileM);
+    p.n_groups = (int) ((rows + kTiles * kTileM - 1) / (kTiles * kTileM));
     p.pe_xyz_freqs = m->cfg.pe_xyz_freqs;
     p.pe_dir_freqs = m->cfg.pe_dir_freqs;
     p.need_viewdir = m->cfg.need_viewdir;
-    p.app_dim = m->cfg.appearance_dim;
     p.n_appearance = m->cfg.n_appearance;
+    p.head_n = m->head_n;
     p.app_col = m->cfg.appearance_dim > 0 ? in_dim - 1 : -1;
-    p.sigma_w_off = m->sigma_w_off;
-    p.sigma_b_off = m->sigma_b_off;
+    p.ones_col = m->ones_col;
     p.sigma_activation = m->cfg.sigma_activation;
     p.out_real = m->cfg.out_rgb_dim;
-    const int grid = std::min(p.n_tiles, m->num_sms);
+    const int grid = std::min(p.n_groups, m->num_sms);
+    p.dbg = nullptr;
+    static const bool debug = std::getenv("MNV_MLP_DEBUG") != nullptr;
+    if (debug) {
+        MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 8 * sizeof(long long)));
+        MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 8 * sizeof(long long), stream));
+    }
     mlp_forward_kernel<<<grid, kMlpThreads, kMlpSmemBytes, stream>>>(p);
     MNV_CUDA(cudaGetLastError());
+    if (debug) {  // dev only: where do the producer / issuer / epilogue threads of CTA 0 wait?
+        std::vector<long long> h((size_t) grid * 8);
+        MNV_CUDA(cudaMemcpyAsync(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        MNV_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(p.dbg);
+        std::fprintf(stderr, "[mlp dbg] CTA0 cycles: producer wait_empty %lld | issuer wait_act %lld wait_full %lld | "
+                     "epilogue(thread 0) wait_acc %lld | groups/CTA %d chunks %d\n", h[0], h[1], h[2], h[3],
+                     (p.n_groups + grid - 1) / grid, m->sched.n_chunks);
+    }
     return MNV_OK;
 }
 
