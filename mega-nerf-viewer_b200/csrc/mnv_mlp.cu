@@ -32,6 +32,7 @@
 // instead of 48 more K columns.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,7 +48,7 @@ constexpr int kMlpThreads = 320;
 constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kTiles = 2;  // row tiles per CTA
-constexpr int kStages = 5;
+constexpr int kMaxStages = 6;  // 6 without view directions, 4 with (the dir-PE buffers take 16 KiB)
 constexpr int kChunkK = 16;
 constexpr int kMaxN = 256;
 constexpr int kStageBytes = kMaxN * kChunkK * 2;  // 8 KiB
@@ -100,6 +101,7 @@ struct MlpParams {
     int pe_xyz_freqs, pe_dir_freqs, ones_col;
     int need_viewdir, n_appearance, app_col, head_n;  // app_col: column of x holding the index (-1: none)
     int sigma_activation;          // 0 = ReLU, 1 = softplus
+    int n_stages;                  // depth of the weight ring
     int out_real;                  // 3 * basis
     long long *dbg;                // dev: per-CTA cycle counters (MNV_MLP_DEBUG=1), else null
 };
@@ -243,16 +245,18 @@ __device__ __forceinline__ void write_pe_octaves(uint8_t *buf, int row, int sbo,
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const int kStages = p.n_stages;
     uint8_t *s_act = smem;                           // [kTiles][kActBytes]
     uint8_t *s_pe = s_act + kTiles * kActBytes;      // [kTiles][kPeBytes]
-    uint8_t *s_dir = s_pe + kTiles * kPeBytes;       // [kTiles][kDirBytes]
-    uint8_t *s_stage = s_dir + kTiles * kDirBytes;   // [kStages][kStageBytes]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_stage + kStages * kStageBytes);
-    uint64_t *bar_full = bars;                       // [kStages] weights landed
-    uint64_t *bar_empty = bars + kStages;            // [kStages] weights consumed
-    uint64_t *bar_acc = bars + 2 * kStages;          // [kTiles] accumulator of the current layer complete
-    uint64_t *bar_act = bars + 2 * kStages + kTiles; // [kTiles] A operand of the next layer written (256 arrivals)
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kStages + 2 * kTiles);
+    uint8_t *s_dir = s_pe + kTiles * kPeBytes;       // [kTiles][kDirBytes], only with view directions
+    uint8_t *s_stage = s_dir + (p.need_viewdir ? kTiles * kDirBytes : 0);  // [kStages][kStageBytes]
+    float *s_bias = reinterpret_cast<float *>(s_stage + kStages * kStageBytes);  // [2][kMaxN] this / next layer's bias row
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_bias + 2 * kMaxN);
+    uint64_t *bar_full = bars;                       // [kMaxStages] weights landed
+    uint64_t *bar_empty = bars + kMaxStages;         // [kMaxStages] weights consumed
+    uint64_t *bar_acc = bars + 2 * kMaxStages;       // [kTiles] accumulator of the current layer complete
+    uint64_t *bar_act = bars + 2 * kMaxStages + kTiles; // [kTiles] A operand of the next layer written (256 arrivals)
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2 * kTiles);
     // issuer-side schedule, 3 words per chunk: low word of tile 0's A descriptor;
     // (tile stride >> 4) | (SBO >> 4) << 16; instruction descriptor.  Then one word per layer:
     // chunk_begin | chunk_end << 16.
@@ -412,9 +416,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
             }
 
             float sigma[kTiles] = {0.f, 0.f};
+            // bias rows travel through shared memory one layer ahead (thread i fetches column i), so the
+            // epilogue's adds never wait on global memory: s_bias[l & 1] is layer l's row
+            {
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // the previous group's last epilogue is done with the rows
+                const uint32_t bo = S.layers[0].bias_off;
+                s_bias[threadIdx.x] = bo != kNoBias ? __ldg(p.biases + bo + threadIdx.x) : 0.f;
+            }
             for (int l = 0; l < n_layers; ++l) {
                 const LayerDesc ld = S.layers[l];
                 const bool last_layer = ld.epilogue == kEpiOut;
+                // all 256 threads are done with layer l-1 (and its bias row); layer l's row is complete
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (l + 1 < n_layers) {
+                    const LayerDesc nx = S.layers[l + 1];
+                    s_bias[((l + 1) & 1) * kMaxN + threadIdx.x] =
+                            (nx.bias_off != kNoBias && threadIdx.x < nx.n) ? __ldg(p.biases + nx.bias_off + threadIdx.x) : 0.f;
+                }
+                const float *lbias = s_bias + (l & 1) * kMaxN;
                 // columns of this thread: half of the layer (the 32-wide output layer: all, by half 0)
                 const int n_mine = ld.n >= 64 ? (ld.n >> 1) : (h == 0 ? ld.n : 0);
                 const int col0 = ld.n >= 64 ? h * n_mine : 0;
@@ -443,20 +462,28 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
 #pragma unroll
                                     for (int j = 0; j < 32; ++j)
                                         if (col + j < p.out_real)
-                                            p.out[grow[t] * p.out_stride + col + j] =
-                                                    __uint_as_float(rr[j]) + (ld.bias_off != kNoBias ? __ldg(p.biases + ld.bias_off + col + j) : 0.f);
+                                            p.out[grow[t] * p.out_stride + col + j] = __uint_as_float(rr[j]) + lbias[col + j];
                                 }
                                 continue;
                             }
                             float v[32];
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]);
-                            if (ld.epilogue == kEpiReluActApp || ld.bias_off != kNoBias) {
-                                const float4 *b4 = reinterpret_cast<const float4 *>(
-                                        (ld.epilogue == kEpiReluActApp ? p.app_bias + (size_t) ai[t] * p.head_n : p.biases + ld.bias_off) + col);
+                            if (ld.epilogue == kEpiReluActApp) {
+                                const float4 *b4 = reinterpret_cast<const float4 *>(p.app_bias + (size_t) ai[t] * p.head_n + col);
 #pragma unroll
                                 for (int g = 0; g < 8; ++g) {
                                     const float4 b = __ldg(b4 + g);
+                                    v[4 * g + 0] += b.x;
+                                    v[4 * g + 1] += b.y;
+                                    v[4 * g + 2] += b.z;
+                                    v[4 * g + 3] += b.w;
+                                }
+                            } else if (ld.bias_off != kNoBias) {
+                                const float4 *b4 = reinterpret_cast<const float4 *>(lbias + col);
+#pragma unroll
+                                for (int g = 0; g < 8; ++g) {
+                                    const float4 b = b4[g];
                                     v[4 * g + 0] += b.x;
                                     v[4 * g + 1] += b.y;
                                     v[4 * g + 2] += b.z;
@@ -527,9 +554,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
     }
 }
 
-constexpr size_t kMlpSmemBytes = kTiles * (kActBytes + kPeBytes + kDirBytes) + kStages * kStageBytes +
-                                 (2 * kStages + 2 * kTiles) * 8 + 16 + kMaxChunks * 12 + kMaxLayers * 4;
-static_assert(kMlpSmemBytes <= 232448, "shared memory budget of one sm_100 CTA");
+constexpr int mlp_stages(bool viewdir) { return viewdir ? 4 : 6; }
+constexpr size_t mlp_smem_bytes(bool viewdir) {
+    return kTiles * (kActBytes + kPeBytes + (viewdir ? kDirBytes : 0)) + mlp_stages(viewdir) * kStageBytes +
+           2 * kMaxN * 4 + (2 * kMaxStages + 2 * kTiles) * 8 + 16 + kMaxChunks * 12 + kMaxLayers * 4;
+}
+static_assert(mlp_smem_bytes(false) <= 232448 && mlp_smem_bytes(true) <= 232448 && mlp_stages(false) <= kMaxStages,
+              "shared memory budget of one sm_100 CTA");
 
 // ------------------------------------------------------------------ host packing
 uint16_t f2bf(float f) {
@@ -735,7 +766,7 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) kMlpSmemBytes);
+                                 (int) std::max(mlp_smem_bytes(false), mlp_smem_bytes(true)));
     if (e != cudaSuccess) {
         *rc_out = cuda_fail(e, "mlp_create", __FILE__, __LINE__);
         mlp_destroy(m);
@@ -800,7 +831,8 @@ int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *ro
         MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 8 * sizeof(long long)));
         MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 8 * sizeof(long long), stream));
     }
-    mlp_forward_kernel<<<grid, kMlpThreads, kMlpSmemBytes, stream>>>(p);
+    p.n_stages = mlp_stages(p.need_viewdir != 0);
+    mlp_forward_kernel<<<grid, kMlpThreads, mlp_smem_bytes(p.need_viewdir != 0), stream>>>(p);
     MNV_CUDA(cudaGetLastError());
     if (debug) {  // dev only: where do the producer / issuer / epilogue threads of CTA 0 wait?
         std::vector<long long> h((size_t) grid * 8);
