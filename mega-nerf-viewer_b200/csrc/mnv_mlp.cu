@@ -48,7 +48,7 @@ constexpr int kMlpThreads = 320;
 constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kTiles = 2;  // row tiles per CTA
-constexpr int kMaxStages = 6;  // 6 without view directions, 4 with (the dir-PE buffers take 16 KiB)
+constexpr int kMaxStages = 7;  // 7 without view directions, 5 with (the dir-PE buffers take 16 KiB)
 constexpr int kChunkK = 16;
 constexpr int kMaxN = 256;
 constexpr int kStageBytes = kMaxN * kChunkK * 2;  // 8 KiB
@@ -58,7 +58,8 @@ constexpr int kPeBytes = kTileM * kPeK * 2;    // 20 KiB
 constexpr int kDirBytes = kTileM * kDirK * 2;  // 8 KiB
 constexpr int kActSBO = (kActK / 8) * 128, kPeSBO = (kPeK / 8) * 128, kDirSBO = (kDirK / 8) * 128;
 constexpr int kTmemCols = 512;
-constexpr int kMaxLayers = 16, kMaxChunks = 224;  // smem copy of the schedule: 12 B per chunk
+constexpr int kMaxLayers = 16, kMaxChunks = 256;
+constexpr int kLayerWords = 12;  // smem copy of one layer's issue schedule
 
 enum { kEpiReluAct = 0, kEpiReluActSigma = 1, kEpiLinearAct = 2, kEpiOut = 3, kEpiReluActApp = 4 };
 enum { kSrcAct = 0, kSrcPE = 1, kSrcDir = 2 };
@@ -71,10 +72,15 @@ struct ChunkDesc {
     uint16_t pad;
 };
 
+struct SegDesc {  // a run of consecutive 16-column chunks of one A buffer
+    uint16_t a_src, a_k0, n_chunks, pad;
+};
 struct LayerDesc {
     uint16_t n;        // padded N (multiple of 32)
     uint16_t n_real;   // real output width
     uint16_t chunk_begin, chunk_end;
+    uint16_t n_segs, pad;
+    SegDesc segs[3];
     uint32_t epilogue;
     uint32_t bias_off;  // float offset of an fp32 bias row the epilogue adds; kNoBias: the bias rides in the GEMM
 };
@@ -179,6 +185,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+__device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // asynchronous: the registers are valid after tmem_wait()
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -257,11 +268,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
     uint64_t *bar_acc = bars + 2 * kMaxStages;       // [kTiles] accumulator of the current layer complete
     uint64_t *bar_act = bars + 2 * kMaxStages + kTiles; // [kTiles] A operand of the next layer written (256 arrivals)
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2 * kTiles);
-    // issuer-side schedule, 3 words per chunk: low word of tile 0's A descriptor;
-    // (tile stride >> 4) | (SBO >> 4) << 16; instruction descriptor.  Then one word per layer:
-    // chunk_begin | chunk_end << 16.
-    uint32_t *s_sched = s_tmem + 4;
-    uint32_t *s_layer = s_sched + 3 * kMaxChunks;
+    // issuer-side schedule, per layer 2 + 3 * 3 words: n_segs | n_chunks << 8 | weight bytes per chunk << 16;
+    // instruction descriptor; then per segment: low word of tile 0's A descriptor, high word,
+    // n_chunks | (tile stride >> 4) << 16
+    uint32_t *s_layer = s_tmem + 4;  // [kMaxLayers][kLayerWords]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MlpSchedule &S = *p.sched;
@@ -284,17 +294,21 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
                      "r"(kTmemCols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int c = threadIdx.x; c < S.n_chunks; c += kMlpThreads) {
-        const ChunkDesc cd = S.chunks[c];
-        const uint8_t *abuf = cd.a_src == kSrcAct ? s_act : (cd.a_src == kSrcPE ? s_pe : s_dir);
-        const uint32_t sbo = cd.a_src == kSrcAct ? kActSBO : (cd.a_src == kSrcPE ? kPeSBO : kDirSBO);
-        const uint32_t stride = cd.a_src == kSrcAct ? kActBytes : (cd.a_src == kSrcPE ? kPeBytes : kDirBytes);
-        s_sched[3 * c + 0] = (((smem_u32(abuf) + (cd.a_k0 >> 3) * 128) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
-        s_sched[3 * c + 1] = (stride >> 4) | ((sbo >> 4) << 16);
-        s_sched[3 * c + 2] = umma_idesc(kTileM, cd.n);
+    if (threadIdx.x < n_layers) {
+        const LayerDesc ld = S.layers[threadIdx.x];
+        uint32_t *w = s_layer + threadIdx.x * kLayerWords;
+        w[0] = (uint32_t) ld.n_segs | ((uint32_t) (ld.chunk_end - ld.chunk_begin) << 8) | ((uint32_t) ld.n * kChunkK * 2u) << 16;
+        w[1] = umma_idesc(kTileM, ld.n);
+        for (int i = 0; i < ld.n_segs; ++i) {
+            const SegDesc sg = ld.segs[i];
+            const uint8_t *abuf = sg.a_src == kSrcAct ? s_act : (sg.a_src == kSrcPE ? s_pe : s_dir);
+            const uint32_t sbo = sg.a_src == kSrcAct ? kActSBO : (sg.a_src == kSrcPE ? kPeSBO : kDirSBO);
+            const uint32_t stride = sg.a_src == kSrcAct ? kActBytes : (sg.a_src == kSrcPE ? kPeBytes : kDirBytes);
+            w[2 + 3 * i] = (((smem_u32(abuf) + (sg.a_k0 >> 3) * 128) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
+            w[3 + 3 * i] = (sbo >> 4) | (1u << 14);
+            w[4 + 3 * i] = (uint32_t) sg.n_chunks | ((stride >> 4) << 16);
+        }
     }
-    if (threadIdx.x < n_layers)
-        s_layer[threadIdx.x] = (uint32_t) S.layers[threadIdx.x].chunk_begin | ((uint32_t) S.layers[threadIdx.x].chunk_end << 16);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -306,67 +320,67 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
         if (lane == 0) {
             uint32_t s = 0, ph = 1;
             for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-                const uint8_t *layer_src = p.weights;
+                const uint8_t *layer_src = p.weights;  // chunks are contiguous in schedule order
                 for (int l = 0; l < n_layers; ++l) {
-                    const uint32_t lw = s_layer[l];
-                    const uint8_t *src = layer_src;
+                    const uint32_t w0 = s_layer[l * kLayerWords];
+                    const uint32_t n_chunks = (w0 >> 8) & 0xffu, bytes = w0 >> 16;
                     for (int t = 0; t < kTiles; ++t) {
-                        src = layer_src;
-                        for (uint32_t c = lw & 0xffffu; c < (lw >> 16); ++c) {
-                            const uint32_t bytes = ((s_sched[3 * c + 2] >> 17) & 0x3fu) * (8u * kChunkK * 2u);  // N * 16 * 2
-                            const long long t0 = p.dbg ? clock64() : 0;
+                        const uint8_t *src = layer_src;
+                        for (uint32_t c = 0; c < n_chunks; ++c) {
                             mbar_wait(bar_empty + s, ph);
-                            if (p.dbg) p.dbg[blockIdx.x * 8 + 0] += clock64() - t0;
                             mbar_expect_tx(bar_full + s, bytes);
                             tma_bulk_g2s(s_stage + s * kStageBytes, src, bytes, bar_full + s);
                             src += bytes;
-                            if (++s == kStages) {
+                            if (++s == (uint32_t) kStages) {
                                 s = 0;
                                 ph ^= 1;
                             }
                         }
                     }
-                    layer_src = src;
+                    layer_src += n_chunks * bytes;
                 }
             }
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        // One thread feeds the tensor pipe: everything per chunk comes from the smem schedule
-        // (3 LDS), descriptors are integer adds — the loop must stay well under the 128 clk an
-        // M=128 x N=256 x K=16 MMA takes.
-        if (lane == 0) {
-            const uint32_t b_lo0 = ((smem_u32(s_stage) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
-            const uint32_t b_hi = ((kChunkK / 8 * 128u) >> 4) | (1u << 14);
-            uint32_t s = 0, ph = 0, act_ph = 0;
-            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
-                for (int l = 0; l < n_layers; ++l) {
-                    const uint32_t lw = s_layer[l];
-                    for (int t = 0; t < kTiles; ++t) {
-                        long long t0 = p.dbg ? clock64() : 0;
-                        mbar_wait(bar_act + t, act_ph);  // A operand of tile t ready, its accumulator drained
-                        if (p.dbg) p.dbg[blockIdx.x * 8 + 1] += clock64() - t0;
-                        uint32_t acc = 0;
-                        for (uint32_t c = lw & 0xffffu; c < (lw >> 16); ++c) {
-                            const uint32_t a_lo = s_sched[3 * c + 0], w1 = s_sched[3 * c + 1], idesc = s_sched[3 * c + 2];
-                            const uint64_t ad = ((uint64_t) ((w1 >> 16) | (1u << 14)) << 32) | (a_lo + t * (w1 & 0xffffu));
-                            const uint64_t bd = ((uint64_t) b_hi << 32) | (b_lo0 + s * (kStageBytes >> 4));
-                            t0 = p.dbg ? clock64() : 0;
+        // The whole warp runs the (warp-uniform) loop and one elected lane issues: per chunk the work is a
+        // barrier poll, two integer adds for the descriptors, the MMA and the commit that frees the weight
+        // stage — it must stay under the 128 clk an M=128 x N=256 x K=16 MMA takes (measured).
+        const uint32_t b_lo0 = ((smem_u32(s_stage) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
+        const uint32_t b_hi = ((kChunkK / 8 * 128u) >> 4) | (1u << 14);
+        const bool issue = elect_one();
+        uint32_t s = 0, ph = 0, act_ph = 0;
+        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+            for (int l = 0; l < n_layers; ++l) {
+                const uint32_t *w = s_layer + l * kLayerWords;
+                const uint32_t n_segs = w[0] & 0xffu, idesc = w[1];
+                for (int t = 0; t < kTiles; ++t) {
+                    mbar_wait(bar_act + t, act_ph);  // A operand of tile t ready, its accumulator drained
+                    uint32_t acc = 0;
+                    for (uint32_t i = 0; i < n_segs; ++i) {
+                        const uint32_t w2 = w[4 + 3 * i];
+                        uint32_t a_lo = w[2 + 3 * i] + t * (w2 >> 16);
+                        const uint32_t a_hi = w[3 + 3 * i];
+                        for (uint32_t c = w2 & 0xffffu; c > 0; --c) {
                             mbar_wait(bar_full + s, ph);
-                            if (p.dbg) p.dbg[blockIdx.x * 8 + 2] += clock64() - t0;
                             tc_fence_after();
-                            umma_bf16(tmem_base + t * kMaxN, ad, bd, idesc, acc);
-                            tc_commit(bar_empty + s);  // frees the weight stage
+                            if (issue) {
+                                umma_bf16(tmem_base + t * kMaxN, ((uint64_t) a_hi << 32) | a_lo,
+                                          ((uint64_t) b_hi << 32) | (b_lo0 + s * (kStageBytes >> 4)), idesc, acc);
+                                tc_commit(bar_empty + s);  // frees the weight stage
+                            }
                             acc = 1;
-                            if (++s == kStages) {
+                            a_lo += (kChunkK / 8 * 128u) >> 4;  // next 16 K columns of the K-major A operand
+                            if (++s == (uint32_t) kStages) {
                                 s = 0;
                                 ph ^= 1;
                             }
                         }
-                        tc_commit(bar_acc + t);  // accumulator complete -> epilogue of tile t
                     }
-                    act_ph ^= 1;
+                    if (issue) tc_commit(bar_acc + t);  // accumulator complete -> epilogue of tile t
+                    __syncwarp();
                 }
+                act_ph ^= 1;
             }
         }
     } else {
@@ -440,9 +454,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
 #pragma unroll
                 for (int t = 0; t < kTiles; ++t) {
                     uint8_t *act = s_act + t * kActBytes;
-                    const long long t0 = (p.dbg && threadIdx.x == 0) ? clock64() : 0;
                     mbar_wait(bar_acc + t, acc_ph);
-                    if (p.dbg && threadIdx.x == 0) p.dbg[blockIdx.x * 8 + 3] += clock64() - t0;
                     tc_fence_after();
                     const uint32_t taddr = tlane + t * kMaxN + col0;
                     uint32_t r[2][32];
@@ -554,10 +566,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpPa
     }
 }
 
-constexpr int mlp_stages(bool viewdir) { return viewdir ? 4 : 6; }
+constexpr int mlp_stages(bool viewdir) { return viewdir ? 5 : 7; }  // everything that is left
 constexpr size_t mlp_smem_bytes(bool viewdir) {
     return kTiles * (kActBytes + kPeBytes + (viewdir ? kDirBytes : 0)) + mlp_stages(viewdir) * kStageBytes +
-           2 * kMaxN * 4 + (2 * kMaxStages + 2 * kTiles) * 8 + 16 + kMaxChunks * 12 + kMaxLayers * 4;
+           2 * kMaxN * 4 + (2 * kMaxStages + 2 * kTiles) * 8 + 16 + kMaxLayers * kLayerWords * 4;
 }
 static_assert(mlp_smem_bytes(false) <= 232448 && mlp_smem_bytes(true) <= 232448 && mlp_stages(false) <= kMaxStages,
               "shared memory budget of one sm_100 CTA");
@@ -661,6 +673,9 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
         bool has_ones = false;
         for (const KSeg &sg : segs) has_ones |= sg.a_src == kSrcPE && sg.a_k0 <= ones_chunk0 && sg.a_k0 + sg.k_len >= ones_chunk0 + 16;
         if (b && !has_ones) segs.push_back({kSrcPE, ones_chunk0, 16, 0, 0});  // bias-only chunk
+        L.n_segs = (uint16_t) segs.size();
+        for (size_t si = 0; si < segs.size(); ++si)
+            L.segs[si] = SegDesc{(uint16_t) segs[si].a_src, (uint16_t) segs[si].a_k0, (uint16_t) (segs[si].k_len / kChunkK), 0};
         for (const KSeg &sg : segs) {
             for (int k0 = 0; k0 < sg.k_len; k0 += kChunkK) {
                 ChunkDesc &C = S.chunks[S.n_chunks++];
@@ -826,23 +841,9 @@ int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *ro
     p.out_real = m->cfg.out_rgb_dim;
     const int grid = std::min(p.n_groups, m->num_sms);
     p.dbg = nullptr;
-    static const bool debug = std::getenv("MNV_MLP_DEBUG") != nullptr;
-    if (debug) {
-        MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 8 * sizeof(long long)));
-        MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 8 * sizeof(long long), stream));
-    }
     p.n_stages = mlp_stages(p.need_viewdir != 0);
     mlp_forward_kernel<<<grid, kMlpThreads, mlp_smem_bytes(p.need_viewdir != 0), stream>>>(p);
     MNV_CUDA(cudaGetLastError());
-    if (debug) {  // dev only: where do the producer / issuer / epilogue threads of CTA 0 wait?
-        std::vector<long long> h((size_t) grid * 8);
-        MNV_CUDA(cudaMemcpyAsync(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, stream));
-        MNV_CUDA(cudaStreamSynchronize(stream));
-        cudaFree(p.dbg);
-        std::fprintf(stderr, "[mlp dbg] CTA0 cycles: producer wait_empty %lld | issuer wait_act %lld wait_full %lld | "
-                     "epilogue(thread 0) wait_acc %lld | groups/CTA %d chunks %d\n", h[0], h[1], h[2], h[3],
-                     (p.n_groups + grid - 1) / grid, m->sched.n_chunks);
-    }
     return MNV_OK;
 }
 

@@ -44,6 +44,28 @@ __global__ void __launch_bounds__(128, 1) k(int mode, int n, int iters, int a_kc
                 bds[j] = desc(b0 + j * 32, 16, 1024, 2);
             }
         }
+        if (commit_every == 1 || commit_every == 11) {
+            volatile uint32_t *sch = (volatile uint32_t *) (smem + 190 * 1024);
+            // a completed barrier to poll: arrive once on bar2[7] -> phase 0 complete
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar2[7])) : "memory");
+            long long t0 = clock64();
+            for (int i = 0; i < iters; ++i) {
+                const uint32_t w0 = sch[3 * (i & 63)], w1 = sch[3 * (i & 63) + 1], w2 = sch[3 * (i & 63) + 2];
+                const uint64_t ad = ads[0] + (w0 & 1) + (w1 & 1), bd = bds[0] + (w2 & 1);
+                if (commit_every == 11) {
+                    asm volatile("{.reg .pred p; W2: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0; @p bra D2; bra W2; D2: }" ::"r"(smem_u32(&bar2[7])) : "memory");
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                asm volatile("{.reg .pred p; setp.ne.b32 p, %4, 0; tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;}" ::
+                             "r"(tmem + (i & 1) * 256), "l"(ad), "l"(bd), "r"(id), "r"(1u) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[i % 6])) : "memory");
+            }
+            long long t1 = clock64();
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+            asm volatile("{.reg .pred p; W3: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0; @p bra D3; bra W3; D3: }" ::"r"(smem_u32(&bar)) : "memory");
+            long long t2 = clock64();
+            if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        } else {
         long long t0 = clock64();
         for (int i = 0; i < iters; i += 4) {
 #pragma unroll
@@ -60,6 +82,7 @@ __global__ void __launch_bounds__(128, 1) k(int mode, int n, int iters, int a_kc
         asm volatile("{.reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0; @p bra D; bra W; D: }" ::"r"(smem_u32(&bar)) : "memory");
         long long t2 = clock64();
         if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -72,7 +95,7 @@ int main() {
     for (int grid : {148})
         for (int mode : {0})
             for (int n : {256, 128})
-                for (int akc : {0, 4, 2}) {
+                for (int akc : {0, 1, 11}) {
                     const int iters = 2000;
                     k<<<grid, 128, 200 * 1024>>>(mode, n, iters, 256, d, akc);
                     cudaError_t e = cudaDeviceSynchronize();
