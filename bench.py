@@ -132,6 +132,51 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
+def measured_tensor_peak():
+    """(burst, sustained) dense bf16 TFLOP/s of this pool's B200s (driver-written), else the nominal fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            j = json.load(f)
+        return float(j["bf16_tflops"]), float(j["bf16_tflops_sustained"]), "measured"
+    except Exception:
+        return 2250.0, 2250.0, "fallback (nominal dense bf16)"
+
+
+def mlp_section(mnv, torch, dev, iters=20):
+    """Config 4's dense contraction: one refinement batch = 4096 splits x 8 children x
+    8 samples = 262144 rows through the fused tcgen05 MLP (8x256 trunk, appearance embedding, SH9 head),
+    random-init weights; CUDA events around each launch, inputs resident; algorithmic FLOPs = 2 * sum in*out."""
+    model = mnv.MlpModel([mnv.synth.make_mlp_weights(seed=3)], device=dev.index)
+    rows = 4096 * 8 * 8
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.rand((rows, model.in_dim), device=dev, generator=g) * 2 - 1
+    x[:, -1] = 0
+    out = torch.empty((rows, model.out_dim + 1), device=dev)  # the reference's [rows, data_dim + 1] result buffer
+    for _ in range(3):
+        model.forward(x, out=out)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        model.forward(x, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    t = float(np.mean(ms))
+    tf = rows * model.flops_per_row / (t * 1e-3) / 1e12
+    burst, sustained, src = measured_tensor_peak()
+    sec = {"workload": f"{rows} rows (4096 splits x 8 children x 8 samples) through one 8x256 Mega-NeRF sub-MLP, "
+                       "appearance embedding on, SH9 head, random-init weights",
+           "rows": rows, "ms_per_launch": t, "mrows_per_s": rows / t / 1e3, "flops_per_row": model.flops_per_row,
+           "dtype": "bf16 operands, fp32 accumulate (TMEM)", "gpu_launches": iters,
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
+                        "frac_of_sustained_peak": tf / sustained, "peak_source": src + " cuBLAS bf16, burst (kernel timed alone)",
+                        "kernel": "mnv::mlp_forward_kernel", "traffic": None}}
+    model.close()
+    return sec
+
+
 def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
     """CPU oracle (port) on all host cores; bounded sample: whole frames of the
     orbit until ~seconds_budget elapsed (at least one)."""
@@ -297,6 +342,7 @@ def main():
                      "gvisits_per_s": visits / (ms_step * 1e-3) / 1e9},
         "clocks": clocks,
     }
+    line["mlp"] = mlp_section(mnv, torch, dev)
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle_py as O
         line["cpu_baseline"] = cpu_baseline(tree, cams, O, opt_kw)

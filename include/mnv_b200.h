@@ -324,6 +324,36 @@ int mnv_render_frame_host_bands(mnv_tree *tree, const mnv_camera *cam,
                                 const mnv_render_options *opt, uint8_t *rgba_host, int band_rows,
                                 int band_mod, int band_rem, mnv_frame_stats *stats);
 
+/* ---- sub-module split across GPUs (second mode; no reference counterpart —
+ * the reference is single-GPU).  GPU g owns one spatial cell of the Mega-NeRF (y, z) grid and
+ * marches every ray of the frame through that cell only (opt->render_bbox = the cell, tree
+ * space); the pixel range [o*block, (o+1)*block) of the frame is composited by owner o.
+ *
+ * mnv_render_voxels_partial: like mnv_render_voxels(offscreen) but each ray's premultiplied
+ *   (r, g, b, alpha) goes, as one 16-byte store, to partial_dst[o] + (slot*block + p % block),
+ *   o = p / block.  partial_dst are device pointers valid on this GPU: the local buffer or
+ *   peers' buffers mapped with mnv_ipc_open (NVLink stores — the exchange is fused in the march).
+ * mnv_signal_peers: after the march on the same stream, raises flag_dst[o][slot] = value in
+ *   every owner (system-scope fence first).
+ * mnv_composite_partials: owner side. partials_dev f32 [n][block][4] in slot order; boxes
+ *   f32 [n][6] host, the cells in slot order; waits on flags_dev[0..n) >= wait_value on the
+ *   device when flags_dev != NULL; orders the segments front to back per ray, composes, blends
+ *   opt->background_brightness and writes RGBA8 for pixels [first_pixel, first_pixel+n_pixels)
+ *   into rgba_dev[0..n_pixels). */
+int mnv_render_voxels_partial(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                              int n_owners, float *const *partial_dst, int block_pixels, int slot,
+                              void *stream);
+int mnv_signal_peers(uint32_t *const *flag_dst, int n, int slot, uint32_t value, void *stream);
+int mnv_composite_partials(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                           const float *partials_dev, int n, int block_pixels, const float *boxes_host,
+                           int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
+                           uint32_t wait_value, void *stream);
+/* CUDA IPC plumbing for the peer mappings (one process per GPU): a 64-byte handle of a buffer
+ * from mnv_malloc, opened in another process with lazy peer access. */
+int mnv_ipc_export(void *ptr_dev, uint8_t handle[64]);
+int mnv_ipc_open(const uint8_t handle[64], void **ptr_dev, int device);
+int mnv_ipc_close(void *ptr_dev);
+
 #ifdef __cplusplus
 }
 #endif

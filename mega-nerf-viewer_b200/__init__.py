@@ -19,6 +19,7 @@ import subprocess
 import numpy as np
 
 from . import synth  # noqa: F401  (synthetic N3Tree generator)
+from . import multigpu  # noqa: F401,E402  (sub-module split across GPUs)
 from .synth import HostTree
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -165,6 +166,17 @@ def lib() -> C.CDLL:
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
     L.mnv_mlp_forward.argtypes = [vp, i32, vp, i64, i32, vp, i32, vp]
+    L.mnv_render_voxels_partial.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), i32, C.POINTER(vp),
+                                            i32, i32, vp]
+    L.mnv_signal_peers.argtypes = [C.POINTER(vp), i32, i32, C.c_uint32, vp]
+    L.mnv_composite_partials.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32, i32, vp, i64, i32,
+                                         vp, vp, C.c_uint32, vp]
+    L.mnv_ipc_export.argtypes = [vp, C.c_char_p]
+    L.mnv_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp), i32]
+    L.mnv_ipc_close.argtypes = [vp]
+    L.mnv_malloc.argtypes = [C.POINTER(vp), C.c_size_t, i32]
+    L.mnv_free.argtypes = [vp]
+    L.mnv_memset.argtypes = [vp, i32, C.c_size_t, vp]
     _lib = L
     return L
 
@@ -407,6 +419,25 @@ class DeviceTree:
         first = int(torch.argmin(shifts).item())  # cuda_renderer.cpp:357
         _check(lib().mnv_tree_prune(self._h, _dptr(td), _dptr(shifts), first, num, _stream_ptr(stream)))
         return num
+
+    # ---- sub-module split across GPUs (csrc/mnv_multigpu.cu) ---------------------------------
+    def render_partial(self, cam, opt: RenderOptions, dst_ptrs, block_pixels: int, slot: int, stream=None):
+        """March the frame clipped to opt.render_bbox and store each ray's premultiplied (r, g, b, alpha) into
+        the owners' buffers (`dst_ptrs`: device addresses, local or IPC-mapped peers)."""
+        cam = make_camera(cam)
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(a)) for a in dst_ptrs])
+        _check(lib().mnv_render_voxels_partial(self._h, C.byref(cam), C.byref(opt), len(dst_ptrs), arr,
+                                               block_pixels, slot, _stream_ptr(stream)))
+
+    def composite_partials(self, cam, opt: RenderOptions, partials_ptr: int, n: int, block_pixels: int, boxes,
+                           first_pixel: int, n_pixels: int, out, flags_ptr: int = 0, wait_value: int = 0, stream=None):
+        cam = make_camera(cam)
+        bx = np.ascontiguousarray(boxes, np.float32)
+        _check(lib().mnv_composite_partials(self._h, C.byref(cam), C.byref(opt), C.c_void_p(partials_ptr), n,
+                                            block_pixels, bx.ctypes.data, first_pixel, n_pixels, _dptr(out),
+                                            C.c_void_p(flags_ptr) if flags_ptr else None, wait_value,
+                                            _stream_ptr(stream)))
+        return out
 
     def render_frame_host(self, cam, opt, rgba_host=None, stats: bool = False, bands=None):
         """The per-frame call with HOST buffers (camera in, RGBA8 frame out).

@@ -285,6 +285,7 @@ int mnv_tree_destroy(mnv_tree *h) {
     cudaFree(t.split_dev);
     cudaFree(t.sample_dev);
     cudaFree(t.stats_dev);
+    cudaFree(t.partial_table_dev);
     if (t.stream) cudaStreamDestroy(t.stream);
     delete h;
     return MNV_OK;
@@ -586,6 +587,67 @@ int mnv_tree_prune_unvisited(mnv_tree *h, int32_t *visited_dev, int64_t *num_del
     if (!h || !visited_dev) return MNV_ERR_INVALID;
     MNV_CUDA(cudaSetDevice(h->t.device));
     return prune_unvisited(h->t, visited_dev, num_deleted_host, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt, int n_owners,
+                              float *const *partial_dst, int block_pixels, int slot, void *stream) {
+    if (!h || !cam || !opt || !partial_dst || n_owners < 1 || n_owners > 8) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    DeviceTree &t = h->t;
+    if (!t.partial_table_dev) MNV_CUDA(cudaMalloc(&t.partial_table_dev, 8 * sizeof(void *)));
+    bool changed = false;
+    for (int i = 0; i < n_owners; ++i) {
+        if (!partial_dst[i]) return MNV_ERR_INVALID;
+        changed |= t.partial_table_host[i] != partial_dst[i];
+        t.partial_table_host[i] = partial_dst[i];
+    }
+    if (changed)  // pageable source: the copy is staged before the call returns
+        MNV_CUDA(cudaMemcpyAsync(t.partial_table_dev, t.partial_table_host, 8 * sizeof(void *), cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+    RenderTargets tg;
+    tg.partial_n = n_owners;
+    tg.partial_block = block_pixels;
+    tg.partial_slot = slot;
+    tg.partial_dst = reinterpret_cast<float4 *const *>(t.partial_table_dev);
+    return launch_render_voxels(h->t, *cam, *opt, tg, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_signal_peers(uint32_t *const *flag_dst, int n, int slot, uint32_t value, void *stream) {
+    if (!flag_dst) return MNV_ERR_INVALID;
+    return launch_signal_peers(flag_dst, n, slot, value, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_composite_partials(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                           const float *partials_dev, int n, int block_pixels, const float *boxes_host,
+                           int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
+                           uint32_t wait_value, void *stream) {
+    if (!h || !cam || !opt) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return launch_composite_partials(h->t, *cam, *opt, partials_dev, n, block_pixels, boxes_host, first_pixel,
+                                     n_pixels, rgba_dev, flags_dev, wait_value, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_ipc_export(void *ptr_dev, uint8_t handle[64]) {
+    if (!ptr_dev || !handle) return MNV_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t hd;
+    MNV_CUDA(cudaIpcGetMemHandle(&hd, ptr_dev));
+    std::memcpy(handle, &hd, 64);
+    return MNV_OK;
+}
+int mnv_ipc_open(const uint8_t handle[64], void **ptr_dev, int device) {
+    if (!ptr_dev || !handle) return MNV_ERR_INVALID;
+    int rc = check_device(device);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle, 64);
+    MNV_CUDA(cudaIpcOpenMemHandle(ptr_dev, hd, cudaIpcMemLazyEnablePeerAccess));
+    return MNV_OK;
+}
+int mnv_ipc_close(void *ptr_dev) {
+    if (ptr_dev) MNV_CUDA(cudaIpcCloseMemHandle(ptr_dev));
+    return MNV_OK;
 }
 
 int mnv_model_create(mnv_model **out, int n_submodules, const mnv_mlp_desc *descs,

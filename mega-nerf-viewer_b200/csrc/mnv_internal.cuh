@@ -69,6 +69,8 @@ struct DeviceTree {
     float *split_dev = nullptr, *sample_dev = nullptr;
     size_t frame_bytes = 0;
     unsigned long long *stats_dev = nullptr;
+    void **partial_table_dev = nullptr;  // 8 pointers: where the owners' partial buffers are mapped on this GPU
+    void *partial_table_host[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t stream = nullptr;
 };
 
@@ -125,6 +127,11 @@ struct RenderTargets {
     unsigned long long *frame_stats = nullptr;  // [4] rays, visits, shaded, rays_hit
     // image-tile partition (multi-GPU): render tiles with (tile % mod) == rem
     int tile_w = 0, tile_h = 0, tile_mod = 1, tile_rem = 0;
+    // sub-module split (multi-GPU): instead of an image, write the ray's premultiplied partial
+    // (r, g, b, alpha) into the memory of the GPU that owns the pixel — pixel p belongs to owner
+    // p / partial_block and lands in its buffer [partial_slot][p % partial_block] (local or peer pointers)
+    float4 *const *partial_dst = nullptr;  // device table of partial_n pointers
+    int partial_n = 0, partial_block = 0, partial_slot = 0;
 };
 
 int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
@@ -195,6 +202,13 @@ int fill_uniform(float *ptr, int64_t n, uint64_t seed, cudaStream_t stream);
 int fill_f32(float *ptr, float v, int64_t n, cudaStream_t stream);
 int fill_i32(int32_t *ptr, int32_t v, int64_t n, cudaStream_t stream);
 int prune_unvisited(DeviceTree &t, int32_t *visited_dev, int64_t *num_deleted, cudaStream_t stream);
+
+// ---- sub-module split across GPUs (mnv_multigpu.cu) ------------------------------------
+int launch_signal_peers(uint32_t *const *flag_dst_host, int n, int slot, uint32_t value, cudaStream_t stream);
+int launch_composite_partials(const DeviceTree &tree, const mnv_camera &cam, const mnv_render_options &opt,
+                              const float *partials_dev, int n, int block, const float *boxes_host,
+                              int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
+                              uint32_t wait_value, cudaStream_t stream);
 
 // ---- candidate selection / sub-module dispatch (mnv_select.cu) ------------------
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,

@@ -394,6 +394,13 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         }
     }
 
+    if (p.tg.partial_n > 0) {
+        // sub-module split: this GPU's segment of the ray, premultiplied, straight into the owner's memory
+        const int owner = idx / p.tg.partial_block;
+        p.tg.partial_dst[owner][(size_t) p.tg.partial_slot * p.tg.partial_block + (idx - owner * p.tg.partial_block)] =
+                make_float4(RS(kRsOut0), RS(kRsOut1), RS(kRsOut2), out3);
+        return;
+    }
     // ---- composite_and_write, renderer_kernel.cu:215-241 --------------------
     const float nalpha = __fadd_rn(1.f, -out3);
     float out0 = RS(kRsOut0), out1 = RS(kRsOut1), out2 = RS(kRsOut2);
@@ -531,7 +538,13 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
         set_error("camera size %dx%d", cam.width, cam.height);
         return MNV_ERR_INVALID;
     }
-    if ((tg.image_linear == nullptr) == (tg.image_surf == 0)) {
+    if (tg.partial_n > 0) {
+        if (tg.partial_n > 8 || tg.partial_block <= 0 || tg.partial_slot < 0 || tg.to_split || tg.visit_hash ||
+            (int64_t) tg.partial_n * tg.partial_block < (int64_t) cam.width * cam.height || !tg.offscreen) {
+            set_error("bad partial-output arguments");
+            return MNV_ERR_INVALID;
+        }
+    } else if ((tg.image_linear == nullptr) == (tg.image_surf == 0)) {
         set_error("exactly one of image_linear / image surface must be given");
         return MNV_ERR_INVALID;
     }

@@ -1,0 +1,189 @@
+"""Sub-module split across the GPUs of one box (second mode) — host plumbing.
+
+One process per GPU.  Rank g owns cell g of the Mega-NeRF (y, z) grid: the restriction of the
+octree to that cell (and, for guided sampling / refinement, that cell's sub-MLP).  Per frame every
+rank marches all rays through its cell, the march kernel stores each ray's partial straight into the
+memory of the rank that owns the pixel (peer stores over NVLink through CUDA-IPC mappings), raises a
+flag there, and every rank composites its contiguous block of P / world pixels.  torch.distributed is
+used ONCE, at set-up, to exchange the 64-byte IPC handles; the per-frame data path has no collective
+and no host synchronisation between ranks (csrc/mnv_multigpu.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import synth
+
+
+def block_pixels(n_pixels: int, world: int) -> int:
+    """Pixels per owner: contiguous ranges of the row-major frame, the last one may be short."""
+    return (n_pixels + world - 1) // world
+
+
+def owner_range(n_pixels: int, world: int, rank: int):
+    b = block_pixels(n_pixels, world)
+    first = min(rank * b, n_pixels)
+    return first, max(0, min(b, n_pixels - first))
+
+
+class DeviceBuffer:
+    """cudaMalloc'd (not torch-cached) device memory: its base address can be exported over CUDA IPC."""
+
+    def __init__(self, nbytes: int, device: int):
+        from . import _check, lib
+
+        self.ptr = C.c_void_p()
+        self.nbytes = nbytes
+        _check(lib().mnv_malloc(C.byref(self.ptr), nbytes, device))
+        _check(lib().mnv_memset(self.ptr, 0, nbytes, None))
+
+    def handle(self) -> bytes:
+        from . import _check, lib
+
+        buf = C.create_string_buffer(64)
+        _check(lib().mnv_ipc_export(self.ptr, buf))
+        return buf.raw
+
+    def free(self):
+        from . import lib
+
+        if self.ptr:
+            lib().mnv_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+def open_handle(handle: bytes, device: int) -> int:
+    from . import _check, lib
+
+    p = C.c_void_p()
+    _check(lib().mnv_ipc_open(handle, C.byref(p), device))
+    return p.value
+
+
+class SubmoduleSplit:
+    """Per-rank state of the split renderer.  `dist` is torch.distributed (initialised) or None for a
+    single process that plays every rank in turn on one GPU (tests)."""
+
+    def __init__(self, tree, width: int, height: int, rank: int = 0, world: int = 1, device: int = 0,
+                 dist=None, grid_dim=None, restrict: bool = True):
+        import torch
+
+        from . import DeviceTree
+
+        self.rank, self.world, self.device, self.dist = rank, world, device, dist
+        self.P = width * height
+        self.block = block_pixels(self.P, world)
+        self.grid_dim = tuple(grid_dim) if grid_dim is not None else synth.grid_for_world(world)
+        self.boxes = synth.cell_boxes(self.grid_dim, world)
+        assert self.boxes.shape[0] == world, "one spatial cell per rank"
+        self.single = dist is None
+        cells = range(world) if self.single else [rank]
+        self.trees = {}
+        for c in cells:
+            sub = synth.restrict_tree(tree, self.boxes[c]) if restrict and world > 1 else tree
+            self.trees[c] = DeviceTree(sub, device=device)
+        self.local_nodes = sum(t.capacity for t in self.trees.values())
+        # receive side: [world slots][block] float4 partials + [world] u32 flags
+        self.partials = DeviceBuffer(world * self.block * 16, device)
+        self.flags = DeviceBuffer(64, device)
+        self.frame_id = 0
+        if self.single:
+            self.dst = [self.partials.ptr.value] * world
+            self.flag_dst = [self.flags.ptr.value] * world
+        else:
+            mine = (self.partials.handle(), self.flags.handle())
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            self.dst, self.flag_dst, self._opened = [], [], []
+            for r, (hp, hf) in enumerate(everyone):
+                if r == rank:
+                    self.dst.append(self.partials.ptr.value)
+                    self.flag_dst.append(self.flags.ptr.value)
+                else:
+                    a, b = open_handle(hp, device), open_handle(hf, device)
+                    self._opened += [a, b]
+                    self.dst.append(a)
+                    self.flag_dst.append(b)
+            dist.barrier()
+        self.out = torch.empty(self.block * 4, dtype=torch.uint8, device=f"cuda:{device}")
+
+    def _opt_for(self, opt, cell):
+        from . import RenderOptions
+
+        o = RenderOptions()
+        C.memmove(C.byref(o), C.byref(opt), C.sizeof(RenderOptions))
+        # intersection of the caller's render_bbox with the cell
+        for a in range(3):
+            o.render_bbox[a] = max(opt.render_bbox[a], float(self.boxes[cell][a]))
+            o.render_bbox[a + 3] = min(opt.render_bbox[a + 3], float(self.boxes[cell][a + 3]))
+        return o
+
+    def march(self, cam, opt, stream=None):
+        """This rank's segment of every ray -> the owners' memories, then the flags."""
+        from . import _check, _stream_ptr, lib
+
+        self.frame_id += 1
+        for cell, dt in self.trees.items():
+            dt.render_partial(cam, self._opt_for(opt, cell), self.dst, self.block, cell, stream=stream)
+            if not self.single:
+                arr = (C.c_void_p * self.world)(*[C.c_void_p(a) for a in self.flag_dst])
+                _check(lib().mnv_signal_peers(arr, self.world, cell, self.frame_id, _stream_ptr(stream)))
+
+    def composite(self, cam, opt, owner=None, stream=None):
+        """RGBA8 of this rank's pixel block (device tensor [n_pixels, 4])."""
+        owner = self.rank if owner is None else owner
+        first, n = owner_range(self.P, self.world, owner)
+        dt = next(iter(self.trees.values()))
+        dt.composite_partials(cam, opt, self.partials.ptr.value, self.world, self.block, self.boxes, first, n,
+                              self.out, flags_ptr=0 if self.single else self.flags.ptr.value,
+                              wait_value=self.frame_id, stream=stream)
+        return self.out[: n * 4].view(n, 4)
+
+    def render_block(self, cam, opt, stream=None):
+        self.march(cam, opt, stream)
+        return self.composite(cam, opt, stream=stream)
+
+    def render_full_single(self, cam, opt):
+        """Single-process mode: the whole frame, every owner's block in turn (tests)."""
+        import torch
+
+        assert self.single
+        cam_w, cam_h = (cam["width"], cam["height"]) if isinstance(cam, dict) else (cam.width, cam.height)
+        frame = torch.empty((self.P, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+        # with one receive buffer the owners are processed one at a time: march fills block `o` of every slot
+        for o in range(self.world):
+            first, n = owner_range(self.P, self.world, o)
+            self._march_for_owner(cam, opt, o)
+            frame[first:first + n] = self.composite(cam, opt, owner=o).clone()
+        return frame.view(cam_h, cam_w, 4)
+
+    def _march_for_owner(self, cam, opt, owner):
+        # every slot writes pixel p to dst[p // block]; in single mode all dst alias one buffer, so only the
+        # pixels of `owner` may land: pass a scratch buffer for the other owners
+        if not hasattr(self, "_scratch"):
+            self._scratch = DeviceBuffer(self.world * self.block * 16, self.device)
+        dst = [self._scratch.ptr.value] * self.world
+        dst[owner] = self.partials.ptr.value
+        self.frame_id += 1
+        for cell, dt in self.trees.items():
+            dt.render_partial(cam, self._opt_for(opt, cell), dst, self.block, cell)
+
+    def close(self):
+        from . import lib
+
+        import torch
+
+        torch.cuda.synchronize()
+        if not self.single:
+            self.dist.barrier()
+            for a in self._opened:
+                lib().mnv_ipc_close(C.c_void_p(a))
+            self.dist.barrier()
+        for t in self.trees.values():
+            t.close()
+        self.partials.free()
+        self.flags.free()
+        if hasattr(self, "_scratch"):
+            self._scratch.free()

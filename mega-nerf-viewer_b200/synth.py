@@ -263,3 +263,94 @@ def default_camera(width: int = 1920, height: int = 1080, pose: int = 0, n_poses
         width=width, height=height, fx=float(fx), fy=float(fx), cx=width / 2.0, cy=height / 2.0,
         c2w=np.concatenate([right, up, back, center.astype(np.float32)]).astype(np.float32),
     )
+
+
+def make_mlp_weights(seed: int = 3, basis_dim: int = 9, n_appearance: int = 4, appearance_dim: int = 48,
+                     need_viewdir: bool = False, width: int = 256, n_layers: int = 8, skip_layer: int = 4,
+                     pe_xyz: int = 12, pe_dir: int = 4, head_width: int = 128, sigma_activation: int = 1) -> dict:
+    """Random-init Mega-NeRF sub-MLP of the shapes BASELINE.json names,
+    PyTorch's default initialisers restated in numpy (nn.Linear: U(-1/sqrt(in), 1/sqrt(in)) for weight
+    and bias; nn.Embedding: N(0, 1)).  Returns the dict mega_nerf_viewer_b200.MlpModel takes."""
+    rng = np.random.default_rng(seed)
+
+    def linear(n_out, n_in):
+        k = 1.0 / np.sqrt(n_in)
+        return (rng.uniform(-k, k, (n_out, n_in)).astype(np.float32), rng.uniform(-k, k, n_out).astype(np.float32))
+
+    pe = 3 + 6 * pe_xyz
+    trunk = [linear(width, pe if i == 0 else (width + pe if i == skip_layer else width)) for i in range(n_layers)]
+    sigma_w, sigma_b = linear(1, width)
+    final_w, final_b = linear(width, width)
+    head_in = width + ((3 + 6 * pe_dir) if need_viewdir else 0) + appearance_dim
+    head1_w, head1_b = linear(head_width, head_in)
+    head2_w, head2_b = linear(3 * basis_dim, head_width)
+    return dict(
+        trunk_w=[w for w, _ in trunk], trunk_b=[b for _, b in trunk], sigma_w=sigma_w, sigma_b=sigma_b,
+        final_w=final_w, final_b=final_b,
+        embedding=rng.standard_normal((n_appearance, appearance_dim)).astype(np.float32) if appearance_dim > 0 else None,
+        head1_w=head1_w, head1_b=head1_b, head2_w=head2_w, head2_b=head2_b, skip_layer=skip_layer,
+        pe_xyz_freqs=pe_xyz, pe_dir_freqs=pe_dir, need_viewdir=need_viewdir, sigma_activation=sigma_activation)
+
+
+def cell_boxes(grid_dim, n_cells: int | None = None) -> np.ndarray:
+    """Tree-space boxes [n, 6] = (lo xyz, hi xyz) of the Mega-NeRF (y, z) cluster grid (the rule of
+    rt_core.cuh:541-549: cell = gy * grid_dim[1] + gz over the y and z extents; x is not split)."""
+    g0, g1 = int(grid_dim[0]), int(grid_dim[1])
+    out = []
+    for gy in range(g0):
+        for gz in range(g1):
+            out.append([0.0, gy / g0, gz / g1, 1.0, (gy + 1) / g0, (gz + 1) / g1])
+    out = np.asarray(out, np.float32)
+    return out if n_cells is None else out[:n_cells]
+
+
+def grid_for_world(world: int):
+    """(y, z) cell grid used when the sub-modules are sharded over `world` GPUs."""
+    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}[world]
+
+
+def restrict_tree(tree: HostTree, box) -> HostTree:
+    """The part of `tree` a GPU that owns the tree-space `box` needs: every subtree that does not
+    overlap the box is replaced by one empty leaf (sigma 0).  Leaf data inside the box, and the
+    leaf-visit sequence of any ray clipped to the box, are unchanged."""
+    lo, hi = np.asarray(box[:3], np.float64), np.asarray(box[3:], np.float64)
+    D = tree.data_dim
+    nodes = np.array([0], np.int64)         # old node ids of the current level
+    coords = np.zeros((1, 3), np.int64)     # cell coordinates of those nodes at their level
+    level = 0
+    new_child, new_parent, new_depth, new_data = [], [], [], []
+    n_new = 1
+    new_id_of = [np.array([0], np.int64)]
+    parents_packed = [np.array([0], np.int64)]
+    while nodes.size:
+        bits = np.stack(np.meshgrid([0, 1], [0, 1], [0, 1], indexing="ij"), -1).reshape(8, 3)
+        ccoord = coords[:, None, :] * 2 + bits[None]                    # [n, 8, 3] at level+1
+        size = 1.0 / (1 << (level + 1))
+        clo, chi = ccoord * size, (ccoord + 1) * size
+        overlap = np.all((clo < hi) & (chi > lo), axis=-1)                # [n, 8]
+        rel = tree.child[nodes]                                           # [n, 8]
+        keep = (rel != 0) & overlap
+        data = tree.data[nodes].copy()
+        cut = (rel != 0) & ~overlap
+        data[cut] = 0                                                     # pruned subtree -> empty leaf
+        my_ids = new_id_of[-1]
+        kn, kc = np.nonzero(keep)
+        next_ids = n_new + np.arange(kn.size, dtype=np.int64)
+        ch = np.zeros_like(rel)
+        ch[kn, kc] = (next_ids - my_ids[kn]).astype(np.int32)
+        new_child.append(ch)
+        new_data.append(data)
+        new_depth.append(np.full(nodes.size, level, np.int32))
+        new_parent.append(parents_packed[-1])
+        parents_packed.append(my_ids[kn] * 8 + kc)
+        new_id_of.append(next_ids)
+        n_new += kn.size
+        nodes = nodes[kn] + rel[kn, kc]
+        coords = ccoord[kn, kc]
+        level += 1
+    return HostTree(N=2, data_dim=D, data_format=tree.data_format,
+                    child=np.concatenate(new_child).astype(np.int32),
+                    parent=np.concatenate(new_parent).astype(np.int32),
+                    depth=np.concatenate(new_depth).astype(np.int32),
+                    data=np.concatenate(new_data).astype(np.float16),
+                    scale=tree.scale.copy(), offset=tree.offset.copy())
