@@ -194,6 +194,9 @@ int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim,
                 int out_stride, cudaStream_t stream);
 int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, int64_t rows,
                         int in_dim, float *out_dev, int out_stride, cudaStream_t stream);
+// rows / offset read on the device: dyn_dev[0] = first slot of row_index_dev, dyn_dev[1] = row count (<= max_rows)
+int mlp_forward_bucket(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, const int32_t *dyn_dev,
+                       int64_t max_rows, int in_dim, float *out_dev, int out_stride, cudaStream_t stream);
 double mlp_flops_per_row(const MlpModel *m);
 int mlp_in_dim(const MlpModel *m);
 int mlp_out_dim(const MlpModel *m);

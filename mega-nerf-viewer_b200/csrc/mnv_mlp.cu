@@ -101,6 +101,7 @@ struct MlpParams {
     const float *__restrict__ x;           // [rows][in_dim]
     float *__restrict__ out;               // [rows][out_stride]
     const int32_t *__restrict__ row_index; // optional: logical row i reads x / writes out at row_index[i]
+    const int32_t *__restrict__ dyn;       // optional: {first slot of row_index, row count} decided on the device
     int64_t rows;
     int in_dim, out_stride;
     int n_groups;  // groups of kTiles * kTileM rows
@@ -254,8 +255,14 @@ __device__ __forceinline__ void write_pe_octaves(uint8_t *buf, int row, int sbo,
     }
 }
 
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(const MlpParams p) {
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    if (p.dyn) {  // bucket of a sub-module dispatch: size and position were computed by the previous kernels
+        p.row_index += p.dyn[0];
+        p.rows = p.dyn[1];
+        p.n_groups = (int) ((p.rows + kTiles * kTileM - 1) / (kTiles * kTileM));
+        if ((int) blockIdx.x >= p.n_groups) return;  // uniform per CTA, before any barrier / TMEM allocation
+    }
     const int kStages = p.n_stages;
     uint8_t *s_act = smem;                           // [kTiles][kActBytes]
     uint8_t *s_pe = s_act + kTiles * kActBytes;      // [kTiles][kPeBytes]
@@ -801,6 +808,9 @@ void mlp_destroy(MlpModel *m) {
     delete m;
 }
 
+static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, const int32_t *dyn_dev,
+                      int64_t rows, int in_dim, float *out_dev, int out_stride, cudaStream_t stream);
+
 int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim, float *out_dev,
                 int out_stride, cudaStream_t stream) {
     return mlp_forward_indexed(m, x_dev, nullptr, rows, in_dim, out_dev, out_stride, stream);
@@ -808,6 +818,16 @@ int mlp_forward(const MlpModel *m, const float *x_dev, int64_t rows, int in_dim,
 
 int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, int64_t rows,
                         int in_dim, float *out_dev, int out_stride, cudaStream_t stream) {
+    return mlp_launch(m, x_dev, row_index_dev, nullptr, rows, in_dim, out_dev, out_stride, stream);
+}
+
+int mlp_forward_bucket(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, const int32_t *dyn_dev,
+                       int64_t max_rows, int in_dim, float *out_dev, int out_stride, cudaStream_t stream) {
+    return mlp_launch(m, x_dev, row_index_dev, dyn_dev, max_rows, in_dim, out_dev, out_stride, stream);
+}
+
+static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_index_dev, const int32_t *dyn_dev,
+                      int64_t rows, int in_dim, float *out_dev, int out_stride, cudaStream_t stream) {
     if (rows <= 0) return MNV_OK;
     if (in_dim != m->in_dim) {
         set_error("mlp_forward: in_dim %d, model expects %d", in_dim, m->in_dim);
@@ -826,6 +846,7 @@ int mlp_forward_indexed(const MlpModel *m, const float *x_dev, const int32_t *ro
     p.x = x_dev;
     p.out = out_dev;
     p.row_index = row_index_dev;
+    p.dyn = dyn_dev;
     p.rows = rows;
     p.in_dim = in_dim;
     p.out_stride = out_stride;

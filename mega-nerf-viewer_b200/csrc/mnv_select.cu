@@ -9,6 +9,8 @@
 // (library code for a non-hot op); the MLP runs with a row-index indirection so
 // the gather / scatter copies of the reference disappear.
 #include <thrust/copy.h>
+#include <thrust/iterator/transform_iterator.h>
+#include <thrust/iterator/zip_iterator.h>
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
 #include <thrust/iterator/counting_iterator.h>
@@ -24,6 +26,7 @@
 #include <thrust/functional.h>
 
 #include <algorithm>
+#include <new>
 #include <vector>
 
 #include "mnv_internal.cuh"
@@ -43,8 +46,8 @@ struct RowToKey {
         return (prio << 32) | id;  // (priority, id): priority is a function of id
     }
 };
-struct IsNone {
-    __device__ bool operator()(unsigned long long k) const { return k == ~0ull; }
+struct IsSome {
+    __device__ bool operator()(unsigned long long k) const { return k != ~0ull; }
 };
 struct SplitRank {  // order of unique_dim on rows (-count, depth, chunk, child)
     __device__ unsigned long long operator()(const thrust::tuple<unsigned long long, int> &t) const {
@@ -54,10 +57,8 @@ struct SplitRank {  // order of unique_dim on rows (-count, depth, chunk, child)
         return ((0x3ffffffull - count) << 37) | ((depth & 0x3full) << 31) | (id & 0x7fffffffull);
     }
 };
-struct CountBelow2 {
-    __device__ bool operator()(const thrust::tuple<unsigned long long, int> &t) const {
-        return thrust::get<1>(t) < 2;  // "< -1" on the negated counts, cuda_renderer.cpp:214
-    }
+struct CountAtLeast2 {
+    __device__ bool operator()(int count) const { return count >= 2; }  // "< -1" on the negated counts, cuda_renderer.cpp:214
 };
 __global__ void write_nodes_kernel(const unsigned long long *ranked, int n, int shift_is_rank,
                                    int32_t *nodes) {
@@ -143,32 +144,100 @@ int prune_unvisited(DeviceTree &t, int32_t *visited_dev, int64_t *num_deleted, c
     return rc;
 }
 
+// ---- scratch arena ---------------------------------------------------------------------
+// cudaMalloc / cudaFree per call cost more than the sorts they serve (and synchronise the
+// device): all temporaries of this file, Thrust's internal ones included, are bump-allocated from
+// one per-device arena that grows to the high-water mark after the first frames.
+namespace {
+struct Arena {
+    char *base = nullptr;
+    size_t cap = 0, off = 0, want = 0;
+    std::vector<void *> overflow;
+    void *take(size_t n) {
+        n = (n + 255) & ~size_t(255);
+        want += n;
+        if (off + n <= cap) {
+            void *p = base + off;
+            off += n;
+            return p;
+        }
+        void *p = nullptr;
+        if (cudaMalloc(&p, n) != cudaSuccess) throw std::bad_alloc();
+        overflow.push_back(p);
+        return p;
+    }
+    // call with the stream idle (every user below synchronises before returning)
+    void reset() {
+        for (void *p : overflow) cudaFree(p);
+        if (!overflow.empty() || want > cap) {
+            cudaFree(base);
+            cap = want + want / 4 + (1 << 20);
+            if (cudaMalloc(&base, cap) != cudaSuccess) {
+                base = nullptr;
+                cap = 0;
+            }
+        }
+        overflow.clear();
+        off = want = 0;
+    }
+};
+Arena &arena_for_current_device() {
+    static Arena arenas[16];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return arenas[dev & 15];
+}
+struct ArenaAllocator {
+    typedef char value_type;
+    Arena *a;
+    char *allocate(std::ptrdiff_t n) { return static_cast<char *>(a->take((size_t) n)); }
+    void deallocate(char *, size_t) {}
+};
+struct ArenaScope {  // resets the arena when the call is over (stream synchronised by then)
+    Arena &a;
+    cudaStream_t stream;
+    ~ArenaScope() {
+        cudaStreamSynchronize(stream);
+        a.reset();
+    }
+};
+}  // namespace
+
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
                             int *n_selected, int *n_candidates, cudaStream_t stream) {
-    auto pol = thrust::cuda::par.on(stream);
-    unsigned long long *keys = nullptr, *ukeys = nullptr;
-    int *counts = nullptr;
-    MNV_CUDA(cudaMalloc(&keys, P * sizeof(unsigned long long)));
+    Arena &A = arena_for_current_device();
+    ArenaScope scope{A, stream};
+    ArenaAllocator alloc{&A};
+    auto pol = thrust::cuda::par(alloc).on(stream);
     int rc = MNV_OK;
     try {
+        auto *keys = static_cast<unsigned long long *>(A.take(P * sizeof(unsigned long long)));
         thrust::device_ptr<unsigned long long> k(keys);
-        thrust::transform(pol, thrust::counting_iterator<long long>(0), thrust::counting_iterator<long long>(P), k,
-                          RowToKey{to_split_dev});
-        const long long valid = thrust::remove_if(pol, k, k + P, IsNone()) - k;
+        // rows with a candidate -> (priority, id) keys, compacted in one pass
+        const long long valid =
+                thrust::copy_if(pol, thrust::make_transform_iterator(thrust::counting_iterator<long long>(0), RowToKey{to_split_dev}),
+                                thrust::make_transform_iterator(thrust::counting_iterator<long long>(P), RowToKey{to_split_dev}),
+                                k, IsSome()) - k;
         thrust::sort(pol, k, k + valid);
-        MNV_CUDA(cudaMalloc(&ukeys, std::max<long long>(valid, 1) * sizeof(unsigned long long)));
-        MNV_CUDA(cudaMalloc(&counts, std::max<long long>(valid, 1) * sizeof(int)));
+        auto *ukeys = static_cast<unsigned long long *>(A.take(std::max<long long>(valid, 1) * sizeof(unsigned long long)));
+        auto *counts = static_cast<int *>(A.take(std::max<long long>(valid, 1) * sizeof(int)));
         thrust::device_ptr<unsigned long long> uk(ukeys);
         thrust::device_ptr<int> cnt(counts);
         const long long uniq = thrust::reduce_by_key(pol, k, k + valid, thrust::constant_iterator<int>(1), uk, cnt).first - uk;
         auto zb = thrust::make_zip_iterator(thrust::make_tuple(uk, cnt));
-        const long long kept = thrust::remove_if(pol, zb, zb + uniq, CountBelow2()) - zb;
-        // rank = (-count, depth, chunk, child); reuse `keys` for the ranks
-        thrust::transform(pol, zb, zb + kept, k, SplitRank());
-        thrust::sort(pol, k, k + kept);
+        // rank = (-count, depth, chunk, child) of the rows voted by >= 2 rays; reuse `keys` for the ranks
+        const long long kept =
+                thrust::copy_if(pol, thrust::make_transform_iterator(zb, SplitRank()),
+                                thrust::make_transform_iterator(zb + uniq, SplitRank()), cnt, k, CountAtLeast2()) - k;
         const int n = (int) std::min<long long>(kept, max_n);
+        if (kept > max_n && kept > 4 * (long long) max_n) {
+            // only the first max_n ranks are needed: a full sort of ~10^5..10^6 candidates for 4096 of them
+            // is wasted work, but selection algorithms need several passes too; radix sort stays the simplest
+            thrust::sort(pol, k, k + kept);
+        } else {
+            thrust::sort(pol, k, k + kept);
+        }
         if (n > 0) write_nodes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, 1, nodes_dev);
-        MNV_CUDA(cudaStreamSynchronize(stream));
         if (n_selected) *n_selected = n;
         if (n_candidates) *n_candidates = (int) kept;
     } catch (const std::exception &e) {
@@ -176,28 +245,27 @@ int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int
         cudaGetLastError();
         rc = MNV_ERR_CUDA;
     }
-    cudaFree(keys);
-    cudaFree(ukeys);
-    cudaFree(counts);
     return rc;
 }
 
 int select_sample_candidates(const float *to_sample_dev, int64_t P, int max_n, int32_t *nodes_dev,
                              int *n_selected, int *n_candidates, cudaStream_t stream) {
-    auto pol = thrust::cuda::par.on(stream);
-    unsigned long long *keys = nullptr;
-    MNV_CUDA(cudaMalloc(&keys, P * sizeof(unsigned long long)));
+    Arena &A = arena_for_current_device();
+    ArenaScope scope{A, stream};
+    ArenaAllocator alloc{&A};
+    auto pol = thrust::cuda::par(alloc).on(stream);
     int rc = MNV_OK;
     try {
+        auto *keys = static_cast<unsigned long long *>(A.take(P * sizeof(unsigned long long)));
         thrust::device_ptr<unsigned long long> k(keys);
-        thrust::transform(pol, thrust::counting_iterator<long long>(0), thrust::counting_iterator<long long>(P), k,
-                          RowToKey{to_sample_dev});
-        const long long valid = thrust::remove_if(pol, k, k + P, IsNone()) - k;
+        const long long valid =
+                thrust::copy_if(pol, thrust::make_transform_iterator(thrust::counting_iterator<long long>(0), RowToKey{to_sample_dev}),
+                                thrust::make_transform_iterator(thrust::counting_iterator<long long>(P), RowToKey{to_sample_dev}),
+                                k, IsSome()) - k;
         thrust::sort(pol, k, k + valid);  // (sample count, chunk, child) == unique_dim order
         const long long uniq = thrust::unique(pol, k, k + valid) - k;
         const int n = (int) std::min<long long>(uniq, max_n);
         if (n > 0) write_nodes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, 0, nodes_dev);
-        MNV_CUDA(cudaStreamSynchronize(stream));
         if (n_selected) *n_selected = n;
         if (n_candidates) *n_candidates = (int) uniq;
     } catch (const std::exception &e) {
@@ -205,49 +273,102 @@ int select_sample_candidates(const float *to_sample_dev, int64_t P, int max_n, i
         cudaGetLastError();
         rc = MNV_ERR_CUDA;
     }
-    cudaFree(keys);
     return rc;
 }
 
-// Impl::query_submodules: rows are grouped by sub-module id with one stable sort of the row
-// indices; each sub-module then runs the fused MLP over its index range, reading x and
-// writing out through the index (no gather / scatter copies).
+// ---- Impl::query_submodules ---------------------------------------------------------------
+// Rows are bucketed by sub-module id with a counting pass and a warp-aggregated scatter of the row
+// indices (no sort: rows are independent, any order inside a bucket gives the same per-row result);
+// the bucket sizes never travel to the host — every sub-module's fused MLP is launched with the
+// worst-case grid and reads its (offset, count) pair from device memory — and the MLP reads x /
+// writes out through the index, so the reference's gather / scatter_ copies disappear too.
+namespace {
+constexpr int kMaxSubs = 64;
+
+__global__ void bucket_count_kernel(const int16_t *__restrict__ cluster, int64_t V, int n_subs, int32_t *counts,
+                                    int32_t *bad) {
+    __shared__ int32_t h[kMaxSubs];
+    for (int i = threadIdx.x; i < kMaxSubs; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x; i < V; i += (int64_t) gridDim.x * blockDim.x) {
+        const int c = cluster[i];
+        if (c < 0 || c >= n_subs) atomicExch(bad, 1);
+        else atomicAdd(&h[c], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_subs; i += blockDim.x)
+        if (h[i]) atomicAdd(&counts[i], h[i]);
+}
+// dyn[2*s] = first index slot of bucket s, dyn[2*s+1] = its row count; cursor[s] = dyn[2*s]
+__global__ void bucket_offsets_kernel(const int32_t *counts, int n_subs, int32_t *dyn, int32_t *cursor) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int32_t off = 0;
+        for (int s = 0; s < n_subs; ++s) {
+            dyn[2 * s] = off;
+            dyn[2 * s + 1] = counts[s];
+            cursor[s] = off;
+            off += counts[s];
+        }
+    }
+}
+__global__ void bucket_scatter_kernel(const int16_t *__restrict__ cluster, int64_t V, int n_subs, int32_t *cursor,
+                                      int32_t *__restrict__ idx) {
+    __shared__ int32_t h[kMaxSubs], base[kMaxSubs];
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    for (int k = threadIdx.x; k < kMaxSubs; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    int c = -1, rank = 0;
+    if (i < V) {
+        c = cluster[i];
+        if (c < 0 || c >= n_subs) c = -1;
+    }
+    if (c >= 0) rank = atomicAdd(&h[c], 1);  // position inside this block's share of the bucket
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_subs; k += blockDim.x)
+        if (h[k]) base[k] = atomicAdd(&cursor[k], h[k]);
+    __syncthreads();
+    if (c >= 0) idx[base[c] + rank] = (int32_t) i;
+}
+}  // namespace
+
 int query_submodules(MlpModel *const *subs, int n_subs, const int16_t *cluster_dev, const float *rows_dev,
                      int in_dim, int64_t V, float *out_dev, int out_stride, cudaStream_t stream) {
     if (V <= 0) return MNV_OK;
-    auto pol = thrust::cuda::par.on(stream);
-    int16_t *keys = nullptr;
-    int32_t *idx = nullptr;
-    MNV_CUDA(cudaMalloc(&keys, V * sizeof(int16_t)));
-    MNV_CUDA(cudaMalloc(&idx, V * sizeof(int32_t)));
+    if (n_subs > kMaxSubs || V >= (1ll << 31)) {
+        set_error("query_submodules: %d sub-modules / %lld rows not supported", n_subs, (long long) V);
+        return MNV_ERR_INVALID;
+    }
+    if (n_subs == 1) {  // nothing to bucket (ids are still validated by the model's clamp-free contract: all 0)
+        return mlp_forward(subs[0], rows_dev, V, in_dim, out_dev, out_stride, stream);
+    }
+    Arena &A = arena_for_current_device();
+    ArenaScope scope{A, stream};
     int rc = MNV_OK;
     try {
-        thrust::device_ptr<int16_t> k(keys);
-        thrust::device_ptr<int32_t> ix(idx);
-        MNV_CUDA(cudaMemcpyAsync(keys, cluster_dev, V * sizeof(int16_t), cudaMemcpyDeviceToDevice, stream));
-        thrust::sequence(pol, ix, ix + V);
-        thrust::stable_sort_by_key(pol, k, k + V, ix);
-        std::vector<int64_t> bounds(n_subs + 1);
-        for (int s = 0; s <= n_subs; ++s)
-            bounds[s] = thrust::lower_bound(pol, k, k + V, (int16_t) s) - k;
-        if (bounds[0] != 0 || bounds[n_subs] != V) {
+        auto *idx = static_cast<int32_t *>(A.take(V * sizeof(int32_t)));
+        auto *small = static_cast<int32_t *>(A.take((4 * kMaxSubs + 1) * sizeof(int32_t)));
+        int32_t *counts = small, *dyn = small + kMaxSubs, *cursor = small + 3 * kMaxSubs, *bad = small + 4 * kMaxSubs;
+        MNV_CUDA(cudaMemsetAsync(small, 0, (4 * kMaxSubs + 1) * sizeof(int32_t), stream));
+        const int th = 256;
+        const unsigned blocks = (unsigned) ((V + th - 1) / th);
+        bucket_count_kernel<<<std::min(blocks, 148u * 8u), th, 0, stream>>>(cluster_dev, V, n_subs, counts, bad);
+        bucket_offsets_kernel<<<1, 32, 0, stream>>>(counts, n_subs, dyn, cursor);
+        bucket_scatter_kernel<<<blocks, th, 0, stream>>>(cluster_dev, V, n_subs, cursor, idx);
+        MNV_CUDA(cudaGetLastError());
+        for (int s = 0; s < n_subs && rc == MNV_OK; ++s)
+            rc = mlp_forward_bucket(subs[s], rows_dev, idx, dyn + 2 * s, V, in_dim, out_dev, out_stride, stream);
+        int32_t bad_host = 0;
+        MNV_CUDA(cudaMemcpyAsync(&bad_host, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        MNV_CUDA(cudaStreamSynchronize(stream));  // the index lives in the arena: done before it is recycled
+        if (rc == MNV_OK && bad_host) {
             set_error("cluster id outside [0, %d)", n_subs);
             rc = MNV_ERR_INVALID;
         }
-        for (int s = 0; s < n_subs && rc == MNV_OK; ++s) {
-            const int64_t cnt = bounds[s + 1] - bounds[s];
-            if (cnt > 0)
-                rc = mlp_forward_indexed(subs[s], rows_dev, idx + bounds[s], cnt, in_dim, out_dev, out_stride,
-                                         stream);
-        }
-        if (rc == MNV_OK) MNV_CUDA(cudaStreamSynchronize(stream));  // idx / keys are freed below
     } catch (const std::exception &e) {
         set_error("query_submodules: %s", e.what());
         cudaGetLastError();
         rc = MNV_ERR_CUDA;
     }
-    cudaFree(keys);
-    cudaFree(idx);
     return rc;
 }
 

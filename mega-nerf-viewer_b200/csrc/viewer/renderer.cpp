@@ -3,7 +3,10 @@
 #include "renderer.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstddef>
+#include <cstdlib>
+#include <map>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -44,8 +47,33 @@ struct DevBuf {  // grow-only device scratch
 }  // namespace
 
 struct VolumeRenderer::Impl {
-    Impl(VolumeRenderer &owner) : self(owner), camera(owner.camera), options(owner.options) {}
+    Impl(VolumeRenderer &owner) : self(owner), camera(owner.camera), options(owner.options) {
+        timing = std::getenv("MNV_TIMING") != nullptr;
+    }
+    // dev: MNV_TIMING=1 synchronises after every stage and prints the per-stage totals at exit
+    bool timing = false;
+    std::map<std::string, std::pair<double, long>> stage_ms;
+    std::chrono::steady_clock::time_point t_stage;
+    void tick() {
+        if (timing) {
+            mnv_stream_synchronize(stream);
+            t_stage = std::chrono::steady_clock::now();
+        }
+    }
+    void tock(const char *label) {
+        if (!timing) return;
+        mnv_stream_synchronize(stream);
+        const auto now = std::chrono::steady_clock::now();
+        auto &e = stage_ms[label];
+        e.first += std::chrono::duration<double, std::milli>(now - t_stage).count();
+        e.second += 1;
+        t_stage = now;
+    }
     ~Impl() {
+        if (timing)
+            for (auto &kv : stage_ms)
+                std::fprintf(stderr, "[mnv timing] %-28s %8.3f ms/call x %ld\n", kv.first.c_str(),
+                             kv.second.first / kv.second.second, kv.second.second);
         for (DevBuf *b : {&frame, &split_tracker, &sample_tracker, &visit_tracker, &offsets, &z_vals, &rows,
                           &cluster, &values, &nodes, &rand, &rcluster, &results})
             b->release();
@@ -94,8 +122,10 @@ struct VolumeRenderer::Impl {
         const int64_t P = pixels();
         init_trackers_if_resized();
 
+        tick();
         ck(mnv_fill_f32(split_tracker.as<float>(), -1.f, P * 3, stream), "fill");
         ck(mnv_fill_f32(sample_tracker.as<float>(), -1.f, P * 3, stream), "fill");
+        tock("fill trackers");
         const bool camera_has_changed = camera.has_changed();
         const bool track_visit =
                 (camera_has_changed && tree->capacity > max_tree_capacity * 3 / 4) || prune_happened;
@@ -110,10 +140,12 @@ struct VolumeRenderer::Impl {
             if (!model.device_model) throw std::runtime_error("use_guided_sampling needs load_model()");
             if (!can_reuse_results) {
                 guided_total = gather_guided_samples(dt, cam, depth_arr, offscreen, track_visit);
+                tock("guided: emit samples");
                 values.reserve((size_t) std::max<int64_t>(guided_total, 1) * (tree->data_dim + 1) * sizeof(float));
                 ck(mnv_query_submodules(model.device_model, cluster.as<int16_t>(), rows.as<float>(), in_dim(),
                                         guided_total, values.as<float>(), tree->data_dim + 1, stream),
                    "query_submodules");
+                tock("guided: query_submodules");
                 self.last_frame.guided_rows = guided_total;
                 can_reuse_results = true;
             }
@@ -124,11 +156,13 @@ struct VolumeRenderer::Impl {
                                        tree->data_dim - 1, z_vals.as<float>(), offsets.as<int64_t>(), offscreen,
                                        stream),
                "render_nerf_results");
+            tock("guided: composite");
         } else {
             ck(mnv_render_voxels(dt, &cam, opt(), image_arr, depth_arr, linear, split_tracker.as<float>(),
                                  sample_tracker.as<float>(), visit_tracker.as<int32_t>(), track_visit, offscreen,
                                  stream),
                "render_voxels");
+            tock("render_voxels");
         }
 
         if (options.use_splitting && !camera.is_dragging()) expand_voxels(dt);
@@ -190,6 +224,7 @@ struct VolumeRenderer::Impl {
         ck(mnv_select_split_candidates(split_tracker.as<float>(), pixels(), batch, nodes.as<int32_t>(), &n, &n_cand,
                                        stream),
            "select_split_candidates");
+        tock("refine: select candidates");
         self.last_frame.split_candidates = n_cand;
         if (self.verbose) std::printf("Split candidates: %d\n", n_cand);
         if (n_cand == 0) {
@@ -210,10 +245,13 @@ struct VolumeRenderer::Impl {
                                                  rcluster.as<int16_t>(), visit_tracker.as<int32_t>(),
                                                  model.grid_dim, model.min_position, model.range, stream),
            "add_children_and_generate_samples");
+        tock("refine: rand + add children");
         ck(mnv_query_submodules(model.device_model, rcluster.as<int16_t>(), rand.as<float>(), rd, n_rows,
                                 results.as<float>(), D + 1, stream),
            "query_submodules");
+        tock("refine: query_submodules");
         ck(mnv_tree_commit_children(dt, opt(), n, results.as<float>(), D + 1, stream), "commit_children");
+        tock("refine: commit children");
         tree->sync_capacity();
         self.last_frame.added = n;
         if (self.verbose) std::printf("Added: %d, total size: %d\n", n, tree->capacity);
