@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-headless", action="store_true", help="skip the config 4 / 5 sections (C++ driver)")
     return ap.parse_args()
 
 
@@ -175,6 +176,46 @@ def mlp_section(mnv, torch, dev, iters=20):
                         "kernel": "mnv::mlp_forward_kernel", "traffic": None}}
     model.close()
     return sec
+
+
+def headless_sections(mnv, tree, W, H):
+    """Configs 4 and 5 of BASELINE.json through the C++ API (viewer::VolumeRenderer via bin/mnv_headless): frames
+    with dynamic refinement on (4192-leaf split batches x 8 children x 8 samples through 8 sub-MLPs per frame) and
+    with guided sampling (per-sample MLP evaluation, 16-pose orbit so every frame re-samples).  Wall clock per
+    frame including the RGBA8 read-back.  Returns {} when the driver binary is missing."""
+    import subprocess
+    import tempfile
+
+    if not os.path.exists(mnv.HEADLESS_BIN):
+        return {}
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        tp, mp = os.path.join(d, "tree.npz"), os.path.join(d, "model.npz")
+        tree.save_npz(tp)
+        subs = [mnv.synth.make_mlp_weights(seed=3 + i) for i in range(8)]
+        mnv.save_model_container(mp, subs, grid_dim=(2, 4), min_position=(-1, -1, -1), max_position=(1, 1, 1))
+
+        def run(*extra):
+            r = subprocess.run([mnv.HEADLESS_BIN, tp, "--model", mp, *map(str, extra)], capture_output=True,
+                               text=True, timeout=600)
+            if r.returncode != 0:
+                return {"error": r.stderr[-300:]}
+            j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+            return {k: j[k] for k in ("width", "height", "frames", "ms_per_frame_median", "fps_median",
+                                      "mrays_per_s_median", "capacity", "guided_rows", "nodes_added")}
+
+        out["refinement"] = dict(run("--width", W, "--height", H, "--frames", 32, "--use_splitting",
+                                     "--max_tree_capacity", tree.capacity + 400000),
+                                 workload="config 4: frame + vote aggregation + 4192 splits + 268288-row MLP batch over "
+                                          "8 sub-modules + commit, every frame")
+        gw, gh = W // 2, H // 2
+        g = run("--width", gw, "--height", gh, "--frames", 8, "--use_guided_sampling")
+        if "guided_rows" in g and g.get("frames"):
+            g["mlp_rows_per_frame"] = g["guided_rows"] / g["frames"]
+            g["mrows_per_s"] = g["mlp_rows_per_frame"] / g["ms_per_frame_median"] / 1e3
+        out["guided_sampling"] = dict(g, workload=f"config 5 on one GPU at {gw}x{gh}: sample emission + per-sample MLP "
+                                                  "over 8 sub-modules + per-ray compositing, every frame")
+    return out
 
 
 def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
@@ -343,6 +384,11 @@ def main():
         "clocks": clocks,
     }
     line["mlp"] = mlp_section(mnv, torch, dev)
+    if world == 1 and not args.no_headless:
+        dt.close()
+        del flush, ts, tp, out
+        torch.cuda.empty_cache()
+        line.update(headless_sections(mnv, tree, W, H))
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle_py as O
         line["cpu_baseline"] = cpu_baseline(tree, cams, O, opt_kw)
@@ -365,7 +411,15 @@ def run_reference(args, tree, cams, opt_kw, config, have_gpu):
         import torch
         npz = "/tmp/mnv_bench_tree.npz"
         tree.save_npz(npz)
-        ref = O.RefRenderer(npz)
+        sys.stdout.flush()
+        saved = os.dup(1)  # the reference's loader prints to stdout: keep this arm's stdout to the one JSON line
+        os.dup2(2, 1)
+        try:
+            ref = O.RefRenderer(npz)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         opt = O.default_options(**opt_kw)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
         sampler = ClockSampler(0)
