@@ -54,6 +54,13 @@ def parse():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--depth", type=int, default=DEPTH)
+    ap.add_argument("--workload", default="1080p", choices=["1080p", "mill19"],
+                    help="1080p: BASELINE.json configs[1] (the driver's run); mill19: configs[2], a 3840x2160 frame of a "
+                         "multi-GB octree of 8 spatial blocks (2x4 on y,z), depth <= 12")
+    ap.add_argument("--mode", default="tiles", choices=["tiles", "split"],
+                    help="N > 1: image tiles with the tree replicated (default) or one spatial cell per GPU with "
+                         "partials composited over NVLink peer stores")
+    ap.add_argument("--max-nodes", type=int, default=16_000_000, help="node budget of the mill19 tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-headless", action="store_true", help="skip the config 4 / 5 sections (C++ driver)")
     return ap.parse_args()
@@ -218,6 +225,31 @@ def headless_sections(mnv, tree, W, H):
     return out
 
 
+def shared_tree(make, rank, world, dist, mnv):
+    """Multi-GB trees are generated once (rank 0) and mapped by the other ranks from /dev/shm."""
+    if world == 1:
+        return make()
+    import shutil
+    d = "/dev/shm/mnv_bench_tree"
+    if rank == 0:
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        t = make()
+        for k in ("child", "parent", "depth", "data", "scale", "offset"):
+            np.save(os.path.join(d, k + ".npy"), getattr(t, k))
+        with open(os.path.join(d, "meta.json"), "w") as f:
+            json.dump({"data_dim": t.data_dim, "data_format": t.data_format}, f)
+    dist.barrier()
+    if rank != 0:
+        with open(os.path.join(d, "meta.json")) as f:
+            meta = json.load(f)
+        a = {k: np.load(os.path.join(d, k + ".npy"), mmap_mode="r") for k in ("child", "parent", "depth", "data", "scale", "offset")}
+        t = mnv.HostTree(N=2, data_dim=meta["data_dim"], data_format=meta["data_format"], child=a["child"],
+                         parent=a["parent"], depth=a["depth"], data=a["data"], scale=np.array(a["scale"]),
+                         offset=np.array(a["offset"]))
+    return t
+
+
 def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
     """CPU oracle (port) on all host cores; bounded sample: whole frames of the
     orbit until ~seconds_budget elapsed (at least one)."""
@@ -258,10 +290,20 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl" if have_gpu else "gloo")
 
-    tree = mnv.synth.make_tree(depth=args.depth, data_format=FMT)
+    if args.workload == "mill19":
+        if (args.width, args.height) == (WIDTH, HEIGHT):
+            W, H = 3840, 2160
+            P = W * H
+        tree = shared_tree(lambda: mnv.synth.make_tree(depth=12, data_format=FMT, blocks_yz=(2, 4),
+                                                        block_depths=[12, 11, 11, 12, 11, 12, 12, 11],
+                                                        max_nodes=args.max_nodes), rank, world, dist, mnv)
+        wl = f"Mill-19-scale: headless {W}x{H} frame, 8 spatial blocks (2x4 on y,z), depth <= 12"
+    else:
+        tree = mnv.synth.make_tree(depth=args.depth, data_format=FMT)
+        wl = f"headless {W}x{H} frame, synthetic depth-{args.depth}"
     cams = [mnv.synth.default_camera(W, H, pose=i, n_poses=N_POSES) for i in range(N_POSES)]
     opt_kw = dict(background_brightness=0.0, basis_minmax=[0, 8])  # CLI bg default; set() basis range
-    config = {"workload": f"headless {W}x{H} frame, synthetic depth-{args.depth} {FMT} N3Tree "
+    config = {"workload": f"{wl} {FMT} N3Tree "
                           f"({tree.capacity} nodes, {tree.nbytes() / 1e9:.2f} GB AoS), {N_POSES}-pose orbit",
               "resolution": [W, H], "tree_nodes": tree.capacity, "data_format": FMT,
               "options": "RenderOptions defaults, background_brightness=0",
@@ -273,6 +315,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the native path has no CPU fallback")
 
     dev = torch.device("cuda", local_rank)
+    if args.mode == "split" and world > 1:
+        return run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, world, local_rank)
     dt = mnv.DeviceTree(tree, device=local_rank)
     opt = mnv.default_options(**opt_kw)
     out = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
@@ -395,6 +439,77 @@ def main():
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+    return 0
+
+
+def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, world, local_rank):
+    """N > 1, --mode split: one spatial cell (restricted subtree) per GPU, every GPU marches every ray through
+    its cell, partials land in the pixel owner's memory as NVLink peer stores, device-side flags, front-to-back
+    composite of each owner's P / N pixels (csrc/mnv_multigpu.cu).  Step = march + signal + composite."""
+    P = W * H
+    dev = torch.device("cuda", local_rank)
+    sp = mnv.multigpu.SubmoduleSplit(tree, W, H, rank=rank, world=world, device=local_rank, dist=dist)
+    opt = mnv.default_options(**opt_kw)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    first, n = mnv.multigpu.owner_range(P, world, rank)
+    host = torch.empty((max(n, 1), 4), dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(steps, warmup, e2e):
+        for i in range(warmup):
+            sp.render_block(cams[i % N_POSES], opt)
+        barrier()
+        ms = []
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            if e2e:
+                t0 = time.perf_counter()
+                blk = sp.render_block(cams[i % N_POSES], opt)
+                host[:n].copy_(blk, non_blocking=True)
+                torch.cuda.synchronize()
+                ms.append((time.perf_counter() - t0) * 1e3)
+            else:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sp.render_block(cams[i % N_POSES], opt)
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+        barrier()
+        t = torch.tensor(ms, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_start = time.time()
+    ms = timed(args.steps, args.warmup, False)
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    e2e_ms = timed(args.steps, 3, True)
+    nodes = torch.tensor([sp.local_nodes], device=dev)
+    dist.all_reduce(nodes, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms_step = float(ms.mean())
+        config = dict(config, parallelism=f"sub-module split: {world} spatial cells, grid {sp.grid_dim} on (y,z); "
+                      f"largest per-GPU subtree {int(nodes.item())} nodes of {tree.capacity}")
+        line = {"metric": "Mrays/s", "value": P / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 storage, fp64 ray setup)",
+                "data": "synthetic", "config": config, "fps": 1e3 / ms_step,
+                "e2e": {"value": P / (float(e2e_ms.mean()) * 1e-3) / 1e6, "unit": "Mrays/s",
+                        "ms_per_step": float(e2e_ms.mean()), "h2d_bytes_per_step": 176,
+                        "d2h_bytes_per_step": int(n) * 4, "api": "multigpu.SubmoduleSplit.render_block + D2H of the owner's block"},
+                "gpu_launches": args.steps * 3,
+                "exchange": {"bytes_per_gpu_per_step": P * 16, "transport": "NVLink peer stores from the march kernel "
+                             "(CUDA IPC mappings), no collective"},
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    sp.close()
+    dist.destroy_process_group()
     return 0
 
 

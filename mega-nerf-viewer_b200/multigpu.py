@@ -85,8 +85,12 @@ class SubmoduleSplit:
             sub = synth.restrict_tree(tree, self.boxes[c]) if restrict and world > 1 else tree
             self.trees[c] = DeviceTree(sub, device=device)
         self.local_nodes = sum(t.capacity for t in self.trees.values())
-        # receive side: [world slots][block] float4 partials + [world] u32 flags
-        self.partials = DeviceBuffer(world * self.block * 16, device)
+        # receive side: [2 frame parities][world slots][block] float4 partials + [world] u32 flags.
+        # Two parities make the frames self-synchronising: a producer can start frame k+1 only after its own
+        # composite of frame k, which waited for every peer's frame-k flag, which each peer raised after its
+        # composite of frame k-1 — so the buffer of parity (k+1) & 1 is no longer being read anywhere.
+        self.stride = world * self.block * 16
+        self.partials = DeviceBuffer(2 * self.stride, device)
         self.flags = DeviceBuffer(64, device)
         self.frame_id = 0
         if self.single:
@@ -125,8 +129,9 @@ class SubmoduleSplit:
         from . import _check, _stream_ptr, lib
 
         self.frame_id += 1
+        par = (self.frame_id & 1) * self.stride
         for cell, dt in self.trees.items():
-            dt.render_partial(cam, self._opt_for(opt, cell), self.dst, self.block, cell, stream=stream)
+            dt.render_partial(cam, self._opt_for(opt, cell), [a + par for a in self.dst], self.block, cell, stream=stream)
             if not self.single:
                 arr = (C.c_void_p * self.world)(*[C.c_void_p(a) for a in self.flag_dst])
                 _check(lib().mnv_signal_peers(arr, self.world, cell, self.frame_id, _stream_ptr(stream)))
@@ -136,7 +141,8 @@ class SubmoduleSplit:
         owner = self.rank if owner is None else owner
         first, n = owner_range(self.P, self.world, owner)
         dt = next(iter(self.trees.values()))
-        dt.composite_partials(cam, opt, self.partials.ptr.value, self.world, self.block, self.boxes, first, n,
+        dt.composite_partials(cam, opt, self.partials.ptr.value + (self.frame_id & 1) * self.stride, self.world,
+                              self.block, self.boxes, first, n,
                               self.out, flags_ptr=0 if self.single else self.flags.ptr.value,
                               wait_value=self.frame_id, stream=stream)
         return self.out[: n * 4].view(n, 4)
@@ -164,9 +170,9 @@ class SubmoduleSplit:
         # pixels of `owner` may land: pass a scratch buffer for the other owners
         if not hasattr(self, "_scratch"):
             self._scratch = DeviceBuffer(self.world * self.block * 16, self.device)
-        dst = [self._scratch.ptr.value] * self.world
-        dst[owner] = self.partials.ptr.value
         self.frame_id += 1
+        dst = [self._scratch.ptr.value] * self.world
+        dst[owner] = self.partials.ptr.value + (self.frame_id & 1) * self.stride
         for cell, dt in self.trees.items():
             dt.render_partial(cam, self._opt_for(opt, cell), dst, self.block, cell)
 

@@ -69,9 +69,16 @@ def main():
     opt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8])
     full = mnv.DeviceTree(tree, device=local) if rank == 0 else None
     worst, fracs, psnrs = 0, [], []
+    # all frames back to back with no host synchronisation between the ranks (the device-side flags and the two
+    # buffer parities order them), results checked afterwards
+    blocks = []
     for f in range(args.frames):
         cam = mnv.synth.default_camera(w, h, pose=f)
-        blk = sp.render_block(cam, opt)
+        blocks.append(sp.render_block(cam, opt).clone())
+    torch.cuda.synchronize()
+    for f in range(args.frames):
+        cam = mnv.synth.default_camera(w, h, pose=f)
+        blk = blocks[f]
         padded = torch.zeros((sp.block, 4), dtype=torch.uint8, device=blk.device)
         padded[: blk.shape[0]] = blk
         parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
