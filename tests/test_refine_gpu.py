@@ -13,6 +13,29 @@ def _pick_leaves(tree, n, seed):
     return leaves[rng.choice(len(leaves), n, replace=False)].astype(np.int32)
 
 
+def _assert_renders_like_a_fresh_build(mnv, dt, tree):
+    """The march reads a derived two-level index (csrc/mnv_internal.cuh `wide`): after any refinement step it must
+    describe the same tree as the authoritative planes — render the live tree and a tree rebuilt from its download."""
+    import torch
+
+    data, child, parent, counts = dt.download()
+    t2 = mnv.HostTree(N=2, data_dim=tree.data_dim, data_format=tree.data_format, child=child, parent=parent,
+                      depth=np.zeros(child.shape[0], np.int32), data=data, scale=tree.scale, offset=tree.offset)
+    dt2 = mnv.DeviceTree(t2, sample_counts=counts)
+    opt = mnv.default_options(background_brightness=0.0, max_sample_count=12)
+    for pose in (0, 3, 9):
+        cam = mnv.synth.default_camera(160, 90, pose=pose)
+        P = 160 * 90
+        outs = []
+        for d in (dt, dt2):
+            ts, tp = torch.empty((P, 3), device="cuda"), torch.empty((P, 3), device="cuda")
+            img = d.render(cam, opt, to_split=ts, to_sample=tp)
+            outs.append((img.cpu().numpy(), ts.cpu().numpy(), tp.cpu().numpy()))
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
+    dt2.close()
+
+
 @pytest.mark.parametrize("okw", [dict(), dict(need_viewdir=True, appearance_embedding=1), dict(appearance_embedding=0)])
 def test_add_children_commit_and_generate(okw, mnv, oracle, tmp_path):
     import torch
@@ -61,6 +84,7 @@ def test_add_children_commit_and_generate(okw, mnv, oracle, tmp_path):
     pts = s_nat[:, 0, :3] * tree.scale + tree.offset
     q = dt.query_points(pts.astype(np.float32)).cpu().numpy()
     assert np.array_equal(q[:, 0] * 8 + q[:, 1], packed)
+    _assert_renders_like_a_fresh_build(mnv, dt, tree)
 
     # generate_samples for existing leaves (A11) + running-mean update
     nodes = _pick_leaves(tree, 50, 4)
@@ -83,6 +107,7 @@ def test_add_children_commit_and_generate(okw, mnv, oracle, tmp_path):
     got2 = data2[nodes[:, 0], nodes[:, 1]].astype(np.float32)
     assert np.allclose(got2, want2, rtol=2e-3, atol=2e-3)
     assert (counts2[nodes[:, 0], nodes[:, 1]] == 16).all()
+    _assert_renders_like_a_fresh_build(mnv, dt, tree)
 
     if oracle.ref_available():
         npz = str(tmp_path / "t.npz")
