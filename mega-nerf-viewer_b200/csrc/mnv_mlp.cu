@@ -357,19 +357,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         const uint32_t b_hi = ((kChunkK / 8 * 128u) >> 4) | (1u << 14);
         const bool issue = elect_one();
         uint32_t s = 0, ph = 0, act_ph = 0;
+        long long w_act = 0, w_full = 0, w_act_l[kMaxLayers] = {0};
+        const long long t_begin = p.dbg ? clock64() : 0;
         for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
             for (int l = 0; l < n_layers; ++l) {
                 const uint32_t *w = s_layer + l * kLayerWords;
                 const uint32_t n_segs = w[0] & 0xffu, idesc = w[1];
                 for (int t = 0; t < kTiles; ++t) {
+                    const long long t0 = p.dbg ? clock64() : 0;
                     mbar_wait(bar_act + t, act_ph);  // A operand of tile t ready, its accumulator drained
+                    if (p.dbg) {
+                        const long long d = clock64() - t0;
+                        w_act += d;
+                        w_act_l[l] += d;
+                    }
                     uint32_t acc = 0;
                     for (uint32_t i = 0; i < n_segs; ++i) {
                         const uint32_t w2 = w[4 + 3 * i];
                         uint32_t a_lo = w[2 + 3 * i] + t * (w2 >> 16);
                         const uint32_t a_hi = w[3 + 3 * i];
                         for (uint32_t c = w2 & 0xffffu; c > 0; --c) {
+                            const long long t1 = p.dbg ? clock64() : 0;
                             mbar_wait(bar_full + s, ph);
+                            if (p.dbg) w_full += clock64() - t1;
                             tc_fence_after();
                             if (issue) {
                                 umma_bf16(tmem_base + t * kMaxN, ((uint64_t) a_hi << 32) | a_lo,
@@ -389,6 +399,13 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                 }
                 act_ph ^= 1;
             }
+        }
+        if (p.dbg && issue) {
+            long long *o = p.dbg + (size_t) blockIdx.x * 32;
+            o[0] = clock64() - t_begin;
+            o[1] = w_act;
+            o[2] = w_full;
+            for (int l = 0; l < n_layers && l < 16; ++l) o[8 + l] = w_act_l[l];
         }
     } else {
         // ===================== PE + epilogue warps =====================
@@ -862,9 +879,24 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
     p.out_real = m->cfg.out_rgb_dim;
     const int grid = std::min(p.n_groups, m->num_sms);
     p.dbg = nullptr;
+    static const bool debug = std::getenv("MNV_MLP_DEBUG") != nullptr;  // dev: where does the issuer wait?
+    if (debug) {
+        MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 32 * sizeof(long long)));
+        MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 32 * sizeof(long long), stream));
+    }
     p.n_stages = mlp_stages(p.need_viewdir != 0);
     mlp_forward_kernel<<<grid, kMlpThreads, mlp_smem_bytes(p.need_viewdir != 0), stream>>>(p);
     MNV_CUDA(cudaGetLastError());
+    if (debug) {
+        std::vector<long long> h((size_t) grid * 32);
+        MNV_CUDA(cudaMemcpyAsync(h.data(), p.dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        MNV_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(p.dbg);
+        std::fprintf(stderr, "[mlp dbg] CTA0 issuer: total %lld clk = wait_act %lld + wait_full %lld + issue %lld; wait_act per layer:",
+                     h[0], h[1], h[2], h[0] - h[1] - h[2]);
+        for (int l = 0; l < m->sched.n_layers; ++l) std::fprintf(stderr, " %lld", h[8 + l]);
+        std::fprintf(stderr, "\n");
+    }
     return MNV_OK;
 }
 
