@@ -20,6 +20,7 @@ import numpy as np
 
 from . import synth  # noqa: F401  (synthetic N3Tree generator)
 from . import multigpu  # noqa: F401,E402  (sub-module split across GPUs)
+from . import export  # noqa: F401,E402  (Mega-NeRF checkpoint -> model container)
 from .synth import HostTree
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -65,6 +65,53 @@ def test_loader_invradius_scalar_and_extra_keys(built, tmp_path):
     assert j["capacity"] == cap
 
 
+@pytest.mark.parametrize("n_retain", [0, 1, 3])
+def test_loader_vq_compressed_tree(built, tmp_path, n_retain):
+    """quant_colors / quant_map / data_retained / sigma (n3tree.cpp:109-175): basis functions
+    [n_retain, n_basis) through per-basis 65536-entry codebooks, the first n_retain stored plainly,
+    destination index channel * n_basis + basis (the reference's own write index drops `+ basis`)."""
+    mnv = built
+    tree = mnv.synth.make_tree(depth=4)
+    cap, nb = tree.capacity, 9
+    n_q = nb - n_retain
+    rng = np.random.default_rng(11 + n_retain)
+    book = rng.standard_normal((n_q, 65536, 3)).astype(np.float16)
+    qmap = rng.integers(0, 65536, (n_q, cap, 2, 2, 2), dtype=np.uint16)
+    retained = rng.standard_normal((n_retain, cap, 2, 2, 2, 3)).astype(np.float16)
+    sigma = tree.data[..., -1].reshape(cap, 2, 2, 2)
+    want = np.zeros((cap, 8, 28), np.float16)
+    for b in range(n_q):
+        col = book[b][qmap[b].reshape(cap, 8)]            # [cap, 8, 3]
+        for ch in range(3):
+            want[:, :, ch * nb + n_retain + b] = col[..., ch]
+    for b in range(n_retain):
+        for ch in range(3):
+            want[:, :, ch * nb + b] = retained[b].reshape(cap, 8, 3)[..., ch]
+    want[:, :, 27] = sigma.reshape(cap, 8)
+    arrays = dict(data_dim=np.int64(28), data_format=np.array("SH9"), invradius3=tree.scale, offset=tree.offset,
+                  child=tree.child.reshape(cap, 2, 2, 2), parent_depth=np.stack([tree.parent, tree.depth], 1).astype(np.int32),
+                  quant_colors=book, quant_map=qmap, sigma=sigma)
+    if n_retain:
+        arrays["data_retained"] = retained
+    path = tmp_path / "vq.npz"
+    np.savez_compressed(path, **arrays)
+    r = run(mnv, path, "--selftest-load")
+    assert r.returncode == 0, r.stderr
+    assert "Decoding quantized colors" in r.stdout
+    j = last_json(r.stdout)
+    assert j["capacity"] == cap and j["data_dim"] == 28
+    assert j["data"] == mnv.bytes_checksum(want.view(np.uint16))
+    # schema violations
+    bad = dict(arrays, quant_colors=book.astype(np.float32))
+    np.savez(tmp_path / "bad.npz", **bad)
+    r = run(mnv, tmp_path / "bad.npz", "--selftest-load")
+    assert r.returncode == 1 and "half precision" in r.stderr
+    bad = dict(arrays, quant_map=qmap[:-1])
+    np.savez(tmp_path / "bad2.npz", **bad)
+    r = run(mnv, tmp_path / "bad2.npz", "--selftest-load")
+    assert r.returncode == 1
+
+
 def test_loader_errors(built, tmp_path):
     mnv = built
     r = run(mnv, tmp_path / "nope.npz", "--selftest-load")  # n3tree.cpp:19-22: message, empty tree
