@@ -185,6 +185,33 @@ def mlp_section(mnv, torch, dev, iters=20):
     return sec
 
 
+def point_query_section(mnv, torch, dev, dt, tree, n=4_000_000):
+    """Config 1 of BASELINE.json on this tree: query_single_from_root (rt_core.cuh:117-159) for n uniform points —
+    the native integer-cell descent on the GPU next to the CPU port on the host cores; results must be equal."""
+    from oracle import oracle_py as O
+
+    rng = np.random.default_rng(2)
+    xyz = rng.random((n, 3), dtype=np.float32)
+    x = torch.from_numpy(xyz).to(dev)
+    out = dt.query_points(x)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = dt.query_points(x)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    m = min(n, 1_000_000)
+    t0 = time.perf_counter()
+    cpu = O.query_points(tree, xyz[:m])
+    t_cpu = time.perf_counter() - t0
+    equal = bool(np.array_equal(out[:m].cpu().numpy(), cpu))
+    return {"points": n, "gpu_mqueries_per_s": n / float(np.mean(ms)) / 1e3, "cpu_port_mqueries_per_s": m / t_cpu / 1e6,
+            "cpu_cores": int(O.lib().oracle_num_threads()), "equal_to_cpu_port": equal}
+
+
 def headless_sections(mnv, tree, W, H):
     """Configs 4 and 5 of BASELINE.json through the C++ API (viewer::VolumeRenderer via bin/mnv_headless): frames
     with dynamic refinement on (4192-leaf split batches x 8 children x 8 samples through 8 sub-MLPs per frame) and
@@ -428,6 +455,8 @@ def main():
         "clocks": clocks,
     }
     line["mlp"] = mlp_section(mnv, torch, dev)
+    if world == 1 and not args.no_cpu_baseline:
+        line["point_query"] = point_query_section(mnv, torch, dev, dt, tree)
     if world == 1 and not args.no_headless:
         dt.close()
         del flush, ts, tp, out

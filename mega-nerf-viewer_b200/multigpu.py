@@ -193,3 +193,102 @@ class SubmoduleSplit:
         self.flags.free()
         if hasattr(self, "_scratch"):
             self._scratch.free()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Image-row blocks with the tree AND the sub-MLPs replicated (first mode) for the two paths
+# that run the MLP: guided sampling and dynamic refinement.  The eight sub-modules are 1.2 MB of bf16 each —
+# replicating them is free — so guided sampling needs no exchange at all: every rank emits, evaluates and
+# composites the rays of its own rows (a windowed camera: same intrinsics, cy shifted by the first row).
+# Refinement needs one collective per frame: the per-ray votes (the two [P, 3] tracker arrays) are
+# all-gathered, after which every rank runs the identical, deterministic select -> split -> MLP -> commit
+# sequence on its replica, so the replicas stay bit-identical without broadcasting payloads.
+
+
+def row_block(height: int, world: int, rank: int):
+    """Rows [first, first + n) of rank's block; blocks are multiples of 8 rows (the march kernel's tile height)."""
+    per = ((height + world - 1) // world + 7) // 8 * 8
+    first = min(rank * per, height)
+    return first, max(0, min(per, height - first))
+
+
+def window_camera(cam: dict, first_row: int, n_rows: int) -> dict:
+    """The camera of rows [first_row, first_row + n_rows): identical rays, bit for bit, when cy is a multiple of 0.5."""
+    return dict(cam, height=int(n_rows), cy=float(cam["cy"]) - float(first_row))
+
+
+class ReplicatedPipeline:
+    def __init__(self, tree, submodules, grid_dim, min_position, max_position, rank=0, world=1, device=0,
+                 dist=None, max_capacity=0, seed=0x5eed):
+        from . import DeviceTree, MlpModel
+
+        self.rank, self.world, self.device, self.dist, self.seed = rank, world, device, dist, seed
+        self.dt = DeviceTree(tree, max_capacity=max_capacity, device=device)
+        self.model = MlpModel(submodules, grid_dim=grid_dim, min_position=min_position, max_position=max_position,
+                              device=device)
+        self.grid_dim = list(grid_dim)
+        self.min_position = list(min_position)
+        self.range = [float(b) - float(a) for a, b in zip(min_position, max_position)]
+        self.data_dim = tree.data_dim
+        self.steps = 0
+
+    def guided_block(self, cam: dict, opt, capacity_rows=None):
+        """RGBA8 [rows of this rank, W, 4] of the guided-sampling frame."""
+        import torch
+
+        first, n = row_block(cam["height"], self.world, self.rank)
+        wc = window_camera(cam, first, n)
+        cap = capacity_rows or max(1 << 16, n * cam["width"] * 24)
+        g = self.dt.guided_samples(wc, opt, self.grid_dim, self.min_position, self.range, capacity_rows=cap)
+        vals = torch.empty((max(g["total"], 1), self.data_dim + 1), device=f"cuda:{self.device}")
+        if g["total"]:
+            self.model.query_submodules(g["cluster"], g["rows"], vals)
+        return self.dt.render_nerf_results(wc, opt, vals, g["z_vals"], g["offsets"], sigma_col=self.data_dim - 1), g["total"]
+
+    def refine_frame(self, cam: dict, opt):
+        """One frame with refinement on: own rows rendered with vote tracking, votes all-gathered, the identical
+        split / MLP / commit on every replica.  Returns (RGBA8 block of this rank, nodes added)."""
+        import torch
+
+        from . import select_candidates
+
+        dev = f"cuda:{self.device}"
+        W, H = cam["width"], cam["height"]
+        first, n = row_block(H, self.world, self.rank)
+        per = row_block(H, self.world, 0)[1]
+        wc = window_camera(cam, first, n)
+        ts = torch.full((per * W, 3), -1.0, device=dev)
+        tp = torch.full((per * W, 3), -1.0, device=dev)
+        img = self.dt.render(wc, opt, to_split=ts[: n * W], to_sample=tp[: n * W]) if n else None
+        if self.world > 1:
+            all_ts = torch.empty((self.world * per * W, 3), device=dev)
+            self.dist.all_gather_into_tensor(all_ts, ts)
+            ts = all_ts
+        nodes, _ = select_candidates(ts, opt.split_batch_size, "split")
+        k = nodes.shape[0]
+        self.steps += 1
+        if k == 0 or self.dt.capacity + k > self.dt.max_capacity:
+            return img, 0
+        c = opt.samples_per_corner
+        rd = 3 + (3 if opt.need_viewdir else 0) + (1 if opt.appearance_embedding != -1 else 0)
+        g = torch.Generator(device=dev).manual_seed(self.seed + self.steps)  # the same numbers on every replica
+        samples = torch.rand((k * 8, c, rd), device=dev, generator=g)
+        cluster = torch.zeros((k * 8, c), dtype=torch.int16, device=dev)
+        self.dt.add_children(opt, nodes, samples, cluster, self.grid_dim, self.min_position, self.range)
+        results = torch.empty((k * 8 * c, self.data_dim + 1), device=dev)
+        self.model.query_submodules(cluster.view(-1), samples.view(-1, rd), results)
+        self.dt.commit_children(opt, k, results.view(k * 8, c, -1))
+        return img, k
+
+    def tree_checksum(self) -> int:
+        data, child, parent, counts = self.dt.download()
+        import zlib
+
+        h = 0
+        for a in (child, parent, data.view(np.uint16), counts):
+            h = zlib.crc32(np.ascontiguousarray(a).tobytes(), h)
+        return h
+
+    def close(self):
+        self.model.close()
+        self.dt.close()
