@@ -160,6 +160,12 @@ int mnv_memcpy_d2h_async(void *dst_host, const void *src_dev, size_t bytes, void
 int mnv_stream_create(void **stream, int device); /* non-blocking cudaStream_t */
 int mnv_stream_destroy(void *stream);
 int mnv_stream_synchronize(void *stream);
+/* cudaArray_t surfaces of the kind the viewer registers from its GL renderbuffers (RGBA8 colour, R32F
+ * "fake depth", src/renderer/cuda_renderer.cpp:419-441) for hosts without GL: kind 0 = RGBA8, 1 = R32F. */
+int mnv_array_create(void **array, int width, int height, int kind, int device);
+int mnv_array_destroy(void *array);
+int mnv_array_upload(void *array, const void *src_host, size_t row_bytes, int height);
+int mnv_array_download(void *dst_host, void *array, size_t row_bytes, int height);
 
 /* ---- tree: N3Tree::move_to_device, src/n3tree/n3tree.cpp:207-246 --------- */
 int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *desc, int64_t max_capacity, int device);

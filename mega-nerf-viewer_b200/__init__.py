@@ -175,6 +175,10 @@ def lib() -> C.CDLL:
     L.mnv_ipc_export.argtypes = [vp, C.c_char_p]
     L.mnv_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp), i32]
     L.mnv_ipc_close.argtypes = [vp]
+    L.mnv_array_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
+    L.mnv_array_destroy.argtypes = [vp]
+    L.mnv_array_upload.argtypes = [vp, vp, C.c_size_t, i32]
+    L.mnv_array_download.argtypes = [vp, vp, C.c_size_t, i32]
     L.mnv_malloc.argtypes = [C.POINTER(vp), C.c_size_t, i32]
     L.mnv_free.argtypes = [vp]
     L.mnv_memset.argtypes = [vp, i32, C.c_size_t, vp]
@@ -420,6 +424,33 @@ class DeviceTree:
         first = int(torch.argmin(shifts).item())  # cuda_renderer.cpp:357
         _check(lib().mnv_tree_prune(self._h, _dptr(td), _dptr(shifts), first, num, _stream_ptr(stream)))
         return num
+
+    # ---- the viewer's presentation path: cudaArray surfaces, offscreen = false -----------------
+    def render_interop(self, cam, opt: RenderOptions, prior_rgba: np.ndarray, depth: np.ndarray,
+                       track_visit: bool = False, visited=None, to_split=None, to_sample=None):
+        """mnv_render_voxels exactly as Impl::render drives it (cuda_renderer.cpp:141-142): the RGBA8 surface
+        already holds what GL drew (`prior_rgba` [H, W, 4] u8), the R32F surface the mesh depth (`depth`
+        [H, W] f32), the frame is composited over them in place.  Returns the RGBA8 frame (numpy)."""
+        torch = _torch()
+        cam = make_camera(cam)
+        h, w = cam.height, cam.width
+        img, dep = C.c_void_p(), C.c_void_p()
+        _check(lib().mnv_array_create(C.byref(img), w, h, 0, self.device))
+        _check(lib().mnv_array_create(C.byref(dep), w, h, 1, self.device))
+        try:
+            pr = np.ascontiguousarray(prior_rgba, np.uint8)
+            dp = np.ascontiguousarray(depth, np.float32)
+            _check(lib().mnv_array_upload(img, pr.ctypes.data, w * 4, h))
+            _check(lib().mnv_array_upload(dep, dp.ctypes.data, w * 4, h))
+            _check(lib().mnv_render_voxels(self._h, C.byref(cam), C.byref(opt), img, dep, None, _dptr(to_split),
+                                           _dptr(to_sample), _dptr(visited), track_visit, False, _stream_ptr(None)))
+            torch.cuda.synchronize()
+            out = np.empty((h, w, 4), np.uint8)
+            _check(lib().mnv_array_download(out.ctypes.data, img, w * 4, h))
+        finally:
+            lib().mnv_array_destroy(img)
+            lib().mnv_array_destroy(dep)
+        return out
 
     # ---- sub-module split across GPUs (csrc/mnv_multigpu.cu) ---------------------------------
     def render_partial(self, cam, opt: RenderOptions, dst_ptrs, block_pixels: int, slot: int, stream=None):

@@ -176,6 +176,34 @@ int mnv_stream_synchronize(void *stream) {
     return MNV_OK;
 }
 
+int mnv_array_create(void **array, int width, int height, int kind, int device) {
+    if (!array || width <= 0 || height <= 0 || (kind != 0 && kind != 1)) return MNV_ERR_INVALID;
+    int rc = check_device(device);
+    if (rc != MNV_OK) return rc;
+    MNV_CUDA(cudaSetDevice(device));
+    const cudaChannelFormatDesc desc = kind == 0 ? cudaCreateChannelDesc<uchar4>() : cudaCreateChannelDesc<float>();
+    cudaArray_t a = nullptr;
+    MNV_CUDA(cudaMallocArray(&a, &desc, (size_t) width, (size_t) height, cudaArraySurfaceLoadStore));
+    *array = a;
+    return MNV_OK;
+}
+int mnv_array_destroy(void *array) {
+    if (array) MNV_CUDA(cudaFreeArray(static_cast<cudaArray_t>(array)));
+    return MNV_OK;
+}
+int mnv_array_upload(void *array, const void *src_host, size_t row_bytes, int height) {
+    if (!array || !src_host) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaMemcpy2DToArray(static_cast<cudaArray_t>(array), 0, 0, src_host, row_bytes, row_bytes, (size_t) height,
+                                 cudaMemcpyHostToDevice));
+    return MNV_OK;
+}
+int mnv_array_download(void *dst_host, void *array, size_t row_bytes, int height) {
+    if (!array || !dst_host) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaMemcpy2DFromArray(dst_host, row_bytes, static_cast<cudaArray_t>(array), 0, 0, row_bytes,
+                                   (size_t) height, cudaMemcpyDeviceToHost));
+    return MNV_OK;
+}
+
 void mnv_render_options_default(mnv_render_options *o) {
     if (!o) return;
     std::memset(o, 0, sizeof(*o));

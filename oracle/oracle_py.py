@@ -321,6 +321,22 @@ class RefRenderer:
         assert rc == 0, rc
         return dict(rgba=rgba, to_split=split, to_sample=sample, ms=ms)
 
+    def render_interop(self, cam: dict, opt: RenderOptions, prior_rgba: np.ndarray, depth: np.ndarray,
+                       track_visit: bool = False, max_capacity: int = 0):
+        """render_voxels(offscreen=false) over a prior colour surface and a mesh-depth surface, like the viewer."""
+        w, h, intr, c2w = self._cam_args(cam)
+        pr = np.ascontiguousarray(prior_rgba, np.uint8)
+        dp = np.ascontiguousarray(depth, np.float32)
+        rgba = np.zeros((h, w, 4), np.uint8)
+        visited = np.zeros(max_capacity, np.int32) if max_capacity else None
+        self.L.ref_render_voxels_interop.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        rc = self.L.ref_render_voxels_interop(self.h, w, h, intr.ctypes.data, c2w.ctypes.data, C.byref(opt),
+                                              C.sizeof(opt), pr.ctypes.data, dp.ctypes.data, rgba.ctypes.data,
+                                              int(track_visit), _ptr(visited))
+        assert rc == 0, rc
+        return rgba, visited
+
     def render_frame_host(self, cam: dict, opt: RenderOptions, rgba: np.ndarray):
         w, h, intr, c2w = self._cam_args(cam)
         rc = self.L.ref_render_frame_host(self.h, w, h, intr.ctypes.data, c2w.ctypes.data,

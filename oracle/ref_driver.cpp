@@ -432,4 +432,43 @@ int ref_camera_trace(int w, int h, float fx, float *out) {
     return 0;
 }
 
+// viewer::render_voxels the way Impl::render calls it (cuda_renderer.cpp:141-142): offscreen = false, the
+// RGBA8 surface already holds what GL drew (prior_rgba), the R32F surface the mesh depth t_max (depth), visit
+// tracking optional.  Host pointers in / out; visited_out int32 [max_capacity].
+int ref_render_voxels_interop(void *ctx, int w, int h, const float *intr, const float *c2w, const void *opt_pod,
+                              int opt_size, const unsigned char *prior_rgba, const float *depth,
+                              unsigned char *rgba_out, int track_visit, int *visited_out) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    if (opt_size != (int) sizeof(viewer::RenderOptions)) return 1;
+    viewer::RenderOptions opt;
+    std::memcpy(&opt, opt_pod, sizeof(opt));
+    ensure_target(c, w, h);
+    set_camera(c, w, h, intr, c2w);
+    cudaArray_t darr = nullptr;
+    cudaChannelFormatDesc fdesc = cudaCreateChannelDesc<float>();
+    cudaMallocArray(&darr, &fdesc, w, h, cudaArraySurfaceLoadStore);
+    cudaMemcpy2DToArray(c->img, 0, 0, prior_rgba, (size_t) w * 4, (size_t) w * 4, h, cudaMemcpyHostToDevice);
+    cudaMemcpy2DToArray(darr, 0, 0, depth, (size_t) w * 4, (size_t) w * 4, h, cudaMemcpyHostToDevice);
+    c->split.fill_(-1);
+    c->sample.fill_(-1);
+    c->visited.zero_();
+    c->visited[0] = 1;  // cuda_renderer.cpp:506
+    cudaDeviceSynchronize();
+    viewer::render_voxels(c->tree, *c->cam, opt, c->img, darr, c->stream, c->split, c->sample, c->visited,
+                          track_visit != 0, /*offscreen=*/false);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) {
+        fprintf(stderr, "ref_render_voxels_interop: %s\n", cudaGetErrorString(err));
+        cudaFreeArray(darr);
+        return 2;
+    }
+    cudaMemcpy2DFromArray(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h, cudaMemcpyDeviceToHost);
+    if (visited_out) {
+        auto t = c->visited.cpu();
+        std::memcpy(visited_out, t.data_ptr(), t.numel() * 4);
+    }
+    cudaFreeArray(darr);
+    return 0;
+}
+
 }  // extern "C"
