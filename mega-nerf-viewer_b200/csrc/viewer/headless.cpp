@@ -4,7 +4,7 @@
 //
 //   mnv_headless tree.npz [--model model.npz] [--width W --height H] [--frames N] [--poses K]
 //                [--max_tree_capacity C] [--use_splitting] [--use_guided_sampling]
-//                [--bg B] [--out frame.ppm] [--raw frame.rgba] [--seed S] [--verbose]
+//                [--bg B] [--out frame.ppm] [--raw frame.rgba] [--save refined.npz] [--seed S] [--verbose]
 //                [--selftest-load] [--selftest-camera] [--selftest-wireframe D]
 //
 // Prints one JSON line with the wall-clock frame statistics (camera upload + render + refinement
@@ -62,7 +62,7 @@ void print_camera(const Camera &c) {
 }  // namespace
 
 int main(int argc, char **argv) {
-    std::string tree_path, model_path, out_ppm, out_raw;
+    std::string tree_path, model_path, out_ppm, out_raw, save_path, resave_path;
     int width = 1920, height = 1080, frames = 16, poses = 16, wire_depth = -1;
     long max_cap = 0;
     bool splitting = false, guided = false, verbose = false, st_load = false, st_camera = false;
@@ -88,6 +88,8 @@ int main(int argc, char **argv) {
         else if (a == "--bg") bg = (float) std::atof(val());
         else if (a == "--out") out_ppm = val();
         else if (a == "--raw") out_raw = val();
+        else if (a == "--save") save_path = val();              // write the (refined) tree after the last frame
+        else if (a == "--selftest-resave") resave_path = val(); // host only: load, write back
         else if (a == "--seed") seed = std::strtoull(val(), nullptr, 0);
         else if (a == "--verbose") verbose = true;
         else if (a == "--selftest-load") st_load = true;
@@ -122,6 +124,10 @@ int main(int argc, char **argv) {
         }
         N3Tree tree(tree_path);
         if (tree.capacity == 0) return 3;
+        if (!resave_path.empty()) {
+            tree.save(resave_path);
+            return 0;
+        }
         if (st_load) {  // host-only: checksums of what N3Tree::open produced
             std::printf("{\"N\": %d, \"data_dim\": %d, \"format\": \"%s\", \"basis_dim\": %d, \"capacity\": %d, "
                         "\"scale\": [%.9g, %.9g, %.9g], \"offset\": [%.9g, %.9g, %.9g], "
@@ -176,6 +182,10 @@ int main(int argc, char **argv) {
                 added += rend.last_frame.added;
                 resampled += rend.last_frame.resampled;
             }
+        }
+        if (!save_path.empty()) {
+            tree.download();
+            tree.save(save_path);
         }
         const uint8_t *px = rend.frame_host();
         const size_t nbytes = (size_t) width * height * 4;

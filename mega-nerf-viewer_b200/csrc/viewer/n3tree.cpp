@@ -1,5 +1,6 @@
 #include "n3tree.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -188,6 +189,47 @@ void N3Tree::download() {
     if (mnv_tree_download(device_tree, 0, cap, data.data_ptr(), child.data_ptr(), parent.data_ptr(),
                           sample_counts.data_ptr()) != MNV_OK)
         throw std::runtime_error(std::string("download: ") + mnv_last_error());
+}
+
+void N3Tree::save(const std::string &path) const {
+    const int64_t cap = child.size(0);
+    if (cap == 0 || data.size(0) != cap) throw std::runtime_error("save: empty or inconsistent tree");
+    // parent_depth [cap, 2]: packed parent slot, depth of the node (root 0); children follow their parents
+    // in every tree this library produces, a second pass covers foreign orderings
+    std::vector<int32_t> pd((size_t) cap * 2, 0);
+    std::vector<int32_t> depth((size_t) cap, -1);
+    depth[0] = 0;
+    for (int pass = 0; pass < 64; ++pass) {
+        bool pending = false;
+        for (int64_t n = 0; n < cap; ++n) {
+            if (depth[(size_t) n] < 0) {
+                pending = true;
+                continue;
+            }
+            for (int c = 0; c < N3_; ++c) {
+                const int32_t rel = child.v[(size_t) n * N3_ + c];
+                if (rel != 0 && n + rel > 0 && n + rel < cap) depth[(size_t) (n + rel)] = depth[(size_t) n] + 1;
+            }
+        }
+        if (!pending) break;
+    }
+    for (int64_t n = 0; n < cap; ++n) {
+        pd[(size_t) n * 2] = n < parent.numel() ? parent.v[(size_t) n] : 0;
+        pd[(size_t) n * 2 + 1] = std::max(depth[(size_t) n], 0);
+    }
+    const int64_t dd = data_dim;
+    const std::string fmt = data_format.to_string();
+    std::vector<uint32_t> fmt_u(fmt.begin(), fmt.end());  // '<U*': UCS-4
+    const size_t ucap = (size_t) cap, uN = (size_t) N;
+    std::vector<npz::Member> m;
+    m.push_back({"data_dim", "<i8", {}, &dd, 8});
+    m.push_back({"data_format", "<U" + std::to_string(fmt.size()), {}, fmt_u.data(), fmt_u.size() * 4});
+    m.push_back({"invradius3", "<f4", {3}, scale.v.data(), 12});
+    m.push_back({"offset", "<f4", {3}, offset.v.data(), 12});
+    m.push_back({"child", "<i4", {ucap, uN, uN, uN}, child.v.data(), child.v.size() * 4});
+    m.push_back({"parent_depth", "<i4", {ucap, 2}, pd.data(), pd.size() * 4});
+    m.push_back({"data", "<f2", {ucap, uN, uN, uN, (size_t) data_dim}, data.v.data(), data.v.size() * 2});
+    npz::save(path, m);
 }
 
 namespace {

@@ -72,6 +72,9 @@ struct N3Tree {
     mnv_tree *device_tree = nullptr;       // set by move_to_device
     void sync_capacity();                  // refresh `capacity` after device-side refinement
     void download();                       // refresh the host arrays from the device tree
+    // Write the tree in the svox schema open() reads (after download(): the refined tree).  The reference has no
+    // writer; `parent_depth` column 1 is recomputed from the links.
+    void save(const std::string &path) const;
 
    private:
     int N2_ = 0, N3_ = 0;

@@ -163,4 +163,129 @@ Archive load(const std::string &path) {
     return out;
 }
 
+namespace {
+void put16(std::vector<uint8_t> &b, uint16_t v) { b.push_back(v & 0xff); b.push_back(v >> 8); }
+void put32(std::vector<uint8_t> &b, uint32_t v) { for (int i = 0; i < 4; ++i) b.push_back((v >> (8 * i)) & 0xff); }
+void put64(std::vector<uint8_t> &b, uint64_t v) { for (int i = 0; i < 8; ++i) b.push_back((v >> (8 * i)) & 0xff); }
+uint32_t crc_of(const uint8_t *hdr, size_t nh, const void *data, size_t nd) {
+    uLong c = crc32(0L, Z_NULL, 0);
+    c = crc32(c, hdr, (uInt) nh);
+    const uint8_t *p = static_cast<const uint8_t *>(data);
+    while (nd) {  // zlib's length is 32-bit
+        const size_t n = std::min<size_t>(nd, 1u << 30);
+        c = crc32(c, p, (uInt) n);
+        p += n;
+        nd -= n;
+    }
+    return (uint32_t) c;
+}
+std::vector<uint8_t> npy_header(const Member &m) {
+    std::string d = "{'descr': '" + m.descr + "', 'fortran_order': False, 'shape': (";
+    for (size_t i = 0; i < m.shape.size(); ++i) d += std::to_string(m.shape[i]) + (m.shape.size() == 1 || i + 1 < m.shape.size() ? "," : "") + (i + 1 < m.shape.size() ? " " : "");
+    d += "), }";
+    size_t total = 10 + d.size() + 1;
+    const size_t pad = (64 - total % 64) % 64;
+    d.append(pad, ' ');
+    d.push_back('\n');
+    std::vector<uint8_t> h = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0};
+    put16(h, (uint16_t) d.size());
+    h.insert(h.end(), d.begin(), d.end());
+    return h;
+}
+}  // namespace
+
+void save(const std::string &path, const std::vector<Member> &members) {
+    std::ofstream f(path, std::ios::binary | std::ios::trunc);
+    if (!f) fail("cannot create " + path);
+    struct Central { std::string name; uint32_t crc; uint64_t size, offset; };
+    std::vector<Central> central;
+    uint64_t offset = 0;
+    for (const Member &m : members) {
+        const std::vector<uint8_t> hdr = npy_header(m);
+        const std::string name = m.name + ".npy";
+        const uint64_t size = hdr.size() + m.nbytes;
+        const uint32_t crc = crc_of(hdr.data(), hdr.size(), m.data, m.nbytes);
+        std::vector<uint8_t> lh;
+        put32(lh, 0x04034b50);
+        put16(lh, 45);  // version needed: ZIP64
+        put16(lh, 0);
+        put16(lh, 0);   // stored
+        put16(lh, 0);
+        put16(lh, 0x21);  // DOS time / date (1980-01-01)
+        put32(lh, crc);
+        put32(lh, 0xffffffffu);  // sizes live in the ZIP64 extra field (like numpy's force_zip64)
+        put32(lh, 0xffffffffu);
+        put16(lh, (uint16_t) name.size());
+        put16(lh, 20);
+        lh.insert(lh.end(), name.begin(), name.end());
+        put16(lh, 0x0001);
+        put16(lh, 16);
+        put64(lh, size);
+        put64(lh, size);
+        f.write(reinterpret_cast<const char *>(lh.data()), (std::streamsize) lh.size());
+        f.write(reinterpret_cast<const char *>(hdr.data()), (std::streamsize) hdr.size());
+        const char *p = static_cast<const char *>(m.data);
+        for (size_t done = 0; done < m.nbytes;) {
+            const size_t n = std::min<size_t>(m.nbytes - done, 1u << 30);
+            f.write(p + done, (std::streamsize) n);
+            done += n;
+        }
+        central.push_back({name, crc, size, offset});
+        offset += lh.size() + size;
+    }
+    const uint64_t cd_start = offset;
+    std::vector<uint8_t> cd;
+    for (const Central &c : central) {
+        put32(cd, 0x02014b50);
+        put16(cd, 45);
+        put16(cd, 45);
+        put16(cd, 0);
+        put16(cd, 0);
+        put16(cd, 0);
+        put16(cd, 0x21);
+        put32(cd, c.crc);
+        put32(cd, 0xffffffffu);
+        put32(cd, 0xffffffffu);
+        put16(cd, (uint16_t) c.name.size());
+        put16(cd, 28);  // ZIP64 extra: usize, csize, offset
+        put16(cd, 0);
+        put16(cd, 0);
+        put16(cd, 0);
+        put32(cd, 0);
+        put32(cd, 0xffffffffu);
+        cd.insert(cd.end(), c.name.begin(), c.name.end());
+        put16(cd, 0x0001);
+        put16(cd, 24);
+        put64(cd, c.size);
+        put64(cd, c.size);
+        put64(cd, c.offset);
+    }
+    const uint64_t cd_size = cd.size();
+    // ZIP64 end of central directory + locator + classic end record
+    put32(cd, 0x06064b50);
+    put64(cd, 44);
+    put16(cd, 45);
+    put16(cd, 45);
+    put32(cd, 0);
+    put32(cd, 0);
+    put64(cd, central.size());
+    put64(cd, central.size());
+    put64(cd, cd_size);
+    put64(cd, cd_start);
+    put32(cd, 0x07064b50);
+    put32(cd, 0);
+    put64(cd, cd_start + cd_size);
+    put32(cd, 1);
+    put32(cd, 0x06054b50);
+    put16(cd, 0);
+    put16(cd, 0);
+    put16(cd, (uint16_t) std::min<size_t>(central.size(), 0xffff));
+    put16(cd, (uint16_t) std::min<size_t>(central.size(), 0xffff));
+    put32(cd, (uint32_t) std::min<uint64_t>(cd_size, 0xffffffffu));
+    put32(cd, 0xffffffffu);
+    put16(cd, 0);
+    f.write(reinterpret_cast<const char *>(cd.data()), (std::streamsize) cd.size());
+    if (!f) fail("short write " + path);
+}
+
 }  // namespace viewer::npz

@@ -30,6 +30,17 @@ using Archive = std::map<std::string, Array>;
 
 // Throws std::runtime_error on malformed input.
 Archive load(const std::string &path);
+
+// Writer side (the reference only reads): `.npy` v1 members, stored (no compression), ZIP64 records
+// whenever a size or offset needs them, so multi-GB refined trees can be written.
+struct Member {
+    std::string name;            // without ".npy"
+    std::string descr;           // numpy dtype string, e.g. "<f2", "<i4", "<U3"
+    std::vector<size_t> shape;   // {} = scalar
+    const void *data;
+    size_t nbytes;
+};
+void save(const std::string &path, const std::vector<Member> &members);
 Array parse_npy(const uint8_t *buf, size_t len);
 
 }  // namespace viewer::npz

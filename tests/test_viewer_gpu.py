@@ -73,6 +73,28 @@ def test_headless_refinement_grows_the_tree(mnv, tmp_path):
     assert j2["frame_hash"] == j["frame_hash"] and j2["capacity"] == j["capacity"]
 
 
+def test_headless_saves_the_refined_tree(mnv, tmp_path):
+    """--save after refinement: the file holds the grown tree and renders like the live one."""
+    tree = mnv.synth.make_tree(depth=6)
+    path, mpath, out = tmp_path / "t.npz", tmp_path / "m.npz", tmp_path / "refined.npz"
+    tree.save_npz(str(path))
+    make_model(mnv, mpath)
+    raw = tmp_path / "f.rgba"
+    j = run(mnv, path, "--model", mpath, "--width", 320, "--height", 180, "--frames", 3, "--poses", 1,
+            "--use_splitting", "--max_tree_capacity", tree.capacity + 20000, "--save", out)
+    refined = mnv.HostTree.load_npz(str(out))
+    assert refined.capacity == j["capacity"] > tree.capacity
+    assert np.array_equal(refined.child[: tree.capacity] != 0, tree.child != 0) is False  # some leaves were split
+    # a fresh, non-refining run on the saved tree reproduces a frame of the refined scene
+    j2 = run(mnv, out, "--width", 320, "--height", 180, "--frames", 1, "--poses", 1, "--raw", raw)
+    assert j2["capacity"] == refined.capacity
+    dt = mnv.DeviceTree(refined)
+    opt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8])
+    want = dt.render(cam_from(j2, 320, 180), opt).cpu().numpy()
+    assert np.array_equal(np.fromfile(raw, np.uint8).reshape(180, 320, 4), want)
+    dt.close()
+
+
 def test_headless_prunes_when_full(mnv, tmp_path):
     """max_tree_capacity - capacity < split_batch_size triggers Impl::prune_tree
     (cuda_renderer.cpp:146-151).  Visit tracking only starts once capacity > 3/4 max or after a

@@ -112,6 +112,30 @@ def test_loader_vq_compressed_tree(built, tmp_path, n_retain):
     assert r.returncode == 1
 
 
+@pytest.mark.parametrize("fmt", ["SH9", "RGBA"])
+def test_tree_writer_round_trip(built, tmp_path, fmt):
+    """viewer::N3Tree::save (the reference has no writer): numpy reads the file back array for array, zipfile
+    accepts the archive, and the C++ loader reads its own output."""
+    mnv = built
+    tree = mnv.synth.make_tree(depth=5, data_format=fmt)
+    src, dst = tmp_path / "a.npz", tmp_path / "b.npz"
+    tree.save_npz(str(src), compressed=True)
+    r = run(mnv, src, "--selftest-resave", dst)
+    assert r.returncode == 0, r.stderr
+    with zipfile.ZipFile(dst) as z:
+        assert z.testzip() is None  # CRCs
+        assert sorted(z.namelist()) == sorted(k + ".npy" for k in
+                                              ("data_dim", "data_format", "invradius3", "offset", "child", "parent_depth", "data"))
+    back = mnv.HostTree.load_npz(str(dst))
+    assert back.data_format == fmt and back.data_dim == tree.data_dim
+    assert np.array_equal(back.child, tree.child) and np.array_equal(back.parent, tree.parent)
+    assert np.array_equal(back.depth, tree.depth)  # recomputed from the links
+    assert np.array_equal(back.data.view(np.uint16), tree.data.view(np.uint16))
+    assert np.array_equal(back.scale, tree.scale) and np.array_equal(back.offset, tree.offset)
+    a, b = run(mnv, src, "--selftest-load"), run(mnv, dst, "--selftest-load")
+    assert a.returncode == 0 and b.returncode == 0 and last_json(a.stdout) == last_json(b.stdout)
+
+
 def test_loader_errors(built, tmp_path):
     mnv = built
     r = run(mnv, tmp_path / "nope.npz", "--selftest-load")  # n3tree.cpp:19-22: message, empty tree
