@@ -122,9 +122,9 @@ def algorithmic_bytes(stats: dict, pixels: int, trackers: bool) -> int:
     return int(empty * 6 + stats["shaded_visits"] * 60 + pixels * (4 + (24 if trackers else 0)))
 
 
-def ncu_traffic():
+def ncu_traffic(name="traversal_ncu_summary.json"):
     """dram bytes per launch from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "traversal_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", name)
     try:
         with open(p) as f:
             return json.load(f).get("dram_bytes_per_launch")
@@ -180,7 +180,7 @@ def mlp_section(mnv, torch, dev, iters=20):
            "dtype": "bf16 operands, fp32 accumulate (TMEM)", "gpu_launches": iters,
            "roofline": {"bound": "tensor", "achieved": tf, "peak": burst, "unit": "TFLOP/s", "frac": tf / burst,
                         "frac_of_sustained_peak": tf / sustained, "peak_source": src + " cuBLAS bf16, burst (kernel timed alone)",
-                        "kernel": "mnv::mlp_forward_kernel", "traffic": None}}
+                        "kernel": "mnv::mlp_forward_kernel", "traffic": ncu_traffic("mlp_ncu_summary.json")}}
     model.close()
     return sec
 
