@@ -41,6 +41,14 @@
 
 #include "mnv_internal.cuh"
 
+// -DMNV_MLP_TIMING (EXTRA=-DMNV_MLP_TIMING make) compiles cycle counters into the issuing lane; with
+// MNV_MLP_DEBUG=1 in the environment every launch then prints where that lane waited.
+#ifdef MNV_MLP_TIMING
+#define MLP_T(...) __VA_ARGS__
+#else
+#define MLP_T(...)
+#endif
+
 namespace mnv {
 namespace {
 
@@ -110,7 +118,7 @@ struct MlpParams {
     int sigma_activation;          // 0 = ReLU, 1 = softplus
     int n_stages;                  // depth of the weight ring
     int out_real;                  // 3 * basis
-    long long *dbg;                // dev: per-CTA cycle counters (MNV_MLP_DEBUG=1), else null
+    long long *dbg;                // per-CTA cycle counters, only in -DMNV_MLP_TIMING builds (MNV_MLP_DEBUG=1), else null
 };
 
 // ------------------------------------------------------------------ PTX helpers
@@ -163,12 +171,8 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
                          smem_u32(bar))
                  : "memory");
 }
-// UMMA shared-memory descriptor, K-major, SWIZZLE_NONE (cute::UMMA::SmemDescriptor):
-// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t) ((saddr >> 4) & 0x3fffu) | ((uint64_t) ((lbo >> 4) & 0x3fffu) << 16) |
-           ((uint64_t) ((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
+// UMMA shared-memory descriptors (K-major, SWIZZLE_NONE, cute::UMMA::SmemDescriptor layout) are assembled from
+// two 32-bit halves in the issue loop: low = start>>4 [0,14) | LBO>>4 [16,30); high = SBO>>4 [0,14) | version 1 [14,16).
 // Instruction descriptor kind::f16: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1,
 // A,B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29)
 __device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
@@ -357,29 +361,24 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         const uint32_t b_hi = ((kChunkK / 8 * 128u) >> 4) | (1u << 14);
         const bool issue = elect_one();
         uint32_t s = 0, ph = 0, act_ph = 0;
-        long long w_act = 0, w_full = 0, w_act_l[kMaxLayers] = {0};
-        const long long t_begin = p.dbg ? clock64() : 0;
+        MLP_T(long long w_act = 0, w_full = 0, w_act_l[kMaxLayers] = {0}; const long long t_begin = p.dbg ? clock64() : 0;)
         for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
             for (int l = 0; l < n_layers; ++l) {
                 const uint32_t *w = s_layer + l * kLayerWords;
                 const uint32_t n_segs = w[0] & 0xffu, idesc = w[1];
                 for (int t = 0; t < kTiles; ++t) {
-                    const long long t0 = p.dbg ? clock64() : 0;
+                    MLP_T(const long long t0 = p.dbg ? clock64() : 0;)
                     mbar_wait(bar_act + t, act_ph);  // A operand of tile t ready, its accumulator drained
-                    if (p.dbg) {
-                        const long long d = clock64() - t0;
-                        w_act += d;
-                        w_act_l[l] += d;
-                    }
+                    MLP_T(if (p.dbg) { const long long d = clock64() - t0; w_act += d; w_act_l[l] += d; })
                     uint32_t acc = 0;
                     for (uint32_t i = 0; i < n_segs; ++i) {
                         const uint32_t w2 = w[4 + 3 * i];
                         uint32_t a_lo = w[2 + 3 * i] + t * (w2 >> 16);
                         const uint32_t a_hi = w[3 + 3 * i];
                         for (uint32_t c = w2 & 0xffffu; c > 0; --c) {
-                            const long long t1 = p.dbg ? clock64() : 0;
+                            MLP_T(const long long t1 = p.dbg ? clock64() : 0;)
                             mbar_wait(bar_full + s, ph);
-                            if (p.dbg) w_full += clock64() - t1;
+                            MLP_T(if (p.dbg) w_full += clock64() - t1;)
                             tc_fence_after();
                             if (issue) {
                                 umma_bf16(tmem_base + t * kMaxN, ((uint64_t) a_hi << 32) | a_lo,
@@ -400,6 +399,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                 act_ph ^= 1;
             }
         }
+#ifdef MNV_MLP_TIMING
         if (p.dbg && issue) {
             long long *o = p.dbg + (size_t) blockIdx.x * 32;
             o[0] = clock64() - t_begin;
@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
             o[2] = w_full;
             for (int l = 0; l < n_layers && l < 16; ++l) o[8 + l] = w_act_l[l];
         }
+#endif
     } else {
         // ===================== PE + epilogue warps =====================
         // thread = (row of the tile, column half); both tiles in turn
@@ -879,7 +880,11 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
     p.out_real = m->cfg.out_rgb_dim;
     const int grid = std::min(p.n_groups, m->num_sms);
     p.dbg = nullptr;
+#ifdef MNV_MLP_TIMING
     static const bool debug = std::getenv("MNV_MLP_DEBUG") != nullptr;  // dev: where does the issuer wait?
+#else
+    const bool debug = false;
+#endif
     if (debug) {
         MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 32 * sizeof(long long)));
         MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 32 * sizeof(long long), stream));

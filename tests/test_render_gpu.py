@@ -160,3 +160,33 @@ def test_full_size_matches_reference_kernel(big, mnv, oracle, torch_cuda, tmp_pa
     m = dt.render_logged(cam, opt)
     assert np.array_equal(ri["hash"], m["hash"]) and np.array_equal(ri["count"], m["count"])
     refi.close()
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 5), (33, 17), (127, 65), (250, 141)])
+def test_ragged_frame_sizes_match_the_reference_kernel(mnv, oracle, tmp_path, w, h):
+    """Frames that are not multiples of the 16x8 CTA tile / 8x4 warp tile, down to a single pixel, with a principal
+    point off the half-pixel grid: pixels and candidates equal to the reference kernel's (oracle/_ref), or to
+    the CPU port within one LSB when the reference build is absent."""
+    import torch
+
+    tree = mnv.synth.make_tree(depth=6)
+    cam = mnv.synth.default_camera(w, h, pose=6)
+    cam["cx"], cam["cy"] = w * 0.47 + 0.3, h * 0.52 - 0.2
+    okw = dict(background_brightness=0.25, basis_minmax=[0, 8])
+    dt = mnv.DeviceTree(tree)
+    P = w * h
+    ts, tp = torch.empty((P, 3), device="cuda"), torch.empty((P, 3), device="cuda")
+    got = dt.render(cam, mnv.default_options(**okw), to_split=ts, to_sample=tp).cpu().numpy()
+    assert got.shape == (h, w, 4) and (got[..., 3] == 255).all()
+    if oracle.ref_available():
+        npz = str(tmp_path / "t.npz")
+        tree.save_npz(npz)
+        ref = oracle.RefRenderer(npz)
+        r = ref.render(cam, oracle.default_options(**okw))
+        assert np.array_equal(got, r["rgba"])
+        assert np.array_equal(ts.cpu().numpy(), r["to_split"]) and np.array_equal(tp.cpu().numpy(), r["to_sample"])
+        ref.close()
+    else:
+        o = oracle.render_voxels(tree, cam, oracle.default_options(**okw))
+        assert np.abs(got.astype(int) - o["rgba"].astype(int)).max() <= 1
+    dt.close()
