@@ -5,7 +5,7 @@
 //   mnv_headless tree.npz [--model model.npz] [--width W --height H] [--frames N] [--poses K]
 //                [--max_tree_capacity C] [--use_splitting] [--use_guided_sampling]
 //                [--bg B] [--out frame.ppm] [--raw frame.rgba] [--save refined.npz] [--seed S] [--verbose]
-//                [--selftest-load] [--selftest-camera] [--selftest-wireframe D]
+//                [--interop] [--selftest-load] [--selftest-camera] [--selftest-wireframe D]
 //
 // Prints one JSON line with the wall-clock frame statistics (camera upload + render + refinement
 // + RGBA8 read-back per frame).
@@ -17,9 +17,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "../../../include/mnv_b200.h"
 #include "n3tree.hpp"
 #include "renderer.hpp"
 
@@ -65,7 +67,7 @@ int main(int argc, char **argv) {
     std::string tree_path, model_path, out_ppm, out_raw, save_path, resave_path;
     int width = 1920, height = 1080, frames = 16, poses = 16, wire_depth = -1;
     long max_cap = 0;
-    bool splitting = false, guided = false, verbose = false, st_load = false, st_camera = false;
+    bool splitting = false, guided = false, verbose = false, st_load = false, st_camera = false, interop = false;
     float bg = 0.f;
     uint64_t seed = 0x5eed;
     for (int i = 1; i < argc; ++i) {
@@ -92,6 +94,7 @@ int main(int argc, char **argv) {
         else if (a == "--selftest-resave") resave_path = val(); // host only: load, write back
         else if (a == "--seed") seed = std::strtoull(val(), nullptr, 0);
         else if (a == "--verbose") verbose = true;
+        else if (a == "--interop") interop = true;  // present through cudaArray surfaces, like the GL viewer does
         else if (a == "--selftest-load") st_load = true;
         else if (a == "--selftest-camera") st_camera = true;
         else if (a == "--selftest-wireframe") wire_depth = std::atoi(val());
@@ -167,13 +170,38 @@ int main(int argc, char **argv) {
         rend.resize(width, height);
         rend.camera.fx = rend.camera.fy = 1111.f * (width / 800.f);
 
+        // --interop: the presentation path of the GL viewer without GL — double-buffered RGBA8 + R32F cudaArray
+        // surfaces (what cudaGraphicsSubResourceGetMappedArray hands out, cuda_renderer.cpp:447-455), cleared per
+        // frame like glClearNamedFramebufferfv does (:72-79), composited in place with offscreen = false
+        void *ca[4] = {nullptr, nullptr, nullptr, nullptr};
+        std::vector<uint8_t> clear_rgba, frame_px;
+        std::vector<float> clear_depth;
+        if (interop) {
+            for (int i = 0; i < 4; ++i)
+                if (mnv_array_create(&ca[i], width, height, i & 1, 0) != MNV_OK) throw std::runtime_error(mnv_last_error());
+            rend.set_interop_surfaces(ca);
+            const uint8_t c8 = (uint8_t) std::min(255.f, std::max(0.f, bg * 255.f));
+            clear_rgba.assign((size_t) width * height * 4, c8);
+            for (size_t i = 3; i < clear_rgba.size(); i += 4) clear_rgba[i] = 255;
+            clear_depth.assign((size_t) width * height, 1e9f);
+            frame_px.resize((size_t) width * height * 4);
+        }
+        int buf = 0;
         std::vector<double> ms;
         int64_t guided_rows = 0, added = 0, resampled = 0;
         for (int f = -2; f < frames; ++f) {  // two untimed warm-up frames
             set_pose(rend.camera, ((f % poses) + poses) % poses, poses);
+            if (interop) {
+                mnv_array_upload(ca[buf * 2], clear_rgba.data(), (size_t) width * 4, height);
+                mnv_array_upload(ca[buf * 2 + 1], clear_depth.data(), (size_t) width * 4, height);
+            }
             const auto t0 = std::chrono::steady_clock::now();
             rend.render();
-            const uint8_t *px = rend.frame_host();
+            const uint8_t *px = interop ? nullptr : rend.frame_host();
+            if (interop) {
+                mnv_array_download(frame_px.data(), ca[buf * 2], (size_t) width * 4, height);
+                buf ^= 1;
+            }
             const auto t1 = std::chrono::steady_clock::now();
             (void) px;
             if (f >= 0) {
@@ -187,7 +215,7 @@ int main(int argc, char **argv) {
             tree.download();
             tree.save(save_path);
         }
-        const uint8_t *px = rend.frame_host();
+        const uint8_t *px = interop ? frame_px.data() : rend.frame_host();
         const size_t nbytes = (size_t) width * height * 4;
         if (!out_ppm.empty()) {
             std::ofstream o(out_ppm, std::ios::binary);
@@ -217,6 +245,7 @@ int main(int argc, char **argv) {
                     rend.camera.transform[1][1], rend.camera.transform[1][2], rend.camera.transform[2][0],
                     rend.camera.transform[2][1], rend.camera.transform[2][2], rend.camera.transform[3][0],
                     rend.camera.transform[3][1], rend.camera.transform[3][2]);
+        for (void *a : ca) mnv_array_destroy(a);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "mnv_headless: %s\n", e.what());
         return 1;

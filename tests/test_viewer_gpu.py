@@ -46,6 +46,21 @@ def test_headless_octree_frame_is_bit_exact(mnv, tmp_path):
     dt.close()
 
 
+@pytest.mark.parametrize("bg", [0.0, 1.0])
+def test_headless_interop_surfaces_equal_the_offscreen_frame(mnv, tmp_path, bg):
+    """VolumeRenderer::set_interop_surfaces: frames composited in place over cleared RGBA8 / R32F cudaArray surfaces
+    (the GL viewer's presentation path, offscreen = false) equal the headless offscreen frames."""
+    tree = mnv.synth.make_tree(depth=6)
+    path = tmp_path / "t.npz"
+    tree.save_npz(str(path))
+    a, b = tmp_path / "a.rgba", tmp_path / "b.rgba"
+    ja = run(mnv, path, "--width", 320, "--height", 180, "--frames", 3, "--bg", bg, "--raw", a)
+    jb = run(mnv, path, "--width", 320, "--height", 180, "--frames", 3, "--bg", bg, "--raw", b, "--interop")
+    fa, fb = np.fromfile(a, np.uint8), np.fromfile(b, np.uint8)
+    assert np.array_equal(fa, fb) and ja["frame_hash"] == jb["frame_hash"]
+    assert fa.reshape(180, 320, 4)[..., :3].std() > 0
+
+
 def make_model(mnv, path, n_sub=1, grid=(1, 1)):
     import torch
     from mlp_reference import MegaNerfMLP
