@@ -159,8 +159,8 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 
     // ---- render_voxels_trace_ray, rt_core.cuh:162-332 ----------------------
     if (TRACK) {
-        RS(kRsSplitPrio) = (float) (opt.max_depth + 1);
-        RS(kRsSampPrio) = (float) (opt.max_sample_count + 1);
+        RSI(kRsSplitPrio) = opt.max_depth + 1;  // priorities stay integers during the march, converted once per ray
+        RSI(kRsSampPrio) = opt.max_sample_count + 1;
         RSI(kRsSplitId) = -1;  // packed leaf id node*8 + child
         RSI(kRsSampId) = -1;
         RS(kRsMaxW) = -1.f;
@@ -313,13 +313,13 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 if (TRACK) {
                     if (weight > RS(kRsMaxW) && depth < opt.max_depth) {
                         RSI(kRsSplitId) = (int32_t) (node * 8u + cidx);
-                        RS(kRsSplitPrio) = (float) depth;
+                        RSI(kRsSplitPrio) = depth;
                         RS(kRsMaxW) = weight;
                         flags |= 1u;
                     }
                     if (weight > RS(kRsMaxSW) && scount < opt.max_sample_count) {
                         RSI(kRsSampId) = (int32_t) (node * 8u + cidx);
-                        RS(kRsSampPrio) = (float) scount;
+                        RSI(kRsSampPrio) = scount;
                         RS(kRsMaxSW) = weight;
                         flags |= 2u;
                     }
@@ -372,11 +372,11 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             } else if (TRACK) {
                 if (!(flags & 1u) && depth < opt.max_depth) {
                     RSI(kRsSplitId) = (int32_t) (node * 8u + cidx);
-                    RS(kRsSplitPrio) = (float) depth;
+                    RSI(kRsSplitPrio) = depth;
                 }
                 if (!(flags & 2u) && scount < opt.max_sample_count) {
                     RSI(kRsSampId) = (int32_t) (node * 8u + cidx);
-                    RS(kRsSampPrio) = (float) scount;
+                    RSI(kRsSampPrio) = scount;
                 }
             }
             t = __fadd_rn(t, delta_t);
@@ -427,11 +427,11 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         // (priority, chunk, child) as floats, like the reference's trackers
         const int32_t sid = RSI(kRsSplitId), pid = RSI(kRsSampId);
         float *ts = p.tg.to_split + (size_t) idx * 3;
-        ts[0] = RS(kRsSplitPrio);
+        ts[0] = (float) RSI(kRsSplitPrio);
         ts[1] = sid < 0 ? -1.f : (float) (sid >> 3);
         ts[2] = sid < 0 ? -1.f : (float) (sid & 7);
         float *tp = p.tg.to_sample + (size_t) idx * 3;
-        tp[0] = RS(kRsSampPrio);
+        tp[0] = (float) RSI(kRsSampPrio);
         tp[1] = pid < 0 ? -1.f : (float) (pid >> 3);
         tp[2] = pid < 0 ? -1.f : (float) (pid & 7);
     }
