@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--workload", default="1080p", choices=["1080p", "mill19"],
                     help="1080p: BASELINE.json configs[1] (the driver's run); mill19: configs[2], a 3840x2160 frame of a "
                          "multi-GB octree of 8 spatial blocks (2x4 on y,z), depth <= 12")
-    ap.add_argument("--mode", default="tiles", choices=["tiles", "split"],
+    ap.add_argument("--mode", default="tiles", choices=["tiles", "split", "hybrid"],
                     help="N > 1: image tiles with the tree replicated (default) or one spatial cell per GPU with "
                          "partials composited over NVLink peer stores")
     ap.add_argument("--max-nodes", type=int, default=16_000_000, help="node budget of the mill19 tree")
@@ -343,7 +343,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the native path has no CPU fallback")
 
     dev = torch.device("cuda", local_rank)
-    if args.mode == "split" and world > 1:
+    if args.mode in ("split", "hybrid") and world > 1:
         return run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, world, local_rank)
     dt = mnv.DeviceTree(tree, device=local_rank)
     opt = mnv.default_options(**opt_kw)
@@ -478,10 +478,16 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
     composite of each owner's P / N pixels (csrc/mnv_multigpu.cu).  Step = march + signal + composite."""
     P = W * H
     dev = torch.device("cuda", local_rank)
-    sp = mnv.multigpu.SubmoduleSplit(tree, W, H, rank=rank, world=world, device=local_rank, dist=dist)
+    hybrid = args.mode == "hybrid" and world >= 4
+    if hybrid:  # row blocks x spatial cells (4 cells per group; 2 on 4 GPUs)
+        cells = 4 if world >= 8 else 2
+        sp = mnv.multigpu.HybridSplit(tree, W, H, rank, world, local_rank, dist, cells=cells)
+        first, n = sp.pixel_range()
+    else:
+        sp = mnv.multigpu.SubmoduleSplit(tree, W, H, rank=rank, world=world, device=local_rank, dist=dist)
+        first, n = mnv.multigpu.owner_range(P, world, rank)
     opt = mnv.default_options(**opt_kw)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    first, n = mnv.multigpu.owner_range(P, world, rank)
     host = torch.empty((max(n, 1), 4), dtype=torch.uint8).pin_memory()
 
     def barrier():
@@ -520,12 +526,13 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
     e2e_ms = timed(args.steps, 3, True)
-    nodes = torch.tensor([sp.local_nodes], device=dev)
+    nodes = torch.tensor([sp.split.local_nodes if hybrid else sp.local_nodes], device=dev)
     dist.all_reduce(nodes, op=dist.ReduceOp.MAX)
     if rank == 0:
         ms_step = float(ms.mean())
-        config = dict(config, parallelism=f"sub-module split: {world} spatial cells, grid {sp.grid_dim} on (y,z); "
-                      f"largest per-GPU subtree {int(nodes.item())} nodes of {tree.capacity}")
+        desc = (f"hybrid: {sp.groups} row blocks x {sp.split.world} spatial cells (grid {sp.split.grid_dim} on (y,z))" if hybrid
+                else f"sub-module split: {world} spatial cells, grid {sp.grid_dim} on (y,z)")
+        config = dict(config, parallelism=f"{desc}; largest per-GPU subtree {int(nodes.item())} nodes of {tree.capacity}")
         line = {"metric": "Mrays/s", "value": P / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 storage, fp64 ray setup)",
@@ -534,7 +541,7 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
                         "ms_per_step": float(e2e_ms.mean()), "h2d_bytes_per_step": 176,
                         "d2h_bytes_per_step": int(n) * 4, "api": "multigpu.SubmoduleSplit.render_block + D2H of the owner's block"},
                 "gpu_launches": args.steps * 3,
-                "exchange": {"bytes_per_gpu_per_step": P * 16, "transport": "NVLink peer stores from the march kernel "
+                "exchange": {"bytes_per_gpu_per_step": (P // sp.groups if hybrid else P) * 16, "transport": "NVLink peer stores from the march kernel "
                              "(CUDA IPC mappings), no collective"},
                 "clocks": clocks}
         print(json.dumps(line), flush=True)

@@ -67,12 +67,12 @@ class SubmoduleSplit:
     single process that plays every rank in turn on one GPU (tests)."""
 
     def __init__(self, tree, width: int, height: int, rank: int = 0, world: int = 1, device: int = 0,
-                 dist=None, grid_dim=None, restrict: bool = True):
+                 dist=None, grid_dim=None, restrict: bool = True, group=None):
         import torch
 
         from . import DeviceTree
 
-        self.rank, self.world, self.device, self.dist = rank, world, device, dist
+        self.rank, self.world, self.device, self.dist, self.group = rank, world, device, dist, group
         self.P = width * height
         self.block = block_pixels(self.P, world)
         self.grid_dim = tuple(grid_dim) if grid_dim is not None else synth.grid_for_world(world)
@@ -99,7 +99,7 @@ class SubmoduleSplit:
         else:
             mine = (self.partials.handle(), self.flags.handle())
             everyone = [None] * world
-            dist.all_gather_object(everyone, mine)
+            dist.all_gather_object(everyone, mine, group=group)
             self.dst, self.flag_dst, self._opened = [], [], []
             for r, (hp, hf) in enumerate(everyone):
                 if r == rank:
@@ -110,7 +110,7 @@ class SubmoduleSplit:
                     self._opened += [a, b]
                     self.dst.append(a)
                     self.flag_dst.append(b)
-            dist.barrier()
+            dist.barrier(group=group)
         self.out = torch.empty(self.block * 4, dtype=torch.uint8, device=f"cuda:{device}")
 
     def _opt_for(self, opt, cell):
@@ -183,10 +183,10 @@ class SubmoduleSplit:
 
         torch.cuda.synchronize()
         if not self.single:
-            self.dist.barrier()
+            self.dist.barrier(group=self.group)
             for a in self._opened:
                 lib().mnv_ipc_close(C.c_void_p(a))
-            self.dist.barrier()
+            self.dist.barrier(group=self.group)
         for t in self.trees.values():
             t.close()
         self.partials.free()
@@ -292,3 +292,36 @@ class ReplicatedPipeline:
     def close(self):
         self.model.close()
         self.dt.close()
+
+
+class HybridSplit:
+    """Row blocks x spatial cells: the `world` GPUs form world / cells groups; group g renders the rows of block g
+    (windowed camera) and, inside the group, each GPU marches one spatial cell and owns 1 / cells of the block's
+    pixels (SubmoduleSplit over the group's sub-communicator).  Cuts both terms of the frame time — the bulk
+    (pixels / groups, visits / cells) and the longest-ray latency floor (a ray's visits are spread over the cells it
+    crosses) — at the pixel tolerance of the split mode."""
+
+    def __init__(self, tree, width, height, rank, world, device, dist, cells=4):
+        assert world % cells == 0
+        self.groups = world // cells
+        self.g, self.c = rank // cells, rank % cells
+        self.first_row, self.rows = row_block(height, self.groups, self.g)
+        subgroup = None
+        for gi in range(self.groups):  # every rank must create every group
+            grp = dist.new_group(list(range(gi * cells, (gi + 1) * cells)))
+            if gi == self.g:
+                subgroup = grp
+        self.split = SubmoduleSplit(tree, width, max(self.rows, 1), rank=self.c, world=cells, device=device, dist=dist,
+                                    group=subgroup)
+        self.width, self.height = width, height
+
+    def render_block(self, cam: dict, opt, stream=None):
+        """RGBA8 of this rank's pixels: rows [first_row, first_row + rows) of the frame, pixel range `owner_range`."""
+        return self.split.render_block(window_camera(cam, self.first_row, self.rows), opt, stream=stream)
+
+    def pixel_range(self):
+        first, n = owner_range(self.width * self.rows, self.split.world, self.c)
+        return self.first_row * self.width + first, n
+
+    def close(self):
+        self.split.close()

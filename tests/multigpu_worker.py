@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=360)
     ap.add_argument("--backend", default="nccl")
+    ap.add_argument("--hybrid", type=int, default=0, help="cells per group of the row-block x cell mode (0: plain split)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -65,7 +66,16 @@ def main():
         dist.destroy_process_group()
         return 0 if all(flags) else 1
 
-    sp = MG.SubmoduleSplit(tree, w, h, rank=rank, world=world, device=local, dist=dist)
+    if args.hybrid:
+        sp = MG.HybridSplit(tree, w, h, rank, world, local, dist, cells=args.hybrid)
+        first, n = sp.pixel_range()
+        blk_cap = sp.split.block
+    else:
+        sp = MG.SubmoduleSplit(tree, w, h, rank=rank, world=world, device=local, dist=dist)
+        blk_cap = sp.block
+    ranges = [None] * world
+    dist.all_gather_object(ranges, (first, n, blk_cap))
+    cap_max = max(r[2] for r in ranges)
     opt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8])
     full = mnv.DeviceTree(tree, device=local) if rank == 0 else None
     worst, fracs, psnrs = 0, [], []
@@ -79,12 +89,15 @@ def main():
     for f in range(args.frames):
         cam = mnv.synth.default_camera(w, h, pose=f)
         blk = blocks[f]
-        padded = torch.zeros((sp.block, 4), dtype=torch.uint8, device=blk.device)
+        padded = torch.zeros((cap_max, 4), dtype=torch.uint8, device=blk.device)
         padded[: blk.shape[0]] = blk
         parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
         dist.gather(padded, parts, dst=0)
         if rank == 0:
-            got = torch.cat(parts)[:P].view(h, w, 4).cpu().numpy()
+            frame = torch.zeros((P, 4), dtype=torch.uint8, device=blk.device)
+            for (f0, fn, _), part in zip(ranges, parts):
+                frame[f0:f0 + fn] = part[:fn]
+            got = frame.view(h, w, 4).cpu().numpy()
             want = full.render(cam, opt).cpu().numpy()
             d = np.abs(got.astype(int) - want.astype(int))
             worst = max(worst, int(d.max()))
@@ -94,7 +107,8 @@ def main():
     torch.cuda.synchronize()
     if rank == 0:
         print(json.dumps({"world": world, "frames": args.frames, "max_abs": worst, "frac_within_1": min(fracs),
-                          "psnr": min(psnrs), "local_nodes": sp.local_nodes, "full_nodes": tree.capacity}), flush=True)
+                          "psnr": min(psnrs), "local_nodes": sp.split.local_nodes if args.hybrid else sp.local_nodes,
+                          "full_nodes": tree.capacity}), flush=True)
         full.close()
     sp.close()
     dist.destroy_process_group()

@@ -79,6 +79,23 @@ def test_split_across_processes_over_peer_memory(mnv):
     assert j["max_abs"] <= 3 and j["frac_within_1"] >= 0.999 and j["psnr"] >= 50.0
 
 
+def test_hybrid_row_blocks_times_cells_across_processes(mnv):
+    """4 GPUs = 2 row blocks x 2 spatial cells (8 GPUs: 2 x 4): needs >= 4 GPUs."""
+    import torch
+
+    n = torch.cuda.device_count()
+    if n < 4:
+        pytest.skip("needs 4 GPUs")
+    world, cells = (8, 4) if n >= 8 else (4, 2)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29535",
+                        os.path.join(ROOT, "tests", "multigpu_worker.py"), "--frames", "4", "--hybrid", str(cells)],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert j["world"] == world and j["max_abs"] <= 3 and j["frac_within_1"] >= 0.999 and j["psnr"] >= 50.0
+
+
 def test_replicated_pipeline_across_processes(mnv):
     """Guided sampling by row blocks and refinement with all-gathered votes on 2+ GPUs == one GPU, bit for bit."""
     import torch
