@@ -176,6 +176,12 @@ int mnv_tree_device_bytes(const mnv_tree *tree, uint64_t *bytes);
 int mnv_tree_download(const mnv_tree *tree, int64_t first, int64_t count, uint16_t *data,
                       int32_t *child, int32_t *parent, int16_t *sample_counts);
 
+/* Launch order of the march kernel's 16x8-pixel CTA tiles for frames with exactly n tiles
+ * (ceil(W/16) * ceil(H/8)): CTA i renders tile order_dev[i] (a permutation of 0..n-1, caller-owned device
+ * memory; NULL restores row-major).  Results do not depend on the order; the frame time does — the kernel cannot
+ * end before its longest rays do, so tiles that hold them should start first. */
+int mnv_tree_set_tile_order(mnv_tree *tree, const int32_t *order_dev, int n);
+
 /* ---- point query: query_single_from_root, include/cuda/rt_core.cuh:117-159
  * xyz_dev: [n][3] tree-space coordinates; out_dev: [n][3] = chunk, child, depth. */
 int mnv_query_points(const mnv_tree *tree, const float *xyz_dev, int64_t n, int32_t *out_dev,

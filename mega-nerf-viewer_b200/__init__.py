@@ -140,6 +140,7 @@ def lib() -> C.CDLL:
     L.mnv_tree_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mnv_tree_download.argtypes = [vp, i64, i64, vp, vp, vp, vp]
     L.mnv_query_points.argtypes = [vp, vp, i64, vp, vp]
+    L.mnv_tree_set_tile_order.argtypes = [vp, vp, i32]
     L.mnv_render_voxels.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, vp,
                                     vp, vp, C.c_bool, C.c_bool, vp]
     L.mnv_render_voxels_tiles.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp,
@@ -301,6 +302,11 @@ class DeviceTree:
         _check(lib().mnv_tree_download(self._h, first, count, data.ctypes.data, child.ctypes.data,
                                        parent.ctypes.data, sc.ctypes.data))
         return data.view(np.float16), child, parent, sc
+
+    def set_tile_order(self, order=None):
+        """order: CUDA int32 tensor, a permutation of the frame's 16x8 CTA tiles (kept alive by this object)."""
+        self._tile_order = order
+        _check(lib().mnv_tree_set_tile_order(self._h, _dptr(order), 0 if order is None else order.numel()))
 
     # ---- point query (rt_core.cuh:117-159) ---------------------------------
     def query_points(self, xyz, stream=None):

@@ -340,6 +340,13 @@ int mnv_tree_download(const mnv_tree *h, int64_t first, int64_t count, uint16_t 
     return download_device_tree(h->t, first, count, data, child, parent, sample_counts);
 }
 
+int mnv_tree_set_tile_order(mnv_tree *h, const int32_t *order_dev, int n) {
+    if (!h || n < 0) return MNV_ERR_INVALID;
+    h->t.tile_order_dev = order_dev;
+    h->t.tile_order_n = order_dev ? n : 0;
+    return MNV_OK;
+}
+
 int mnv_query_points(const mnv_tree *h, const float *xyz_dev, int64_t n, int32_t *out_dev,
                      void *stream) {
     if (!h || (n > 0 && (!xyz_dev || !out_dev))) return MNV_ERR_INVALID;

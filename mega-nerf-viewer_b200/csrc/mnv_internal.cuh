@@ -69,6 +69,8 @@ struct DeviceTree {
     float *split_dev = nullptr, *sample_dev = nullptr;
     size_t frame_bytes = 0;
     unsigned long long *stats_dev = nullptr;
+    const int32_t *tile_order_dev = nullptr;  // dev hook (mnv_tree_set_tile_order): caller-owned launch order
+    int tile_order_n = 0;
     void **partial_table_dev = nullptr;  // 8 pointers: where the owners' partial buffers are mapped on this GPU
     void *partial_table_host[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaStream_t stream = nullptr;
@@ -125,6 +127,8 @@ struct RenderTargets {
     int32_t *visit_log = nullptr;
     int log_cap = 0;
     unsigned long long *frame_stats = nullptr;  // [4] rays, visits, shaded, rays_hit
+    // launch order of the 16x8-pixel CTA tiles: CTA i renders tile tile_order[i] (null: row-major)
+    const int32_t *tile_order = nullptr;
     // image-tile partition (multi-GPU): render tiles with (tile % mod) == rem
     int tile_w = 0, tile_h = 0, tile_mod = 1, tile_rem = 0;
     // sub-module split (multi-GPU): instead of an image, write the ray's premultiplied partial

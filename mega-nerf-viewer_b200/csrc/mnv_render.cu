@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(kThreads, MNV_MIN_BLOCKS)
 render_voxels_kernel(const RenderParams p) {
     // [path_levels][kThreads] node path | [TERMS][kThreads] SH basis | [words][kThreads] ray state
     extern __shared__ int32_t s_dyn[];
-    const int bt = blockIdx.x;
+    const int bt = p.tg.tile_order ? p.tg.tile_order[blockIdx.x] : (int) blockIdx.x;
     const int bty = bt / p.tiles_x, btx = bt - bty * p.tiles_x;
     if (p.tg.tile_mod > 1) {
         const int mt = ((bty * kTileH) / p.tg.tile_h) * p.mtiles_x + (btx * kTileW) / p.tg.tile_w;
@@ -585,6 +585,8 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
         set_error("visit logging and track_visit cannot be combined");
         return MNV_ERR_INVALID;
     }
+    if (!p.tg.tile_order && tree.tile_order_dev && tree.tile_order_n == p.tiles_x * tiles_y)
+        p.tg.tile_order = tree.tile_order_dev;
     const int terms = tree.format == MNV_FORMAT_SH ? tree.basis_dim : 0;
     const dim3 grid((unsigned) (p.tiles_x * tiles_y));
     const size_t smem = (size_t) (p.path_levels +

@@ -190,3 +190,31 @@ def test_ragged_frame_sizes_match_the_reference_kernel(mnv, oracle, tmp_path, w,
         o = oracle.render_voxels(tree, cam, oracle.default_options(**okw))
         assert np.abs(got.astype(int) - o["rgba"].astype(int)).max() <= 1
     dt.close()
+
+
+def test_tile_launch_order_does_not_change_the_frame(mnv):
+    """mnv_tree_set_tile_order: any permutation of the CTA tiles gives the same pixels and candidates."""
+    import torch
+
+    tree = mnv.synth.make_tree(depth=6)
+    dt = mnv.DeviceTree(tree)
+    w, h = 330, 150
+    cam = mnv.synth.default_camera(w, h, pose=7)
+    opt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8])
+    P = w * h
+    def frame():
+        ts, tp = torch.empty((P, 3), device="cuda"), torch.empty((P, 3), device="cuda")
+        img = dt.render(cam, opt, to_split=ts, to_sample=tp)
+        return img.cpu().numpy(), ts.cpu().numpy(), tp.cpu().numpy()
+    want = frame()
+    n_tiles = ((w + 15) // 16) * ((h + 7) // 8)
+    for seed in (0, 1):
+        order = torch.from_numpy(np.random.default_rng(seed).permutation(n_tiles).astype(np.int32)).cuda()
+        dt.set_tile_order(order)
+        got = frame()
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+    dt.set_tile_order(torch.arange(7, dtype=torch.int32, device="cuda"))  # wrong length: ignored
+    assert np.array_equal(frame()[0], want[0])
+    dt.set_tile_order(None)
+    dt.close()
