@@ -176,6 +176,13 @@ int mnv_tree_device_bytes(const mnv_tree *tree, uint64_t *bytes);
 int mnv_tree_download(const mnv_tree *tree, int64_t first, int64_t count, uint16_t *data,
                       int32_t *child, int32_t *parent, int16_t *sample_counts);
 
+/* The library keeps one cudaSurfaceObject_t per cudaArray_t it has been handed (the reference creates one per
+ * launch and never destroys it, renderer_kernel.cu:377-385).  Call this before such an array is destroyed or
+ * unregistered (the viewer: in resize, before cudaGraphicsUnregisterResource, cuda_renderer.cpp:417-421): it
+ * synchronises the device and destroys the cached objects, so a recycled array handle is never mistaken for
+ * the old one. */
+int mnv_tree_release_surfaces(mnv_tree *tree);
+
 /* Launch order of the march kernel's 16x8-pixel CTA tiles for frames with exactly n tiles
  * (ceil(W/16) * ceil(H/8)): CTA i renders tile order_dev[i] (a permutation of 0..n-1, caller-owned device
  * memory; NULL restores row-major).  Results do not depend on the order; the frame time does — the kernel cannot

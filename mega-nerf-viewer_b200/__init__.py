@@ -141,6 +141,7 @@ def lib() -> C.CDLL:
     L.mnv_tree_download.argtypes = [vp, i64, i64, vp, vp, vp, vp]
     L.mnv_query_points.argtypes = [vp, vp, i64, vp, vp]
     L.mnv_tree_set_tile_order.argtypes = [vp, vp, i32]
+    L.mnv_tree_release_surfaces.argtypes = [vp]
     L.mnv_render_voxels.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, vp,
                                     vp, vp, C.c_bool, C.c_bool, vp]
     L.mnv_render_voxels_tiles.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp,
@@ -454,6 +455,7 @@ class DeviceTree:
             out = np.empty((h, w, 4), np.uint8)
             _check(lib().mnv_array_download(out.ctypes.data, img, w * 4, h))
         finally:
+            lib().mnv_tree_release_surfaces(self._h)  # the arrays die here: drop the surface objects bound to them
             lib().mnv_array_destroy(img)
             lib().mnv_array_destroy(dep)
         return out

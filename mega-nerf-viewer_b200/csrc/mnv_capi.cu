@@ -340,6 +340,15 @@ int mnv_tree_download(const mnv_tree *h, int64_t first, int64_t count, uint16_t 
     return download_device_tree(h->t, first, count, data, child, parent, sample_counts);
 }
 
+int mnv_tree_release_surfaces(mnv_tree *h) {
+    if (!h) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    MNV_CUDA(cudaDeviceSynchronize());  // no launch may still be using them
+    for (auto &kv : h->surfaces) cudaDestroySurfaceObject(kv.second);
+    h->surfaces.clear();
+    return MNV_OK;
+}
+
 int mnv_tree_set_tile_order(mnv_tree *h, const int32_t *order_dev, int n) {
     if (!h || n < 0) return MNV_ERR_INVALID;
     h->t.tile_order_dev = order_dev;

@@ -245,6 +245,7 @@ int main(int argc, char **argv) {
                     rend.camera.transform[1][1], rend.camera.transform[1][2], rend.camera.transform[2][0],
                     rend.camera.transform[2][1], rend.camera.transform[2][2], rend.camera.transform[3][0],
                     rend.camera.transform[3][1], rend.camera.transform[3][2]);
+        if (interop) rend.set_interop_surfaces(nullptr);  // drops the surface objects before the arrays go
         for (void *a : ca) mnv_array_destroy(a);
     } catch (const std::exception &e) {
         std::fprintf(stderr, "mnv_headless: %s\n", e.what());

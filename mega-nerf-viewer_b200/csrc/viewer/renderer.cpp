@@ -321,6 +321,7 @@ struct VolumeRenderer::Impl {
         camera.height = height;
         init_trackers();
         guided_capacity = 0;
+        if (interop && tree && tree->device_tree) mnv_tree_release_surfaces(tree->device_tree);
         interop = false;  // surfaces of the old size are gone; the caller re-registers
     }
 
@@ -385,6 +386,8 @@ void VolumeRenderer::resize(int width, int height) { impl_->resize(width, height
 const char *VolumeRenderer::get_backend() { return "CUDA (sm_100a, mnv_b200)"; }
 
 void VolumeRenderer::set_interop_surfaces(void *const cuda_arrays[4]) {
+    // the previous arrays may be gone (resize re-registers the renderbuffers): forget their surface objects
+    if (impl_->tree && impl_->tree->device_tree) mnv_tree_release_surfaces(impl_->tree->device_tree);
     impl_->interop = cuda_arrays != nullptr;
     for (int i = 0; i < 4; ++i) impl_->ca[i] = cuda_arrays ? cuda_arrays[i] : nullptr;
     impl_->buf_index = 0;
