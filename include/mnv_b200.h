@@ -367,6 +367,42 @@ int mnv_composite_partials(mnv_tree *tree, const mnv_camera *cam, const mnv_rend
                            const float *partials_dev, int n, int block_pixels, const float *boxes_host,
                            int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
                            uint32_t wait_value, void *stream);
+/* Guided sampling with the sub-modules sharded across GPUs (BASELINE.json configs[4]): rank g holds
+ * cell g's subtree and sub-MLP only and handles the segment every ray has inside cell g.  The
+ * emission loop of the unsharded frame (rt_core.cuh:321-357) carries two values along the ray — the
+ * octree transmittance T (emission stops below stop_thresh) and the sample count (capped at
+ * max_guided_samples) — and the compositor (rt_core.cuh:361-372) gives every sample the interval
+ * to the NEXT sample.  One exchange of 16 bytes per ray per rank reproduces all three:
+ * mnv_guided_segment_probe: march the cell with T = 1, count = 0; probe_dev f32 [P][4] =
+ *   (T at the cell's exit, samples emitted, z of the first sample or 3e38, 0).
+ *   The ranks all-gather these -> probe_all_dev f32 [n_cells][P][4].
+ * mnv_guided_samples_segment: mnv_guided_samples for the segment, with T and the count at the
+ *   cell's entry derived from the records of the segments in front of it (ordered by first z).
+ * mnv_render_nerf_results_partial: render_nerf_results_kernel (renderer_kernel.cu:298-319) per
+ *   segment: the segment's last sample gets the interval to the first sample of the next emitting
+ *   segment, and only the ray's overall last sample takes the remaining transmittance.  Stores
+ *   premultiplied (r, g, b, 1 - T_segment) into the pixel owner's buffer like
+ *   mnv_render_voxels_partial.  render_depth is not available here (MNV_ERR_INVALID).
+ * mnv_composite_partials_guided: mnv_composite_partials without the early-termination rule and
+ *   with the frame opaque (out[3] = 1, renderer_kernel.cu:315-316). */
+int mnv_guided_segment_probe(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                             float *probe_dev, void *stream);
+int mnv_guided_samples_segment(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                               const int32_t grid_dim[2], const float min_position[3],
+                               const float range[3], const float *probe_all_dev, int n_cells, int slot,
+                               int64_t *offsets_dev, float *z_vals_dev, float *rows_dev, int row_stride,
+                               int16_t *cluster_dev, int64_t capacity_rows, int64_t *total_rows_host,
+                               void *stream);
+int mnv_render_nerf_results_partial(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                                    const float *sample_values_dev, int value_stride, int sigma_col,
+                                    const float *z_vals_dev, const int64_t *offsets_dev,
+                                    const float *probe_all_dev, int n_cells, int slot, int n_owners,
+                                    float *const *partial_dst, int block_pixels, void *stream);
+int mnv_composite_partials_guided(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
+                                  const float *partials_dev, int n, int block_pixels,
+                                  const float *boxes_host, int64_t first_pixel, int n_pixels,
+                                  uint8_t *rgba_dev, const uint32_t *flags_dev, uint32_t wait_value,
+                                  void *stream);
 /* CUDA IPC plumbing for the peer mappings (one process per GPU): a 64-byte handle of a buffer
  * from mnv_malloc, opened in another process with lazy peer access. */
 int mnv_ipc_export(void *ptr_dev, uint8_t handle[64]);

@@ -174,6 +174,12 @@ def lib() -> C.CDLL:
     L.mnv_signal_peers.argtypes = [C.POINTER(vp), i32, i32, C.c_uint32, vp]
     L.mnv_composite_partials.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32, i32, vp, i64, i32,
                                          vp, vp, C.c_uint32, vp]
+    L.mnv_composite_partials_guided.argtypes = L.mnv_composite_partials.argtypes
+    L.mnv_guided_segment_probe.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp]
+    L.mnv_guided_samples_segment.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, vp, i32, i32,
+                                             vp, vp, vp, i32, vp, i64, C.POINTER(i64), vp]
+    L.mnv_render_nerf_results_partial.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32, i32, vp, vp,
+                                                  vp, i32, i32, i32, C.POINTER(vp), i32, vp]
     L.mnv_ipc_export.argtypes = [vp, C.c_char_p]
     L.mnv_ipc_open.argtypes = [C.c_char_p, C.POINTER(vp), i32]
     L.mnv_ipc_close.argtypes = [vp]
@@ -469,11 +475,55 @@ class DeviceTree:
         _check(lib().mnv_render_voxels_partial(self._h, C.byref(cam), C.byref(opt), len(dst_ptrs), arr,
                                                block_pixels, slot, _stream_ptr(stream)))
 
+    def guided_segment_probe(self, cam, opt: RenderOptions, out=None, stream=None):
+        """Probe pass of the sharded guided frame -> f32 [P, 4] = (T at the cell's exit, samples, first z, 0)."""
+        torch = _torch()
+        cam = make_camera(cam)
+        if out is None:
+            out = torch.empty((cam.width * cam.height, 4), dtype=torch.float32, device=f"cuda:{self.device}")
+        _check(lib().mnv_guided_segment_probe(self._h, C.byref(cam), C.byref(opt), _dptr(out), _stream_ptr(stream)))
+        return out
+
+    def guided_samples_segment(self, cam, opt: RenderOptions, grid_dim, min_position, rng, probe_all, slot: int,
+                               capacity_rows: int, stream=None):
+        """guided_samples for this rank's segment; probe_all f32 [n_cells, P, 4] (all ranks' probe records)."""
+        torch = _torch()
+        cam = make_camera(cam)
+        dev = f"cuda:{self.device}"
+        P = cam.width * cam.height
+        in_dim = 3 + (3 if opt.need_viewdir else 0) + (1 if opt.appearance_embedding != -1 else 0)
+        offsets = torch.empty(P, dtype=torch.int64, device=dev)
+        z = torch.empty(capacity_rows, dtype=torch.float32, device=dev)
+        rows = torch.empty((capacity_rows, in_dim), dtype=torch.float32, device=dev)
+        cluster = torch.empty(capacity_rows, dtype=torch.int16, device=dev)
+        gd = np.ascontiguousarray(grid_dim, np.int32)
+        mp = np.ascontiguousarray(min_position, np.float32)
+        rg = np.ascontiguousarray(rng, np.float32)
+        total = C.c_int64(0)
+        assert probe_all.is_contiguous() and probe_all.shape[1:] == (P, 4)
+        _check(lib().mnv_guided_samples_segment(self._h, C.byref(cam), C.byref(opt), gd.ctypes.data, mp.ctypes.data,
+                                                rg.ctypes.data, _dptr(probe_all), probe_all.shape[0], slot,
+                                                _dptr(offsets), _dptr(z), _dptr(rows), in_dim, _dptr(cluster),
+                                                capacity_rows, C.byref(total), _stream_ptr(stream)))
+        v = total.value
+        return dict(total=v, offsets=offsets, z_vals=z[:v], rows=rows[:v], cluster=cluster[:v])
+
+    def render_nerf_results_partial(self, cam, opt: RenderOptions, values, z_vals, offsets, probe_all, slot: int,
+                                    dst_ptrs, block_pixels: int, sigma_col: int = -1, stream=None):
+        cam = make_camera(cam)
+        arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(a)) for a in dst_ptrs])
+        _check(lib().mnv_render_nerf_results_partial(self._h, C.byref(cam), C.byref(opt), _dptr(values),
+                                                     values.stride(0), sigma_col, _dptr(z_vals), _dptr(offsets),
+                                                     _dptr(probe_all), probe_all.shape[0], slot, len(dst_ptrs), arr,
+                                                     block_pixels, _stream_ptr(stream)))
+
     def composite_partials(self, cam, opt: RenderOptions, partials_ptr: int, n: int, block_pixels: int, boxes,
-                           first_pixel: int, n_pixels: int, out, flags_ptr: int = 0, wait_value: int = 0, stream=None):
+                           first_pixel: int, n_pixels: int, out, flags_ptr: int = 0, wait_value: int = 0, stream=None,
+                           guided: bool = False):
         cam = make_camera(cam)
         bx = np.ascontiguousarray(boxes, np.float32)
-        _check(lib().mnv_composite_partials(self._h, C.byref(cam), C.byref(opt), C.c_void_p(partials_ptr), n,
+        fn = lib().mnv_composite_partials_guided if guided else lib().mnv_composite_partials
+        _check(fn(self._h, C.byref(cam), C.byref(opt), C.c_void_p(partials_ptr), n,
                                             block_pixels, bx.ctypes.data, first_pixel, n_pixels, _dptr(out),
                                             C.c_void_p(flags_ptr) if flags_ptr else None, wait_value,
                                             _stream_ptr(stream)))

@@ -671,6 +671,84 @@ int mnv_composite_partials(mnv_tree *h, const mnv_camera *cam, const mnv_render_
                                      n_pixels, rgba_dev, flags_dev, wait_value, static_cast<cudaStream_t>(stream));
 }
 
+int mnv_composite_partials_guided(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                                  const float *partials_dev, int n, int block_pixels, const float *boxes_host,
+                                  int64_t first_pixel, int n_pixels, uint8_t *rgba_dev,
+                                  const uint32_t *flags_dev, uint32_t wait_value, void *stream) {
+    if (!h || !cam || !opt) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    return launch_composite_partials(h->t, *cam, *opt, partials_dev, n, block_pixels, boxes_host, first_pixel,
+                                     n_pixels, rgba_dev, flags_dev, wait_value, static_cast<cudaStream_t>(stream),
+                                     true);
+}
+
+int mnv_guided_segment_probe(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                             float *probe_dev, void *stream) {
+    if (!h || !cam || !opt || !probe_dev) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    GuidedIO io;
+    io.seg_probe = reinterpret_cast<float4 *>(probe_dev);
+    return launch_guided_samples(h->t, *cam, *opt, io, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_guided_samples_segment(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                               const int32_t grid_dim[2], const float min_position[3], const float range[3],
+                               const float *probe_all_dev, int n_cells, int slot, int64_t *offsets_dev,
+                               float *z_vals_dev, float *rows_dev, int row_stride, int16_t *cluster_dev,
+                               int64_t capacity_rows, int64_t *total_rows_host, void *stream) {
+    if (!h || !cam || !opt || !grid_dim || !min_position || !range || !probe_all_dev || !offsets_dev ||
+        !z_vals_dev || !rows_dev || !cluster_dev) {
+        set_error("mnv_guided_samples_segment: missing argument");
+        return MNV_ERR_INVALID;
+    }
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    GuidedIO io;
+    io.offsets = offsets_dev;
+    io.z_vals = z_vals_dev;
+    io.rows = rows_dev;
+    io.cluster = cluster_dev;
+    io.row_stride = row_stride;
+    io.capacity_rows = capacity_rows;
+    io.total_rows = total_rows_host;
+    for (int i = 0; i < 2; ++i) io.grid_dim[i] = grid_dim[i];
+    for (int i = 0; i < 3; ++i) {
+        io.min_position[i] = min_position[i];
+        io.range[i] = range[i];
+    }
+    io.seg_table = reinterpret_cast<const float4 *>(probe_all_dev);
+    io.seg_n = n_cells;
+    io.seg_slot = slot;
+    return launch_guided_samples(h->t, *cam, *opt, io, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_render_nerf_results_partial(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                                    const float *sample_values_dev, int value_stride, int sigma_col,
+                                    const float *z_vals_dev, const int64_t *offsets_dev,
+                                    const float *probe_all_dev, int n_cells, int slot, int n_owners,
+                                    float *const *partial_dst, int block_pixels, void *stream) {
+    if (!h || !cam || !opt || !partial_dst || n_owners < 1 || n_owners > 8 || !offsets_dev) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    DeviceTree &t = h->t;
+    if (!t.partial_table_dev) MNV_CUDA(cudaMalloc(&t.partial_table_dev, 8 * sizeof(void *)));
+    bool changed = false;
+    for (int i = 0; i < n_owners; ++i) {
+        if (!partial_dst[i]) return MNV_ERR_INVALID;
+        changed |= t.partial_table_host[i] != partial_dst[i];
+        t.partial_table_host[i] = partial_dst[i];
+    }
+    if (changed)
+        MNV_CUDA(cudaMemcpyAsync(t.partial_table_dev, t.partial_table_host, 8 * sizeof(void *), cudaMemcpyHostToDevice,
+                                 static_cast<cudaStream_t>(stream)));
+    NerfSegment seg;
+    seg.seg_table = reinterpret_cast<const float4 *>(probe_all_dev);
+    seg.n_seg = n_cells;
+    seg.slot = slot;
+    seg.partial_dst = reinterpret_cast<float4 *const *>(t.partial_table_dev);
+    seg.partial_block = block_pixels;
+    return launch_composite_nerf(h->t, *cam, *opt, nullptr, 0, sample_values_dev, value_stride, sigma_col,
+                                 z_vals_dev, offsets_dev, true, static_cast<cudaStream_t>(stream), &seg);
+}
+
 int mnv_ipc_export(void *ptr_dev, uint8_t handle[64]) {
     if (!ptr_dev || !handle) return MNV_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");

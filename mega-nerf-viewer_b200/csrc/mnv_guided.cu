@@ -46,7 +46,78 @@ struct GuidedParams {
     // cluster rule (rt_core.cuh:541-549)
     int grid0, grid1;
     float min1, min2, range1, range2;
+    // sub-modules sharded across GPUs: this rank marches one cell's segment of every ray
+    float4 *seg_probe;        // [P] out of the probe pass: (T_segment, samples, z of the first sample, -)
+    const float4 *seg_table;  // [seg_n][P] every rank's probe record (null: unsharded)
+    int seg_n, seg_slot;
 };
+
+constexpr float kNoSegment = 3.0e38f;
+
+// What the march of the unsharded frame would carry into this rank's cell, and where the segment after
+// this one starts — from every rank's probe record of the ray.  Cells are disjoint convex boxes, so the
+// segments of a ray do not interleave: ordering them by the z of their first sample is the march order.
+// A segment emits only while the transmittance is above stop_thresh and the ray has fewer than
+// max_guided_samples samples (the two rules of the emission loop below, rt_core.cuh:335-352).
+struct SegmentContext {
+    float T_in;    // transmittance at the cell's entry
+    int count_in;  // samples the ray already has
+    float z_next;  // first sample of the next emitting segment, kNoSegment if this one is the last
+};
+__device__ __forceinline__ SegmentContext segment_context(const float4 *__restrict__ table, int n, int slot,
+                                                          size_t P, size_t idx, float stop_thresh,
+                                                          int max_samples) {
+    SegmentContext c;
+    c.T_in = 1.f;
+    c.count_in = 0;
+    c.z_next = kNoSegment;
+    const float4 mine = table[(size_t) slot * P + idx];
+    const float z_mine = mine.y > 0.f ? mine.z : kNoSegment;
+    float T_after = 1.f;   // running transmittance / count over the segments behind this one, in z order
+    int count_after = 0;
+    float z_prev = -1.f;
+    int prev_slot = -1;
+    // walk the (at most 8) segments in z order without sorting: repeatedly take the smallest key
+    // greater than the previous one
+    for (int k = 0; k < n; ++k) {
+        float zk = kNoSegment;
+        int ck = -1;
+        float4 rk = make_float4(1.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n; ++s) {
+            const float4 r = table[(size_t) s * P + idx];
+            if (!(r.y > 0.f)) continue;
+            const bool after_prev = r.z > z_prev || (r.z == z_prev && s > prev_slot);
+            const bool before_best = r.z < zk || (r.z == zk && s < ck);
+            if (after_prev && (ck < 0 || before_best)) {
+                zk = r.z;
+                ck = s;
+                rk = r;
+            }
+        }
+        if (ck < 0) break;
+        z_prev = zk;
+        prev_slot = ck;
+        const bool before_me = zk < z_mine || (zk == z_mine && ck < slot);
+        if (before_me) {
+            c.T_in = __fmul_rn(c.T_in, rk.x);
+            c.count_in += (int) rk.y;
+            T_after = c.T_in;
+            count_after = c.count_in;
+        } else if (ck == slot) {
+            T_after = __fmul_rn(c.T_in, rk.x);
+            count_after = c.count_in + (int) rk.y;
+        } else {
+            // a later segment: does it emit anything?
+            if (!(T_after < stop_thresh) && count_after < max_samples) {
+                c.z_next = zk;
+                break;
+            }
+            T_after = __fmul_rn(T_after, rk.x);
+            count_after += (int) rk.y;
+        }
+    }
+    return c;
+}
 
 template <bool EMIT, bool TRACK, bool VISIT>
 __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const GuidedParams p) {
@@ -72,9 +143,19 @@ __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const Guid
     int count = 0;
     const int64_t base = EMIT ? (idx == 0 ? 0 : p.offsets[idx - 1]) : 0;
     const float *cm = p.cam.c2w;
+    float T_init = 1.f, z_first = kNoSegment;
+    int count_init = 0;
+    if (p.seg_table) {
+        const SegmentContext sc = segment_context(p.seg_table, p.seg_n, p.seg_slot,
+                                                  (size_t) p.cam.width * p.cam.height, (size_t) idx,
+                                                  opt.stop_thresh, opt.max_guided_samples);
+        T_init = sc.T_in;
+        count_init = sc.count_in;
+    }
+    float T = T_init;
 
-    if (r.hit) {
-        float T = 1.f, t = r.tmin;
+    if (r.hit && !(T_init < opt.stop_thresh) && count_init < opt.max_guided_samples) {
+        float t = r.tmin;
         MarchState ms;
         while (t < r.tmax) {
             const Leaf lf = march_step<VISIT, /*FUSED_POS=*/false>(p.tree.cell, p.max_level, r, t, opt.step_size, ms, path,
@@ -96,7 +177,13 @@ __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const Guid
                         max_sample_weight = weight;
                     }
                 }
-                if (count < opt.max_guided_samples) {
+                if (count_init + count < opt.max_guided_samples) {
+                    if (!EMIT && p.seg_probe && count == 0) {
+                        const float z0 = __fdiv_rn(__fmul_rn(t, r.d0), p.tree.scale[0]);
+                        const float z1 = __fdiv_rn(__fmul_rn(t, r.d1), p.tree.scale[1]);
+                        const float z2 = __fdiv_rn(__fmul_rn(t, r.d2), p.tree.scale[2]);
+                        z_first = ref_norm3(z0, z1, z2);
+                    }
                     if (EMIT) {
                         // true_z = t*dir/scale ; z = |true_z| ; sample = true_cen + true_dir*z
                         const float z0 = __fdiv_rn(__fmul_rn(t, r.d0), p.tree.scale[0]);
@@ -148,7 +235,10 @@ __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const Guid
             t = __fadd_rn(t, lf.delta_t);
         }
     }
-    if (!EMIT) p.num_samples[idx] = count;
+    if (!EMIT) {
+        if (p.seg_probe) p.seg_probe[idx] = make_float4(T, (float) count, z_first, 0.f);
+        else p.num_samples[idx] = count;
+    }
     if (TRACK) {
         float *ts = p.to_split + (size_t) idx * 3;
         ts[0] = split_prio;
@@ -173,6 +263,11 @@ struct CompositeParams {
     const float *z_vals;
     const int64_t *offsets;
     bool offscreen;
+    // segment mode (sub-modules sharded across GPUs): this rank's samples are one segment of every ray
+    const float4 *seg_table;    // [n_seg][P] every rank's probe record
+    int n_seg, slot;
+    float4 *const *partial_dst;  // owner o's [n_seg][block] float4 buffer
+    int partial_block;
 };
 
 template <int TERMS>
@@ -209,7 +304,7 @@ __device__ __forceinline__ float sh_channel_f32(const float (&B)[TERMS > 0 ? TER
     return tmp;
 }
 
-template <int TERMS>
+template <int TERMS, bool SEG>
 __global__ void __launch_bounds__(256) composite_nerf_kernel(const CompositeParams p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = p.cam.width;
@@ -217,10 +312,16 @@ __global__ void __launch_bounds__(256) composite_nerf_kernel(const CompositePara
     const int x = idx % W, y = idx / W;
     const mnv_render_options &opt = p.opt;
     uint32_t rgbx_init = 0;
-    if (!p.offscreen) rgbx_init = surf2Dread<uint32_t>(p.image_surf, x * 4, y, cudaBoundaryModeZero);
+    if (!SEG && !p.offscreen) rgbx_init = surf2Dread<uint32_t>(p.image_surf, x * 4, y, cudaBoundaryModeZero);
 
     float out0 = 0.f, out1 = 0.f, out2 = 0.f;
     const int64_t start = idx == 0 ? 0 : p.offsets[idx - 1], end = p.offsets[idx];
+    // SEG: where the next segment of this ray begins (cells are disjoint convex boxes: segments do not
+    // interleave), so that this segment's last sample gets the same delta as in the unsharded frame
+    float z_next = kNoSegment, t_end = 1.f;
+    if (SEG && start != end)
+        z_next = segment_context(p.seg_table, p.n_seg, p.slot, (size_t) W * p.cam.height, (size_t) idx,
+                                 opt.stop_thresh, opt.max_guided_samples).z_next;
     if (start != end) {
         // view direction: screen2worlddir + rodrigues (renderer_kernel.cu:311-314)
         const float *m = p.cam.c2w;
@@ -245,12 +346,14 @@ __global__ void __launch_bounds__(256) composite_nerf_kernel(const CompositePara
         for (int64_t i = start; i < end; ++i) {
             const float *sv = p.values + i * p.value_stride;
             float weight;
-            if (i < end - 1) {
-                const float delta = __fadd_rn(p.z_vals[i + 1], -p.z_vals[i]);
+            if (i < end - 1 || (SEG && z_next < 1.0e38f)) {
+                const float zn = i < end - 1 ? p.z_vals[i + 1] : z_next;
+                const float delta = __fadd_rn(zn, -p.z_vals[i]);
                 wc = ref_expf(__fmul_rn(delta, -sv[p.sigma_col]));
                 weight = __fmul_rn(ti, __fadd_rn(1.f, -wc));
             } else {
-                weight = ti;
+                weight = ti;  // the last sample of the ray takes what is left
+                if (SEG) wc = 0.f;
             }
             if (opt.render_depth) {
                 out0 = __fmaf_rn(ti, weight, out0);
@@ -265,7 +368,15 @@ __global__ void __launch_bounds__(256) composite_nerf_kernel(const CompositePara
             }
             ti = __fmul_rn(ti, wc);
         }
-        if (opt.render_depth) out0 = out1 = out2 = fminf(__fmul_rn(out0, 0.3f), 1.0f);
+        t_end = ti;
+        if (!SEG && opt.render_depth) out0 = out1 = out2 = fminf(__fmul_rn(out0, 0.3f), 1.0f);
+    }
+    if constexpr (SEG) {
+        // premultiplied colour + alpha of the segment, straight into the pixel owner's memory
+        const int owner = idx / p.partial_block;
+        p.partial_dst[owner][(size_t) p.slot * p.partial_block + (idx - owner * p.partial_block)] =
+            make_float4(out0, out1, out2, __fadd_rn(1.f, -t_end));
+        return;
     }
     // out[3] = 1 (renderer_kernel.cu:315-316): composite_and_write adds nothing
     const float nalpha = 0.f;
@@ -300,6 +411,28 @@ int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_ren
     if ((io.to_split == nullptr) != (io.to_sample == nullptr)) {
         set_error("to_split and to_sample must be given together");
         return MNV_ERR_INVALID;
+    }
+    if (io.seg_table && (io.seg_n < 1 || io.seg_n > 8 || io.seg_slot < 0 || io.seg_slot >= io.seg_n)) {
+        set_error("guided samples: bad segment description (%d of %d)", io.seg_slot, io.seg_n);
+        return MNV_ERR_INVALID;
+    }
+    if (io.seg_probe) {
+        // probe pass of the sharded frame: the march only
+        GuidedParams q{};
+        q.tree = make_view(tree);
+        q.cam = cam;
+        q.opt = opt;
+        q.depth_surf = io.depth_surf;
+        q.offscreen = io.offscreen;
+        q.tiles_x = (W + 15) / 16;
+        q.max_level = std::min(22, std::max(tree.max_leaf_depth, 1) - 1);
+        q.path_levels = q.max_level + 1;
+        q.seg_probe = io.seg_probe;
+        const dim3 g((unsigned) (q.tiles_x * ((H + 7) / 8)));
+        guided_samples_kernel<false, false, false>
+            <<<g, kGThreads, (size_t) q.path_levels * kGThreads * sizeof(int32_t), stream>>>(q);
+        MNV_CUDA(cudaGetLastError());
+        return MNV_OK;
     }
     if (io.track_visit && !io.visited) {
         set_error("track_visit needs a visited buffer");
@@ -353,6 +486,10 @@ int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_ren
     p.min2 = io.min_position[2];
     p.range1 = io.range[1];
     p.range2 = io.range[2];
+    p.seg_probe = nullptr;
+    p.seg_table = io.seg_table;
+    p.seg_n = io.seg_n;
+    p.seg_slot = io.seg_slot;
     const dim3 grid((unsigned) (p.tiles_x * ((H + 7) / 8)));
     const size_t smem = (size_t) p.path_levels * kGThreads * sizeof(int32_t);
 
@@ -387,12 +524,26 @@ int launch_composite_nerf(const DeviceTree &tree, const mnv_camera &cam,
                           const mnv_render_options &opt, uint8_t *image_linear,
                           cudaSurfaceObject_t image_surf, const float *values, int value_stride,
                           int sigma_col, const float *z_vals, const int64_t *offsets, bool offscreen,
-                          cudaStream_t stream) {
-    if ((image_linear == nullptr) == (image_surf == 0)) {
+                          cudaStream_t stream, const NerfSegment *seg) {
+    if (!seg && (image_linear == nullptr) == (image_surf == 0)) {
         set_error("exactly one of image_linear / image surface must be given");
         return MNV_ERR_INVALID;
     }
+    if (seg && opt.render_depth) {
+        set_error("composite_nerf: render_depth is not available in segment mode");
+        return MNV_ERR_INVALID;
+    }
+    if (seg && (seg->n_seg < 1 || seg->n_seg > 8 || seg->slot < 0 || seg->slot >= seg->n_seg ||
+                !seg->seg_table || !seg->partial_dst || seg->partial_block <= 0)) {
+        set_error("composite_nerf: bad segment description");
+        return MNV_ERR_INVALID;
+    }
     CompositeParams p;
+    p.seg_table = seg ? seg->seg_table : nullptr;
+    p.n_seg = seg ? seg->n_seg : 0;
+    p.slot = seg ? seg->slot : 0;
+    p.partial_dst = seg ? seg->partial_dst : nullptr;
+    p.partial_block = seg ? seg->partial_block : 1;
     p.cam = cam;
     p.opt = opt;
     p.basis_dim = tree.basis_dim;
@@ -409,12 +560,30 @@ int launch_composite_nerf(const DeviceTree &tree, const mnv_camera &cam,
     const int th = 256, blocks = (P + th - 1) / th;
     const int terms = tree.format == MNV_FORMAT_SH ? tree.basis_dim : 0;
     switch (terms) {
-        case 0: composite_nerf_kernel<0><<<blocks, th, 0, stream>>>(p); break;
-        case 1: composite_nerf_kernel<1><<<blocks, th, 0, stream>>>(p); break;
-        case 4: composite_nerf_kernel<4><<<blocks, th, 0, stream>>>(p); break;
-        case 9: composite_nerf_kernel<9><<<blocks, th, 0, stream>>>(p); break;
-        case 16: composite_nerf_kernel<16><<<blocks, th, 0, stream>>>(p); break;
-        case 25: composite_nerf_kernel<25><<<blocks, th, 0, stream>>>(p); break;
+        case 0:
+            if (seg) composite_nerf_kernel<0, true><<<blocks, th, 0, stream>>>(p);
+            else composite_nerf_kernel<0, false><<<blocks, th, 0, stream>>>(p);
+            break;
+        case 1:
+            if (seg) composite_nerf_kernel<1, true><<<blocks, th, 0, stream>>>(p);
+            else composite_nerf_kernel<1, false><<<blocks, th, 0, stream>>>(p);
+            break;
+        case 4:
+            if (seg) composite_nerf_kernel<4, true><<<blocks, th, 0, stream>>>(p);
+            else composite_nerf_kernel<4, false><<<blocks, th, 0, stream>>>(p);
+            break;
+        case 9:
+            if (seg) composite_nerf_kernel<9, true><<<blocks, th, 0, stream>>>(p);
+            else composite_nerf_kernel<9, false><<<blocks, th, 0, stream>>>(p);
+            break;
+        case 16:
+            if (seg) composite_nerf_kernel<16, true><<<blocks, th, 0, stream>>>(p);
+            else composite_nerf_kernel<16, false><<<blocks, th, 0, stream>>>(p);
+            break;
+        case 25:
+            if (seg) composite_nerf_kernel<25, true><<<blocks, th, 0, stream>>>(p);
+            else composite_nerf_kernel<25, false><<<blocks, th, 0, stream>>>(p);
+            break;
         default: set_error("unsupported basis_dim %d", terms); return MNV_ERR_INVALID;
     }
     MNV_CUDA(cudaGetLastError());

@@ -166,14 +166,25 @@ struct GuidedIO {
     bool track_visit = false;
     int32_t grid_dim[2] = {1, 1};
     float min_position[3] = {0, 0, 0}, range[3] = {1, 1, 1};
+    // sub-modules sharded across GPUs (mnv_guided_segment_probe / mnv_guided_samples_segment)
+    float4 *seg_probe = nullptr;        // [P]: probe pass only, nothing else is written
+    const float4 *seg_table = nullptr;  // [seg_n][P] all ranks' probe records
+    int seg_n = 0, seg_slot = 0;
 };
 int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_render_options &opt,
                           const GuidedIO &io, cudaStream_t stream);
+// one rank's share of a guided-sampling frame whose sub-modules are sharded across GPUs
+struct NerfSegment {
+    const float4 *seg_table;     // [n_seg][P] all ranks' probe records
+    int n_seg, slot;
+    float4 *const *partial_dst;  // device table of the owners' buffers
+    int partial_block;
+};
 int launch_composite_nerf(const DeviceTree &tree, const mnv_camera &cam,
                           const mnv_render_options &opt, uint8_t *image_linear,
                           cudaSurfaceObject_t image_surf, const float *values, int value_stride,
                           int sigma_col, const float *z_vals, const int64_t *offsets, bool offscreen,
-                          cudaStream_t stream);
+                          cudaStream_t stream, const NerfSegment *seg = nullptr);
 
 // ---- refinement (mnv_refine.cu) -------------------------------------------------
 int refine_add_children(DeviceTree &t, const mnv_render_options &opt, const int32_t *parent_nodes_dev,
@@ -215,7 +226,7 @@ int launch_signal_peers(uint32_t *const *flag_dst_host, int n, int slot, uint32_
 int launch_composite_partials(const DeviceTree &tree, const mnv_camera &cam, const mnv_render_options &opt,
                               const float *partials_dev, int n, int block, const float *boxes_host,
                               int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
-                              uint32_t wait_value, cudaStream_t stream);
+                              uint32_t wait_value, cudaStream_t stream, bool guided = false);
 
 // ---- candidate selection / sub-module dispatch (mnv_select.cu) ------------------
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,

@@ -34,6 +34,9 @@ struct CompositeParams {
     uint32_t *out;              // RGBA8 [n_pixels]
     const uint32_t *flags;      // [n] raised by the producers (may be null)
     uint32_t wait_value;
+    // segments of a guided-sampling frame (mnv_render_nerf_results_partial): no early-termination
+    // rule, and the frame is opaque — out[3] = 1, renderer_kernel.cu:315-316
+    bool guided;
 };
 
 __global__ void signal_peers_kernel(uint32_t *d0, uint32_t *d1, uint32_t *d2, uint32_t *d3, uint32_t *d4,
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256) composite_partials_kernel(const Composite
             c1 = fmaf(T, s.y, c1);
             c2 = fmaf(T, s.z, c2);
             T *= 1.f - s.w;
-            if (T < p.opt.stop_thresh) {  // rt_core.cuh:289-303
+            if (!p.guided && T < p.opt.stop_thresh) {  // rt_core.cuh:289-303
                 const float scale = 1.f / (1.f - T);
                 c0 *= scale;
                 c1 *= scale;
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(256) composite_partials_kernel(const Composite
         }
     }
     if (!done) alpha = 1.f - T;
+    if (p.guided) alpha = 1.f;
     const float remain = (1.f - alpha) * p.opt.background_brightness;
     c0 += remain;
     c1 += remain;
@@ -144,7 +148,7 @@ int launch_signal_peers(uint32_t *const *dst, int n, int slot, uint32_t value, c
 int launch_composite_partials(const DeviceTree &tree, const mnv_camera &cam, const mnv_render_options &opt,
                               const float *partials_dev, int n, int block, const float *boxes_host,
                               int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
-                              uint32_t wait_value, cudaStream_t stream) {
+                              uint32_t wait_value, cudaStream_t stream, bool guided) {
     if (n < 1 || n > kMaxCells || n_pixels < 0 || n_pixels > block || !partials_dev || !rgba_dev || !boxes_host) {
         set_error("composite_partials: bad arguments (n = %d, block = %d, pixels = %d)", n, block, n_pixels);
         return MNV_ERR_INVALID;
@@ -165,6 +169,7 @@ int launch_composite_partials(const DeviceTree &tree, const mnv_camera &cam, con
     p.out = reinterpret_cast<uint32_t *>(rgba_dev);
     p.flags = flags_dev;
     p.wait_value = wait_value;
+    p.guided = guided;
     composite_partials_kernel<<<(unsigned) ((n_pixels + 255) / 256), 256, 0, stream>>>(p);
     MNV_CUDA(cudaGetLastError());
     return MNV_OK;

@@ -294,6 +294,89 @@ class ReplicatedPipeline:
         self.dt.close()
 
 
+class ShardedGuided(SubmoduleSplit):
+    """Guided sampling with the sub-modules SHARDED (BASELINE.json configs[4]): rank g holds cell g's subtree and
+    sub-MLP g only.  Per frame and rank: probe march of the cell -> one all-gather of 16 B per ray (NCCL) ->
+    emission of the cell's samples with the transmittance / sample count the unsharded march would carry into the
+    cell -> sub-MLP g on those rows -> per-segment compositor whose result leaves as one 16-byte peer store per
+    ray into the pixel owner's memory -> flags -> the owner's front-to-back compositor.  No sample row, MLP
+    output or tree node ever crosses NVLink."""
+
+    def __init__(self, tree, submodules, grid_dim, min_position, max_position, width, height, rank=0, world=1,
+                 device=0, dist=None, group=None):
+        from . import MlpModel
+
+        super().__init__(tree, width, height, rank=rank, world=world, device=device, dist=dist, grid_dim=grid_dim,
+                         group=group)
+        assert len(submodules) == world
+        self.model_grid = list(grid_dim)
+        self.min_position = list(min_position)
+        self.range = [float(b) - float(a) for a, b in zip(min_position, max_position)]
+        self.data_dim = tree.data_dim
+        # one single-sub-module container per cell this process plays
+        self.models = {c: MlpModel([submodules[c]], device=device) for c in self.trees}
+        if self.single:
+            # one receive buffer per owner (the base class aliases them; here every owner's block is kept)
+            self._owner_bufs = DeviceBuffer(world * self.stride, device)
+            self.dst = [self._owner_bufs.ptr.value + o * self.stride for o in range(world)]
+
+    def guided_block(self, cam: dict, opt, capacity_rows=None, stream=None):
+        """RGBA8 [n_pixels, 4] of this rank's pixel block (single-process mode: the whole frame) and the number of
+        MLP rows this process evaluated."""
+        import torch
+
+        from . import _check, _stream_ptr, lib
+
+        dev = f"cuda:{self.device}"
+        P, W = self.P, self.world
+        self.frame_id += 1
+        table = torch.empty((W, P, 4), dtype=torch.float32, device=dev)
+        opts = {c: self._opt_for(opt, c) for c in self.trees}
+        for c, dt in self.trees.items():
+            dt.guided_segment_probe(cam, opts[c], out=table[c], stream=stream)
+        if not self.single:
+            self.dist.all_gather_into_tensor(table.view(-1), table[self.rank].reshape(-1).clone(), group=self.group)
+        par = 0 if self.single else (self.frame_id & 1) * self.stride
+        rows_done = 0
+        for c, dt in self.trees.items():
+            cap = capacity_rows or max(1 << 16, int(table[c, :, 1].sum().item()))
+            g = dt.guided_samples_segment(cam, opts[c], self.model_grid, self.min_position, self.range, table, c,
+                                          capacity_rows=cap, stream=stream)
+            vals = torch.empty((max(g["total"], 1), self.data_dim + 1), device=dev)
+            if g["total"]:
+                self.models[c].forward(g["rows"], 0, out=vals, stream=stream)
+            rows_done += g["total"]
+            dt.render_nerf_results_partial(cam, opts[c], vals, g["z_vals"], g["offsets"], table, c,
+                                           [a + par for a in self.dst], self.block, sigma_col=self.data_dim - 1,
+                                           stream=stream)
+            if not self.single:
+                arr = (C.c_void_p * W)(*[C.c_void_p(a) for a in self.flag_dst])
+                _check(lib().mnv_signal_peers(arr, W, c, self.frame_id, _stream_ptr(stream)))
+        dt0 = next(iter(self.trees.values()))
+        if self.single:
+            frame = torch.empty((P, 4), dtype=torch.uint8, device=dev)
+            for o in range(W):
+                first, n = owner_range(P, W, o)
+                dt0.composite_partials(cam, opt, self.dst[o], W, self.block, self.boxes, first, n, self.out, guided=True,
+                                       stream=stream)
+                frame[first:first + n] = self.out[: n * 4].view(n, 4)
+            return frame, rows_done
+        first, n = owner_range(P, W, self.rank)
+        dt0.composite_partials(cam, opt, self.partials.ptr.value + par, W, self.block, self.boxes, first, n, self.out,
+                               flags_ptr=self.flags.ptr.value, wait_value=self.frame_id, guided=True, stream=stream)
+        return self.out[: n * 4].view(n, 4), rows_done
+
+    def close(self):
+        for m in self.models.values():
+            m.close()
+        if hasattr(self, "_owner_bufs"):
+            import torch
+
+            torch.cuda.synchronize()
+            self._owner_bufs.free()
+        super().close()
+
+
 class HybridSplit:
     """Row blocks x spatial cells: the `world` GPUs form world / cells groups; group g renders the rows of block g
     (windowed camera) and, inside the group, each GPU marches one spatial cell and owns 1 / cells of the block's

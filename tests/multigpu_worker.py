@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--height", type=int, default=360)
     ap.add_argument("--backend", default="nccl")
     ap.add_argument("--hybrid", type=int, default=0, help="cells per group of the row-block x cell mode (0: plain split)")
+    ap.add_argument("--guided", action="store_true", help="guided sampling with the sub-modules sharded by cell")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -66,6 +67,8 @@ def main():
         dist.destroy_process_group()
         return 0 if all(flags) else 1
 
+    if args.guided:
+        return guided_main(args, mnv, MG, dist, tree, rank, world, local)
     if args.hybrid:
         sp = MG.HybridSplit(tree, w, h, rank, world, local, dist, cells=args.hybrid)
         first, n = sp.pixel_range()
@@ -111,6 +114,53 @@ def main():
                           "full_nodes": tree.capacity}), flush=True)
         full.close()
     sp.close()
+    dist.destroy_process_group()
+    return 0
+
+
+def guided_main(args, mnv, MG, dist, tree, rank, world, local):
+    import torch
+
+    w, h = args.width, args.height
+    P = w * h
+    grid = mnv.synth.grid_for_world(world)
+    subs = [mnv.synth.make_mlp_weights(seed=11 + i) for i in range(world)]
+    mn, mx = (-1, -1, -1), (1, 1, 1)
+    gopt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8], use_guided_sampling=True,
+                               appearance_embedding=0)
+    sh = MG.ShardedGuided(tree, subs, grid, mn, mx, w, h, rank=rank, world=world, device=local, dist=dist)
+    solo = MG.ReplicatedPipeline(tree, subs, grid, mn, mx, device=local) if rank == 0 else None
+    first, n = MG.owner_range(P, world, rank)
+    blocks, rows = [], []
+    for f in range(args.frames):  # back to back: flags and buffer parities order the frames
+        blk, r = sh.guided_block(mnv.synth.default_camera(w, h, pose=f), gopt)
+        blocks.append(blk.clone())
+        rows.append(r)
+    torch.cuda.synchronize()
+    worst, fracs, psnrs, rows_all, rows_want = 0, [], [], 0, 0
+    for f in range(args.frames):
+        padded = torch.zeros((sh.block, 4), dtype=torch.uint8, device=f"cuda:{local}")
+        padded[:n] = blocks[f]
+        parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
+        dist.gather(padded, parts, dst=0)
+        rt = torch.tensor([rows[f]], device=f"cuda:{local}")
+        dist.all_reduce(rt)
+        if rank == 0:
+            got = torch.cat(parts)[:P].view(h, w, 4).cpu().numpy()
+            want, rw = solo.guided_block(mnv.synth.default_camera(w, h, pose=f), gopt)
+            d = np.abs(got.astype(int) - want.cpu().numpy().astype(int))
+            worst = max(worst, int(d.max()))
+            fracs.append(float((d <= 1).mean()))
+            mse = float(np.mean(d.astype(np.float64) ** 2))
+            psnrs.append(99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse))
+            rows_all += int(rt.item())
+            rows_want += rw
+    if rank == 0:
+        print(json.dumps({"world": world, "frames": args.frames, "max_abs": worst, "frac_within_1": min(fracs),
+                          "psnr": min(psnrs), "rows": rows_all, "rows_want": rows_want,
+                          "local_nodes": sh.local_nodes, "full_nodes": tree.capacity}), flush=True)
+        solo.close()
+    sh.close()
     dist.destroy_process_group()
     return 0
 
