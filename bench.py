@@ -57,9 +57,10 @@ def parse():
     ap.add_argument("--workload", default="1080p", choices=["1080p", "mill19"],
                     help="1080p: BASELINE.json configs[1] (the driver's run); mill19: configs[2], a 3840x2160 frame of a "
                          "multi-GB octree of 8 spatial blocks (2x4 on y,z), depth <= 12")
-    ap.add_argument("--mode", default="tiles", choices=["tiles", "split", "hybrid"],
+    ap.add_argument("--mode", default="tiles", choices=["tiles", "split", "hybrid", "guided"],
                     help="N > 1: image tiles with the tree replicated (default) or one spatial cell per GPU with "
-                         "partials composited over NVLink peer stores")
+                         "partials composited over NVLink peer stores; guided: the guided-sampling frame (configs[4]) "
+                         "with the sub-modules sharded by cell, timed next to the row-block / replicated variant")
     ap.add_argument("--max-nodes", type=int, default=16_000_000, help="node budget of the mill19 tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-headless", action="store_true", help="skip the config 4 / 5 sections (C++ driver)")
@@ -343,6 +344,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the native path has no CPU fallback")
 
     dev = torch.device("cuda", local_rank)
+    if args.mode == "guided" and world > 1:
+        return run_guided(args, mnv, torch, dist, tree, rank, world, local_rank)
     if args.mode in ("split", "hybrid") and world > 1:
         return run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, world, local_rank)
     dt = mnv.DeviceTree(tree, device=local_rank)
@@ -546,6 +549,84 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     sp.close()
+    dist.destroy_process_group()
+    return 0
+
+
+def run_guided(args, mnv, torch, dist, tree, rank, world, local_rank):
+    """N > 1, --mode guided: BASELINE.json configs[4] — a guided-sampling frame (sample emission + per-sample MLP +
+    compositing) at 960x540 unless --width/--height say otherwise, two ways on the same tree and weights:
+    'sharded'  one spatial cell + its sub-MLP per GPU, every GPU handles its segment of every ray, one all-gather
+               of 16 B per ray and one 16 B peer store per ray (multigpu.ShardedGuided);
+    'rows'     tree and all sub-MLPs replicated, each GPU does the rays of its row block, no exchange
+               (multigpu.ReplicatedPipeline)."""
+    W, H = (960, 540) if (args.width, args.height) == (WIDTH, HEIGHT) else (args.width, args.height)
+    P = W * H
+    dev = torch.device("cuda", local_rank)
+    grid = mnv.synth.grid_for_world(world)
+    subs = [mnv.synth.make_mlp_weights(seed=11 + i) for i in range(world)]
+    mn, mx = (-1, -1, -1), (1, 1, 1)
+    gopt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8], use_guided_sampling=True,
+                               appearance_embedding=0)
+    cams = [mnv.synth.default_camera(W, H, pose=i, n_poses=N_POSES) for i in range(N_POSES)]
+    sh = mnv.multigpu.ShardedGuided(tree, subs, grid, mn, mx, W, H, rank=rank, world=world, device=local_rank, dist=dist)
+    rp = mnv.multigpu.ReplicatedPipeline(tree, subs, grid, mn, mx, rank=rank, world=world, device=local_rank, dist=dist)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps = min(args.steps, 32)
+
+    def timed(fn, cap):
+        rows = 0
+        for i in range(3):
+            fn(cams[i % N_POSES], gopt, capacity_rows=cap)
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = []
+        for i in range(steps):
+            flush.fill_(i & 0xff)
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, r = fn(cams[i % N_POSES], gopt, capacity_rows=cap)
+            torch.cuda.synchronize()
+            ms.append((time.perf_counter() - t0) * 1e3)
+            rows += r
+        t = torch.tensor(ms, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rt = torch.tensor([rows], device=dev, dtype=torch.float64)
+        rmax = rt.clone()
+        dist.all_reduce(rt)
+        dist.all_reduce(rmax, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy(), float(rt.item()) / steps, float(rmax.item()) / steps
+
+    cap = P * 12  # rows: generous for either partition (a ray averages ~10 samples on this tree)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_start = time.time()
+    ms_sh, rows_sh, rows_sh_max = timed(sh.guided_block, cap)
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    ms_rp, rows_rp, rows_rp_max = timed(rp.guided_block, cap)
+    nodes = torch.tensor([sh.local_nodes], device=dev)
+    dist.all_reduce(nodes, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        m = float(np.median(ms_sh))
+        line = {"metric": "Mrays/s", "value": P / (m * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
+                "warmup": 3, "ms_per_step": m, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "bf16 MLP operands, f32 accumulate / compositing", "data": "synthetic",
+                "config": {"workload": f"guided-sampling frame {W}x{H}, synthetic depth-{args.depth} SH9 N3Tree "
+                                       f"({tree.capacity} nodes), {world} sub-modules sharded by (y,z) cell {grid}",
+                           "parallelism": f"one cell + sub-MLP per GPU; largest subtree {int(nodes.item())} nodes",
+                           "timing": "host clock around the frame incl. the row-count sync, max over ranks, median of steps; "
+                                     "L2 flushed between frames"},
+                "fps": 1e3 / m, "mlp_rows_per_frame": rows_sh, "mlp_rows_busiest_gpu": rows_sh_max,
+                "exchange": {"all_gather_bytes_per_gpu": P * 16, "peer_store_bytes_per_gpu": P * 16,
+                             "transport": "NCCL all-gather of probe records + NVLink peer stores of segment partials"},
+                "rows_replicated": {"ms_per_step": float(np.median(ms_rp)), "fps": 1e3 / float(np.median(ms_rp)),
+                                    "mlp_rows_per_frame": rows_rp, "mlp_rows_busiest_gpu": rows_rp_max,
+                                    "parallelism": "row blocks, tree + all sub-MLPs replicated, no exchange"},
+                "gpu_launches": steps * 7, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    sh.close()
+    rp.close()
     dist.destroy_process_group()
     return 0
 

@@ -345,8 +345,13 @@ int mnv_render_frame_host_bands(mnv_tree *tree, const mnv_camera *cam,
 
 /* ---- sub-module split across GPUs (second mode; no reference counterpart —
  * the reference is single-GPU).  GPU g owns one spatial cell of the Mega-NeRF (y, z) grid and
- * marches every ray of the frame through that cell only (opt->render_bbox = the cell, tree
- * space); the pixel range [o*block, (o+1)*block) of the frame is composited by owner o.
+ * marches every ray of the frame through that cell only; the pixel range [o*block, (o+1)*block)
+ * of the frame is composited by owner o.
+ *
+ * cell_box (tree space, lo xyz / hi xyz; NULL: no cell) clips the march on top of opt->render_bbox,
+ *   which stays the caller's.  Where a ray enters the cell through a face inside the render box the
+ *   segment starts step_size behind that face — where the unsharded march would land coming from
+ *   the previous leaf (rt_core.cuh:228-230) — instead of marching a sliver the full frame skips.
  *
  * mnv_render_voxels_partial: like mnv_render_voxels(offscreen) but each ray's premultiplied
  *   (r, g, b, alpha) goes, as one 16-byte store, to partial_dst[o] + (slot*block + p % block),
@@ -360,8 +365,8 @@ int mnv_render_frame_host_bands(mnv_tree *tree, const mnv_camera *cam,
  *   opt->background_brightness and writes RGBA8 for pixels [first_pixel, first_pixel+n_pixels)
  *   into rgba_dev[0..n_pixels). */
 int mnv_render_voxels_partial(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
-                              int n_owners, float *const *partial_dst, int block_pixels, int slot,
-                              void *stream);
+                              const float cell_box[6], int n_owners, float *const *partial_dst,
+                              int block_pixels, int slot, void *stream);
 int mnv_signal_peers(uint32_t *const *flag_dst, int n, int slot, uint32_t value, void *stream);
 int mnv_composite_partials(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
                            const float *partials_dev, int n, int block_pixels, const float *boxes_host,
@@ -386,9 +391,9 @@ int mnv_composite_partials(mnv_tree *tree, const mnv_camera *cam, const mnv_rend
  * mnv_composite_partials_guided: mnv_composite_partials without the early-termination rule and
  *   with the frame opaque (out[3] = 1, renderer_kernel.cu:315-316). */
 int mnv_guided_segment_probe(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
-                             float *probe_dev, void *stream);
+                             const float cell_box[6], float *probe_dev, void *stream);
 int mnv_guided_samples_segment(mnv_tree *tree, const mnv_camera *cam, const mnv_render_options *opt,
-                               const int32_t grid_dim[2], const float min_position[3],
+                               const float cell_box[6], const int32_t grid_dim[2], const float min_position[3],
                                const float range[3], const float *probe_all_dev, int n_cells, int slot,
                                int64_t *offsets_dev, float *z_vals_dev, float *rows_dev, int row_stride,
                                int16_t *cluster_dev, int64_t capacity_rows, int64_t *total_rows_host,

@@ -169,14 +169,14 @@ def lib() -> C.CDLL:
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
     L.mnv_mlp_forward.argtypes = [vp, i32, vp, i64, i32, vp, i32, vp]
-    L.mnv_render_voxels_partial.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), i32, C.POINTER(vp),
+    L.mnv_render_voxels_partial.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32, C.POINTER(vp),
                                             i32, i32, vp]
     L.mnv_signal_peers.argtypes = [C.POINTER(vp), i32, i32, C.c_uint32, vp]
     L.mnv_composite_partials.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32, i32, vp, i64, i32,
                                          vp, vp, C.c_uint32, vp]
     L.mnv_composite_partials_guided.argtypes = L.mnv_composite_partials.argtypes
-    L.mnv_guided_segment_probe.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp]
-    L.mnv_guided_samples_segment.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, vp, i32, i32,
+    L.mnv_guided_segment_probe.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp]
+    L.mnv_guided_samples_segment.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp, vp, vp, i32, i32,
                                              vp, vp, vp, i32, vp, i64, C.POINTER(i64), vp]
     L.mnv_render_nerf_results_partial.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32, i32, vp, vp,
                                                   vp, i32, i32, i32, C.POINTER(vp), i32, vp]
@@ -467,25 +467,29 @@ class DeviceTree:
         return out
 
     # ---- sub-module split across GPUs (csrc/mnv_multigpu.cu) ---------------------------------
-    def render_partial(self, cam, opt: RenderOptions, dst_ptrs, block_pixels: int, slot: int, stream=None):
-        """March the frame clipped to opt.render_bbox and store each ray's premultiplied (r, g, b, alpha) into
-        the owners' buffers (`dst_ptrs`: device addresses, local or IPC-mapped peers)."""
+    def render_partial(self, cam, opt: RenderOptions, dst_ptrs, block_pixels: int, slot: int, cell_box=None,
+                       stream=None):
+        """March the frame clipped to opt.render_bbox and `cell_box` (tree space) and store each ray's premultiplied
+        (r, g, b, alpha) into the owners' buffers (`dst_ptrs`: device addresses, local or IPC-mapped peers)."""
         cam = make_camera(cam)
         arr = (C.c_void_p * len(dst_ptrs))(*[C.c_void_p(int(a)) for a in dst_ptrs])
-        _check(lib().mnv_render_voxels_partial(self._h, C.byref(cam), C.byref(opt), len(dst_ptrs), arr,
-                                               block_pixels, slot, _stream_ptr(stream)))
+        cb = None if cell_box is None else np.ascontiguousarray(cell_box, np.float32)
+        _check(lib().mnv_render_voxels_partial(self._h, C.byref(cam), C.byref(opt), None if cb is None else cb.ctypes.data,
+                                               len(dst_ptrs), arr, block_pixels, slot, _stream_ptr(stream)))
 
-    def guided_segment_probe(self, cam, opt: RenderOptions, out=None, stream=None):
+    def guided_segment_probe(self, cam, opt: RenderOptions, cell_box, out=None, stream=None):
         """Probe pass of the sharded guided frame -> f32 [P, 4] = (T at the cell's exit, samples, first z, 0)."""
         torch = _torch()
         cam = make_camera(cam)
         if out is None:
             out = torch.empty((cam.width * cam.height, 4), dtype=torch.float32, device=f"cuda:{self.device}")
-        _check(lib().mnv_guided_segment_probe(self._h, C.byref(cam), C.byref(opt), _dptr(out), _stream_ptr(stream)))
+        cb = np.ascontiguousarray(cell_box, np.float32)
+        _check(lib().mnv_guided_segment_probe(self._h, C.byref(cam), C.byref(opt), cb.ctypes.data, _dptr(out),
+                                              _stream_ptr(stream)))
         return out
 
-    def guided_samples_segment(self, cam, opt: RenderOptions, grid_dim, min_position, rng, probe_all, slot: int,
-                               capacity_rows: int, stream=None):
+    def guided_samples_segment(self, cam, opt: RenderOptions, cell_box, grid_dim, min_position, rng, probe_all,
+                               slot: int, capacity_rows: int, stream=None):
         """guided_samples for this rank's segment; probe_all f32 [n_cells, P, 4] (all ranks' probe records)."""
         torch = _torch()
         cam = make_camera(cam)
@@ -501,7 +505,9 @@ class DeviceTree:
         rg = np.ascontiguousarray(rng, np.float32)
         total = C.c_int64(0)
         assert probe_all.is_contiguous() and probe_all.shape[1:] == (P, 4)
-        _check(lib().mnv_guided_samples_segment(self._h, C.byref(cam), C.byref(opt), gd.ctypes.data, mp.ctypes.data,
+        cb = np.ascontiguousarray(cell_box, np.float32)
+        _check(lib().mnv_guided_samples_segment(self._h, C.byref(cam), C.byref(opt), cb.ctypes.data, gd.ctypes.data,
+                                                mp.ctypes.data,
                                                 rg.ctypes.data, _dptr(probe_all), probe_all.shape[0], slot,
                                                 _dptr(offsets), _dptr(z), _dptr(rows), in_dim, _dptr(cluster),
                                                 capacity_rows, C.byref(total), _stream_ptr(stream)))

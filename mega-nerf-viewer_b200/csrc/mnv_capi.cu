@@ -633,8 +633,9 @@ int mnv_tree_prune_unvisited(mnv_tree *h, int32_t *visited_dev, int64_t *num_del
     return prune_unvisited(h->t, visited_dev, num_deleted_host, static_cast<cudaStream_t>(stream));
 }
 
-int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt, int n_owners,
-                              float *const *partial_dst, int block_pixels, int slot, void *stream) {
+int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                              const float cell_box[6], int n_owners, float *const *partial_dst, int block_pixels,
+                              int slot, void *stream) {
     if (!h || !cam || !opt || !partial_dst || n_owners < 1 || n_owners > 8) return MNV_ERR_INVALID;
     MNV_CUDA(cudaSetDevice(h->t.device));
     DeviceTree &t = h->t;
@@ -653,6 +654,8 @@ int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_rend
     tg.partial_block = block_pixels;
     tg.partial_slot = slot;
     tg.partial_dst = reinterpret_cast<float4 *const *>(t.partial_table_dev);
+    tg.has_cell = cell_box != nullptr;
+    if (cell_box) std::memcpy(tg.cell_box, cell_box, sizeof(tg.cell_box));
     return launch_render_voxels(h->t, *cam, *opt, tg, static_cast<cudaStream_t>(stream));
 }
 
@@ -683,16 +686,18 @@ int mnv_composite_partials_guided(mnv_tree *h, const mnv_camera *cam, const mnv_
 }
 
 int mnv_guided_segment_probe(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
-                             float *probe_dev, void *stream) {
+                             const float cell_box[6], float *probe_dev, void *stream) {
     if (!h || !cam || !opt || !probe_dev) return MNV_ERR_INVALID;
     MNV_CUDA(cudaSetDevice(h->t.device));
     GuidedIO io;
+    io.has_cell = cell_box != nullptr;
+    if (cell_box) std::memcpy(io.cell_box, cell_box, sizeof(io.cell_box));
     io.seg_probe = reinterpret_cast<float4 *>(probe_dev);
     return launch_guided_samples(h->t, *cam, *opt, io, static_cast<cudaStream_t>(stream));
 }
 
 int mnv_guided_samples_segment(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
-                               const int32_t grid_dim[2], const float min_position[3], const float range[3],
+                               const float cell_box[6], const int32_t grid_dim[2], const float min_position[3], const float range[3],
                                const float *probe_all_dev, int n_cells, int slot, int64_t *offsets_dev,
                                float *z_vals_dev, float *rows_dev, int row_stride, int16_t *cluster_dev,
                                int64_t capacity_rows, int64_t *total_rows_host, void *stream) {
@@ -715,6 +720,8 @@ int mnv_guided_samples_segment(mnv_tree *h, const mnv_camera *cam, const mnv_ren
         io.min_position[i] = min_position[i];
         io.range[i] = range[i];
     }
+    io.has_cell = cell_box != nullptr;
+    if (cell_box) std::memcpy(io.cell_box, cell_box, sizeof(io.cell_box));
     io.seg_table = reinterpret_cast<const float4 *>(probe_all_dev);
     io.seg_n = n_cells;
     io.seg_slot = slot;

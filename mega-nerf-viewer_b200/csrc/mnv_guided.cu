@@ -50,6 +50,8 @@ struct GuidedParams {
     float4 *seg_probe;        // [P] out of the probe pass: (T_segment, samples, z of the first sample, -)
     const float4 *seg_table;  // [seg_n][P] every rank's probe record (null: unsharded)
     int seg_n, seg_slot;
+    bool has_cell;
+    float cell_box[6];
 };
 
 constexpr float kNoSegment = 3.0e38f;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const Guid
     float tmax_bg = 1e9f;
     if (!p.offscreen) tmax_bg = surf2Dread<float>(p.depth_surf, x * 4, y, cudaBoundaryModeZero);
     Ray r;
-    setup_ray(p.tree, p.cam, opt, x, y, tmax_bg, r);
+    setup_ray(p.tree, p.cam, opt, x, y, tmax_bg, r, p.has_cell ? p.cell_box : nullptr);
 
     float split_prio = (float) (opt.max_depth + 1), samp_prio = (float) (opt.max_sample_count + 1);
     int32_t split_id = -1, samp_id = -1;
@@ -428,6 +430,8 @@ int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_ren
         q.max_level = std::min(22, std::max(tree.max_leaf_depth, 1) - 1);
         q.path_levels = q.max_level + 1;
         q.seg_probe = io.seg_probe;
+        q.has_cell = io.has_cell;
+        for (int a = 0; a < 6; ++a) q.cell_box[a] = io.cell_box[a];
         const dim3 g((unsigned) (q.tiles_x * ((H + 7) / 8)));
         guided_samples_kernel<false, false, false>
             <<<g, kGThreads, (size_t) q.path_levels * kGThreads * sizeof(int32_t), stream>>>(q);
@@ -490,6 +494,8 @@ int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_ren
     p.seg_table = io.seg_table;
     p.seg_n = io.seg_n;
     p.seg_slot = io.seg_slot;
+    p.has_cell = io.has_cell;
+    for (int a = 0; a < 6; ++a) p.cell_box[a] = io.cell_box[a];
     const dim3 grid((unsigned) (p.tiles_x * ((H + 7) / 8)));
     const size_t smem = (size_t) p.path_levels * kGThreads * sizeof(int32_t);
 

@@ -136,6 +136,8 @@ struct RenderTargets {
     // p / partial_block and lands in its buffer [partial_slot][p % partial_block] (local or peer pointers)
     float4 *const *partial_dst = nullptr;  // device table of partial_n pointers
     int partial_n = 0, partial_block = 0, partial_slot = 0;
+    bool has_cell = false;  // clip the march to cell_box (tree space) with the interior-entry rule of clip_to_cell
+    float cell_box[6] = {0, 0, 0, 1, 1, 1};
 };
 
 int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
@@ -170,6 +172,8 @@ struct GuidedIO {
     float4 *seg_probe = nullptr;        // [P]: probe pass only, nothing else is written
     const float4 *seg_table = nullptr;  // [seg_n][P] all ranks' probe records
     int seg_n = 0, seg_slot = 0;
+    bool has_cell = false;
+    float cell_box[6] = {0, 0, 0, 1, 1, 1};
 };
 int launch_guided_samples(DeviceTree &tree, const mnv_camera &cam, const mnv_render_options &opt,
                           const GuidedIO &io, cudaStream_t stream);

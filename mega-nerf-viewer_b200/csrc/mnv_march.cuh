@@ -27,7 +27,7 @@ struct Ray {
 // (renderer_kernel.cu:30-61,272-283; rt_core.cuh:70-115,188-199).
 __device__ __forceinline__ void setup_ray(const TreeView &tree, const mnv_camera &cam,
                                           const mnv_render_options &opt, int x, int y,
-                                          float tmax_bg, Ray &r) {
+                                          float tmax_bg, Ray &r, const float *cell_box = nullptr) {
     const float *m = cam.c2w;
     const float vx = __fdiv_rn(__fadd_rn(__fadd_rn((float) x, 0.5f), -cam.cx), cam.fx);
     const float vy = __fdiv_rn(-__fadd_rn(__fadd_rn((float) y, 0.5f), -cam.cy), cam.fy);
@@ -74,6 +74,7 @@ __device__ __forceinline__ void setup_ray(const TreeView &tree, const mnv_camera
         tmin = fmaxf(tmin, fminf(t1, t2));
         tmax = fminf(tmax, fmaxf(t1, t2));
     }
+    if (cell_box) clip_to_cell(cell_box, r.c0, r.c1, r.c2, r.i0, r.i1, r.i2, opt.step_size, tmin, tmax);
     tmax = fminf(tmax, tmax_bg);
     r.tmin = tmin;
     r.tmax = tmax;

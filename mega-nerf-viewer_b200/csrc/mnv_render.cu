@@ -203,6 +203,8 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             tmax = fminf(tmax, fmaxf(t1, t2));
         }
     }
+    if (p.tg.partial_n > 0 && p.tg.has_cell)
+        clip_to_cell(p.tg.cell_box, c0, c1, c2, i0, i1, i2, opt.step_size, tmin, tmax);
     tmax = fminf(tmax, tmax_bg);
 
     if (tmax < 0.f || tmin > tmax) {

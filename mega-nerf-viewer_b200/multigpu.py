@@ -113,17 +113,6 @@ class SubmoduleSplit:
             dist.barrier(group=group)
         self.out = torch.empty(self.block * 4, dtype=torch.uint8, device=f"cuda:{device}")
 
-    def _opt_for(self, opt, cell):
-        from . import RenderOptions
-
-        o = RenderOptions()
-        C.memmove(C.byref(o), C.byref(opt), C.sizeof(RenderOptions))
-        # intersection of the caller's render_bbox with the cell
-        for a in range(3):
-            o.render_bbox[a] = max(opt.render_bbox[a], float(self.boxes[cell][a]))
-            o.render_bbox[a + 3] = min(opt.render_bbox[a + 3], float(self.boxes[cell][a + 3]))
-        return o
-
     def march(self, cam, opt, stream=None):
         """This rank's segment of every ray -> the owners' memories, then the flags."""
         from . import _check, _stream_ptr, lib
@@ -131,7 +120,8 @@ class SubmoduleSplit:
         self.frame_id += 1
         par = (self.frame_id & 1) * self.stride
         for cell, dt in self.trees.items():
-            dt.render_partial(cam, self._opt_for(opt, cell), [a + par for a in self.dst], self.block, cell, stream=stream)
+            dt.render_partial(cam, opt, [a + par for a in self.dst], self.block, cell, cell_box=self.boxes[cell],
+                              stream=stream)
             if not self.single:
                 arr = (C.c_void_p * self.world)(*[C.c_void_p(a) for a in self.flag_dst])
                 _check(lib().mnv_signal_peers(arr, self.world, cell, self.frame_id, _stream_ptr(stream)))
@@ -174,7 +164,7 @@ class SubmoduleSplit:
         dst = [self._scratch.ptr.value] * self.world
         dst[owner] = self.partials.ptr.value + (self.frame_id & 1) * self.stride
         for cell, dt in self.trees.items():
-            dt.render_partial(cam, self._opt_for(opt, cell), dst, self.block, cell)
+            dt.render_partial(cam, opt, dst, self.block, cell, cell_box=self.boxes[cell])
 
     def close(self):
         from . import lib
@@ -331,22 +321,21 @@ class ShardedGuided(SubmoduleSplit):
         P, W = self.P, self.world
         self.frame_id += 1
         table = torch.empty((W, P, 4), dtype=torch.float32, device=dev)
-        opts = {c: self._opt_for(opt, c) for c in self.trees}
         for c, dt in self.trees.items():
-            dt.guided_segment_probe(cam, opts[c], out=table[c], stream=stream)
+            dt.guided_segment_probe(cam, opt, self.boxes[c], out=table[c], stream=stream)
         if not self.single:
             self.dist.all_gather_into_tensor(table.view(-1), table[self.rank].reshape(-1).clone(), group=self.group)
         par = 0 if self.single else (self.frame_id & 1) * self.stride
         rows_done = 0
         for c, dt in self.trees.items():
             cap = capacity_rows or max(1 << 16, int(table[c, :, 1].sum().item()))
-            g = dt.guided_samples_segment(cam, opts[c], self.model_grid, self.min_position, self.range, table, c,
+            g = dt.guided_samples_segment(cam, opt, self.boxes[c], self.model_grid, self.min_position, self.range, table, c,
                                           capacity_rows=cap, stream=stream)
             vals = torch.empty((max(g["total"], 1), self.data_dim + 1), device=dev)
             if g["total"]:
                 self.models[c].forward(g["rows"], 0, out=vals, stream=stream)
             rows_done += g["total"]
-            dt.render_nerf_results_partial(cam, opts[c], vals, g["z_vals"], g["offsets"], table, c,
+            dt.render_nerf_results_partial(cam, opt, vals, g["z_vals"], g["offsets"], table, c,
                                            [a + par for a in self.dst], self.block, sigma_col=self.data_dim - 1,
                                            stream=stream)
             if not self.single:

@@ -144,10 +144,10 @@ def _guided_setup(mnv, world, depth=6):
 def test_sharded_guided_sampling_matches_the_unsharded_frame(mnv, world):
     """Sub-modules sharded by cell (one process plays every rank in turn): probe -> exchange -> segment emission
     -> sub-MLP -> segment compositor -> owner compositor must give the unsharded guided frame: the same number
-    of samples (a clipped march enters a cell exactly at its face, the unsharded one steps in from the previous
-    leaf by step_size, so a grazed sliver of a leaf can be seen by one and skipped by the other: a few rows per
-    100 000), pixels within 1/255 on >= 99.9 % of the channels (fp32 blend order and ulp-level sample positions
-    differ), a sliver pixel at most here and there, PSNR >= 50 dB."""
+    of samples up to a few rows per 100 000 (the segment enters its cell step_size behind the face like the
+    unsharded march coming from the previous leaf, but not at the bit-identical t, so a grazed sliver of a leaf
+    can still be seen by one and skipped by the other), pixels within 1/255 on >= 99.99 % of the channels (fp32
+    blend order and ulp-level sample positions differ), a sliver pixel at most here and there, PSNR >= 60 dB."""
     tree, grid, subs, gopt = _guided_setup(mnv, world)
     w, h = 200, 113
     cam = mnv.synth.default_camera(w, h, pose=3)
@@ -162,9 +162,9 @@ def test_sharded_guided_sampling_matches_the_unsharded_frame(mnv, world):
     assert abs(rows - rows_want) <= max(2, rows_want // 5000), (rows, rows_want)
     d = np.abs(got.astype(int) - want.astype(int))
     assert (got[..., 3] == 255).all()
-    assert (d <= 1).mean() >= 0.999, (d <= 1).mean()
-    assert (d > 3).mean() <= 2e-4 and d.max() <= 16, ((d > 3).mean(), d.max())
-    assert psnr(got, want) >= 50.0, psnr(got, want)
+    assert (d <= 1).mean() >= 0.9999, (d <= 1).mean()
+    assert (d > 3).mean() <= 1e-4 and d.max() <= 32, ((d > 3).mean(), d.max())
+    assert psnr(got, want) >= 60.0, psnr(got, want)
     sh.close()
     solo.close()
 
@@ -206,5 +206,5 @@ def test_sharded_guided_across_processes(mnv):
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     j = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert j["world"] == n and j["max_abs"] <= 16 and j["frac_within_1"] >= 0.999 and j["psnr"] >= 50.0
+    assert j["world"] == n and j["max_abs"] <= 32 and j["frac_within_1"] >= 0.9999 and j["psnr"] >= 60.0
     assert abs(j["rows"] - j["rows_want"]) <= max(2, j["rows_want"] // 5000)
