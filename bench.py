@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--workload", default="1080p", choices=["1080p", "mill19"],
                     help="1080p: BASELINE.json configs[1] (the driver's run); mill19: configs[2], a 3840x2160 frame of a "
                          "multi-GB octree of 8 spatial blocks (2x4 on y,z), depth <= 12")
-    ap.add_argument("--mode", default="tiles", choices=["tiles", "split", "hybrid", "guided"],
+    ap.add_argument("--mode", default="tiles", choices=["tiles", "split", "hybrid", "guided", "refine"],
                     help="N > 1: image tiles with the tree replicated (default) or one spatial cell per GPU with "
                          "partials composited over NVLink peer stores; guided: the guided-sampling frame (configs[4]) "
                          "with the sub-modules sharded by cell, timed next to the row-block / replicated variant")
@@ -82,6 +82,10 @@ class ClockSampler:
                  "-i", str(gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            # nvidia-smi needs a moment to start streaming: a short timed region must not be over before the first row
+            t_wait = time.time() + 3.0
+            while not self.rows and time.time() < t_wait:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         self.marks = []
@@ -260,7 +264,8 @@ def shared_tree(make, rank, world, dist, mnv):
         return make()
     import shutil
     d = "/dev/shm/mnv_bench_tree"
-    if rank == 0:
+    reuse = os.environ.get("MNV_BENCH_REUSE_TREE") == "1" and os.path.exists(os.path.join(d, "meta.json"))
+    if rank == 0 and not reuse:  # MNV_BENCH_REUSE_TREE=1: back-to-back runs on one box keep the generated tree
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
         t = make()
@@ -269,7 +274,7 @@ def shared_tree(make, rank, world, dist, mnv):
         with open(os.path.join(d, "meta.json"), "w") as f:
             json.dump({"data_dim": t.data_dim, "data_format": t.data_format}, f)
     dist.barrier()
-    if rank != 0:
+    if rank != 0 or reuse:
         with open(os.path.join(d, "meta.json")) as f:
             meta = json.load(f)
         a = {k: np.load(os.path.join(d, k + ".npy"), mmap_mode="r") for k in ("child", "parent", "depth", "data", "scale", "offset")}
@@ -344,6 +349,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the native path has no CPU fallback")
 
     dev = torch.device("cuda", local_rank)
+    if args.mode == "refine":
+        return run_refine(args, mnv, torch, dist, tree, cams, config, W, H, rank, world, local_rank)
     if args.mode == "guided" and world > 1:
         return run_guided(args, mnv, torch, dist, tree, rank, world, local_rank)
     if args.mode in ("split", "hybrid") and world > 1:
@@ -550,6 +557,67 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
         print(json.dumps(line), flush=True)
     sp.close()
     dist.destroy_process_group()
+    return 0
+
+
+def run_refine(args, mnv, torch, dist, tree, cams, config, W, H, rank, world, local_rank):
+    """--mode refine (any N): frames with dynamic refinement ON (BASELINE.json configs[3]; with --workload mill19 the
+    north-star target case: 3840x2160 on the multi-GB octree).  Per frame: march with vote tracking (row block of
+    this rank) -> NCCL all-gather of the votes when N > 1 -> candidate selection -> 4096 splits x 8 children x 8
+    samples -> 8 sub-MLPs -> commit into the tree, on every replica (multigpu.ReplicatedPipeline).  Host clock
+    around the frame, max over ranks, median over the timed frames; the tree grows by 4096 nodes x 8 per frame."""
+    P = W * H
+    dev = torch.device("cuda", local_rank)
+    subs = [mnv.synth.make_mlp_weights(seed=3 + i) for i in range(8)]
+    steps = min(args.steps, 48)
+    ropt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8], use_splitting=True, appearance_embedding=0,
+                               split_batch_size=4096)
+    pipe = mnv.multigpu.ReplicatedPipeline(tree, subs, (2, 4), (-1, -1, -1), (1, 1, 1), rank=rank, world=world,
+                                           device=local_rank, dist=dist, max_capacity=tree.capacity + (steps + 4) * 4096)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    added = 0
+    for i in range(3):
+        added += pipe.refine_frame(cams[i % N_POSES], ropt)[1]
+    sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_start = time.time()
+    ms = []
+    for i in range(steps):
+        flush.fill_(i & 0xff)
+        sync()
+        t0 = time.perf_counter()
+        _, k = pipe.refine_frame(cams[i % N_POSES], ropt)
+        torch.cuda.synchronize()
+        ms.append((time.perf_counter() - t0) * 1e3)
+        added += k
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end) if sampler else None
+    t = torch.tensor(ms, device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.cpu().numpy()
+    if rank == 0:
+        m = float(np.median(ms))
+        line = {"metric": "Mrays/s", "value": P / (m * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": world, "steps": steps,
+                "warmup": 3, "ms_per_step": m, "ms_per_step_mean": float(ms.mean()), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 march (fp16 storage), bf16 MLP operands with f32 accumulate", "data": "synthetic",
+                "config": dict(config, refinement="ON: 4096 leaf splits x 8 children x 8 samples = 262144 MLP rows over 8 "
+                                                  "sub-modules + commit, every frame",
+                               parallelism="one GPU" if world == 1 else
+                               f"row blocks over {world} GPUs, tree + sub-MLPs replicated, votes all-gathered (NCCL)"),
+                "fps": 1e3 / m, "nodes_added": int(added), "capacity_end": int(pipe.dt.capacity),
+                "gpu_launches": steps * 12, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    pipe.close()
+    if dist is not None:
+        dist.destroy_process_group()
     return 0
 
 
