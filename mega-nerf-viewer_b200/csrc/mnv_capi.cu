@@ -633,12 +633,9 @@ int mnv_tree_prune_unvisited(mnv_tree *h, int32_t *visited_dev, int64_t *num_del
     return prune_unvisited(h->t, visited_dev, num_deleted_host, static_cast<cudaStream_t>(stream));
 }
 
-int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
-                              const float cell_box[6], int n_owners, float *const *partial_dst, int block_pixels,
-                              int slot, void *stream) {
-    if (!h || !cam || !opt || !partial_dst || n_owners < 1 || n_owners > 8) return MNV_ERR_INVALID;
-    MNV_CUDA(cudaSetDevice(h->t.device));
-    DeviceTree &t = h->t;
+// The owners' receive buffers (local or IPC-mapped peers) as a device-side pointer table, refreshed only
+// when the caller's pointers change (they alternate between two frame parities).
+static int upload_owner_table(DeviceTree &t, int n_owners, float *const *partial_dst, cudaStream_t stream) {
     if (!t.partial_table_dev) MNV_CUDA(cudaMalloc(&t.partial_table_dev, 8 * sizeof(void *)));
     bool changed = false;
     for (int i = 0; i < n_owners; ++i) {
@@ -648,7 +645,18 @@ int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_rend
     }
     if (changed)  // pageable source: the copy is staged before the call returns
         MNV_CUDA(cudaMemcpyAsync(t.partial_table_dev, t.partial_table_host, 8 * sizeof(void *), cudaMemcpyHostToDevice,
-                                 static_cast<cudaStream_t>(stream)));
+                                 stream));
+    return MNV_OK;
+}
+
+int mnv_render_voxels_partial(mnv_tree *h, const mnv_camera *cam, const mnv_render_options *opt,
+                              const float cell_box[6], int n_owners, float *const *partial_dst, int block_pixels,
+                              int slot, void *stream) {
+    if (!h || !cam || !opt || !partial_dst || n_owners < 1 || n_owners > 8) return MNV_ERR_INVALID;
+    MNV_CUDA(cudaSetDevice(h->t.device));
+    DeviceTree &t = h->t;
+    if (int rc = upload_owner_table(t, n_owners, partial_dst, static_cast<cudaStream_t>(stream)); rc != MNV_OK)
+        return rc;
     RenderTargets tg;
     tg.partial_n = n_owners;
     tg.partial_block = block_pixels;
@@ -736,16 +744,8 @@ int mnv_render_nerf_results_partial(mnv_tree *h, const mnv_camera *cam, const mn
     if (!h || !cam || !opt || !partial_dst || n_owners < 1 || n_owners > 8 || !offsets_dev) return MNV_ERR_INVALID;
     MNV_CUDA(cudaSetDevice(h->t.device));
     DeviceTree &t = h->t;
-    if (!t.partial_table_dev) MNV_CUDA(cudaMalloc(&t.partial_table_dev, 8 * sizeof(void *)));
-    bool changed = false;
-    for (int i = 0; i < n_owners; ++i) {
-        if (!partial_dst[i]) return MNV_ERR_INVALID;
-        changed |= t.partial_table_host[i] != partial_dst[i];
-        t.partial_table_host[i] = partial_dst[i];
-    }
-    if (changed)
-        MNV_CUDA(cudaMemcpyAsync(t.partial_table_dev, t.partial_table_host, 8 * sizeof(void *), cudaMemcpyHostToDevice,
-                                 static_cast<cudaStream_t>(stream)));
+    if (int rc = upload_owner_table(t, n_owners, partial_dst, static_cast<cudaStream_t>(stream)); rc != MNV_OK)
+        return rc;
     NerfSegment seg;
     seg.seg_table = reinterpret_cast<const float4 *>(probe_all_dev);
     seg.n_seg = n_cells;

@@ -284,6 +284,38 @@ class ReplicatedPipeline:
         self.dt.close()
 
 
+NO_SEGMENT = 3.0e38
+
+
+def segment_context_host(records, slot: int, stop_thresh: float, max_samples: int):
+    """Host mirror of `segment_context` (csrc/mnv_guided.cu) for one ray, used by the tests of the carry rule.
+    records[c] = (T of cell c's segment marched alone, samples it emitted alone, z of its first sample).
+    Returns (T at the entry of cell `slot`, samples the ray already has there, z of the first sample of the next
+    segment that emits anything or NO_SEGMENT)."""
+    order = sorted((c for c in range(len(records)) if records[c][1] > 0), key=lambda c: (records[c][2], c))
+    T_in, count_in, z_next = 1.0, 0, NO_SEGMENT
+    if slot not in order:
+        z_mine = (NO_SEGMENT, slot)
+    else:
+        z_mine = (records[slot][2], slot)
+    T_after, count_after = 1.0, 0
+    for c in order:
+        T_c, n_c, z_c = records[c]
+        if (z_c, c) < z_mine:
+            T_in *= T_c
+            count_in += int(n_c)
+            T_after, count_after = T_in, count_in
+        elif c == slot:
+            T_after, count_after = T_in * T_c, count_in + int(n_c)
+        else:
+            if not (T_after < stop_thresh) and count_after < max_samples:
+                z_next = z_c
+                break
+            T_after *= T_c
+            count_after += int(n_c)
+    return T_in, count_in, z_next
+
+
 class ShardedGuided(SubmoduleSplit):
     """Guided sampling with the sub-modules SHARDED (BASELINE.json configs[4]): rank g holds cell g's subtree and
     sub-MLP g only.  Per frame and rank: probe march of the cell -> one all-gather of 16 B per ray (NCCL) ->
