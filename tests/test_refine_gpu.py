@@ -14,8 +14,8 @@ def _pick_leaves(tree, n, seed):
 
 
 def _assert_renders_like_a_fresh_build(mnv, dt, tree):
-    """The march reads a derived two-level index (csrc/mnv_internal.cuh `wide`): after any refinement step it must
-    describe the same tree as the authoritative planes — render the live tree and a tree rebuilt from its download."""
+    """The march reads the device planes refinement edits in place (cell words, payload records, sample counts): after
+    any refinement step they must describe the same tree as a fresh upload of the downloaded arrays — render both."""
     import torch
 
     data, child, parent, counts = dt.download()
