@@ -351,6 +351,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if args.mode == "refine":
         return run_refine(args, mnv, torch, dist, tree, cams, config, W, H, rank, world, local_rank)
+    if args.mode == "guided" and world == 1:
+        return run_guided_single(args, mnv, torch, tree, local_rank)
     if args.mode == "guided" and world > 1:
         return run_guided(args, mnv, torch, dist, tree, rank, world, local_rank)
     if args.mode in ("split", "hybrid") and world > 1:
@@ -618,6 +620,50 @@ def run_refine(args, mnv, torch, dist, tree, cams, config, W, H, rank, world, lo
     pipe.close()
     if dist is not None:
         dist.destroy_process_group()
+    return 0
+
+
+def run_guided_single(args, mnv, torch, tree, local_rank):
+    """--mode guided on ONE GPU: the guided-sampling frame (emission + per-sample MLP over 8 sub-modules on a 2x4 (y,z)
+    grid + per-ray compositing) on the workload's tree, in-process.  960x540 unless --width/--height are given."""
+    W, H = (960, 540) if (args.width, args.height) == (WIDTH, HEIGHT) else (args.width, args.height)
+    P = W * H
+    dev = torch.device("cuda", local_rank)
+    subs = [mnv.synth.make_mlp_weights(seed=11 + i) for i in range(8)]
+    gopt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8], use_guided_sampling=True,
+                               appearance_embedding=0)
+    cams = [mnv.synth.default_camera(W, H, pose=i, n_poses=N_POSES) for i in range(N_POSES)]
+    rp = mnv.multigpu.ReplicatedPipeline(tree, subs, (2, 4), (-1, -1, -1), (1, 1, 1), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    steps = min(args.steps, 32)
+    cap = P * 12
+    for i in range(2):
+        rp.guided_block(cams[i], gopt, capacity_rows=cap)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    t_start = time.time()
+    ms, rows = [], 0
+    for i in range(steps):
+        flush.fill_(i & 0xff)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, r = rp.guided_block(cams[i % N_POSES], gopt, capacity_rows=cap)
+        torch.cuda.synchronize()
+        ms.append((time.perf_counter() - t0) * 1e3)
+        rows += r
+    t_end = time.time()
+    clocks = sampler.stop(t_start, t_end)
+    m = float(np.median(ms))
+    line = {"metric": "Mrays/s", "value": P / (m * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": 1, "steps": steps, "warmup": 2,
+            "ms_per_step": m, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 MLP operands, f32 accumulate / compositing", "data": "synthetic",
+            "config": {"workload": f"guided-sampling frame {W}x{H}, {args.workload} tree ({tree.capacity} nodes), 8 sub-modules "
+                                   "on a 2x4 (y,z) grid, one GPU",
+                       "timing": "host clock around the frame incl. the row-count sync, median of steps; L2 flushed between frames"},
+            "fps": 1e3 / m, "mlp_rows_per_frame": rows / steps, "mrows_per_s": rows / steps / m / 1e3,
+            "gpu_launches": steps * 12, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    rp.close()
     return 0
 
 
