@@ -3,7 +3,7 @@ Usage: python tools/gpu_parity.py [--depth 8] [--size 320x180] [--golden]"""
 import argparse, os, sys, time, json
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 import mega_nerf_viewer_b200 as mnv
 from oracle import oracle_py as O

@@ -1,7 +1,7 @@
 """Dev (CPU only, oracle): how many lane-steps does the 8x4-tile-per-warp schedule waste, and what would lane-granular
 refill from a warp-local / global queue recover?  Uses the per-ray leaf-visit counts of the CPU oracle."""
 import os, sys, numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import mega_nerf_viewer_b200 as mnv
 from oracle import oracle_py as O
 W, H = 1920, 1080
