@@ -33,7 +33,8 @@ void N3Tree::open(const std::string &path) {
     };
     {
         const npz::Array &a = need("data_dim");
-        data_dim = a.word_size == 8 ? (int) *a.data<int64_t>() : (int) *a.data<int32_t>();
+        data_dim = a.word_size == 8 ? (int) *a.checked<int64_t>(1, "data_dim") : (int) *a.checked<int32_t>(1, "data_dim");
+        if (data_dim < 4 || data_dim > 3 * 25 + 1) throw std::runtime_error("data_dim out of range");
     }
     {
         const npz::Array &a = need("data_format");  // '<U*': UCS-4 code points
@@ -51,32 +52,40 @@ void N3Tree::open(const std::string &path) {
     scale.v.resize(3);
     offset.v.resize(3);
     if (z.count("invradius3")) {
-        const float *p = need("invradius3").data<float>();
+        const float *p = need("invradius3").checked<float>(3, "invradius3");
         for (int i = 0; i < 3; ++i) scale.v[i] = p[i];
     } else {
         const npz::Array &a = need("invradius");
-        const float s = a.word_size == 8 ? (float) *a.data<double>() : *a.data<float>();
+        const float s = a.word_size == 8 ? (float) *a.checked<double>(1, "invradius") : *a.checked<float>(1, "invradius");
         scale.v = {s, s, s};
     }
     {
-        const float *p = need("offset").data<float>();
+        const float *p = need("offset").checked<float>(3, "offset");
         for (int i = 0; i < 3; ++i) offset.v[i] = p[i];
     }
     const npz::Array &ch = need("child");
-    if (ch.shape.size() != 4 || ch.word_size != 4) throw std::runtime_error("child must be int32 [cap,N,N,N]");
+    if (ch.shape.size() != 4 || ch.word_size != 4 || ch.shape[1] < 1 || ch.shape[1] > 8 || ch.shape[2] != ch.shape[1] ||
+        ch.shape[3] != ch.shape[1] || ch.shape[0] < 1)
+        throw std::runtime_error("child must be int32 [cap,N,N,N]");
     N = (int) ch.shape[1];
     if (N != 2) std::printf("WARNING: N != 2 probably doesn't work.\n");
     N2_ = N * N;
     N3_ = N * N * N;
     const int64_t cap = (int64_t) ch.shape[0];
     child.shape = {cap, N3_};
-    child.v.assign(ch.data<int32_t>(), ch.data<int32_t>() + cap * N3_);
+    {
+        const int32_t *c = ch.checked<int32_t>((size_t) cap * N3_, "child");
+        child.v.assign(c, c + cap * N3_);
+    }
     const npz::Array &pd = need("parent_depth");
     if (pd.word_size != 4 || pd.shape.size() != 2 || pd.shape[1] != 2)
         throw std::runtime_error("parent_depth must be int32 [cap,2]");
     parent.shape = {(int64_t) pd.shape[0]};
     parent.v.resize(pd.shape[0]);
-    for (size_t i = 0; i < pd.shape[0]; ++i) parent.v[i] = pd.data<int32_t>()[2 * i];
+    {
+        const int32_t *q = pd.checked<int32_t>(pd.shape[0] * 2, "parent_depth");
+        for (size_t i = 0; i < pd.shape[0]; ++i) parent.v[i] = q[2 * i];
+    }
     int64_t dcap = 0;
     if (z.count("quant_colors")) {
         // VQ-compressed colours (src/n3tree/n3tree.cpp:109-175): SH basis functions [n_retain, n_basis) come from
@@ -86,11 +95,12 @@ void N3Tree::open(const std::string &path) {
         // the channel factor (:156-158) — SURVEY.md quirk 10, not reproduced.
         std::printf("Decoding quantized colors\n");
         const npz::Array &qc = need("quant_colors"), &qm = need("quant_map"), &sg = need("sigma");
-        if (qc.word_size != 2) throw std::runtime_error("codebook must be stored in half precision");
+        if (qc.word_size != 2 || qc.shape.empty()) throw std::runtime_error("codebook must be stored in half precision");
         if (qm.word_size != 2 || qm.shape.size() < 2) throw std::runtime_error("quant_map must be uint16 [n_basis, cap, ...]");
         const int64_t n_q = (int64_t) qm.shape[0];
         if ((int64_t) qc.shape[0] != n_q) throw std::runtime_error("codebook and map basis numbers does not match");
         if (qc.num_vals() != (size_t) n_q * 65536 * 3) throw std::runtime_error("codebook must be [n_basis, 65536, 3]");
+        if (z.count("data_retained") && need("data_retained").shape.empty()) throw std::runtime_error("data_retained must be half [n_retain, cap, N, N, N, 3]");
         const int64_t n_retain = z.count("data_retained") ? (int64_t) need("data_retained").shape[0] : 0;
         const int64_t n_basis = n_q + n_retain;
         dcap = (int64_t) qm.shape[1];
@@ -127,7 +137,7 @@ void N3Tree::open(const std::string &path) {
         for (int64_t s = 0; s < dcap * N3_; ++s) data.v[(size_t) s * data_dim + data_dim - 1] = sig[s];
     } else {
         const npz::Array &dn = need("data");
-        if (dn.word_size != 2) throw std::runtime_error("data must be stored in half precision");
+        if (dn.word_size != 2 || dn.shape.empty()) throw std::runtime_error("data must be stored in half precision");
         dcap = (int64_t) dn.shape[0];
         if ((int64_t) dn.num_vals() != dcap * N3_ * data_dim) throw std::runtime_error("data shape does not match data_dim");
         data.shape = {dcap, N3_, data_dim};
@@ -137,6 +147,12 @@ void N3Tree::open(const std::string &path) {
     sample_counts.v.assign((size_t) dcap * N3_, (int16_t) 8);  // n3tree.cpp:191-193
     if (dcap != parent.size(0)) throw std::runtime_error("data and parent sizes not aligned");
     if (dcap != child.size(0)) throw std::runtime_error("data and child sizes not aligned");
+    // relative child links must stay inside the tree (the march follows them without checks)
+    for (int64_t i = 0; i < dcap; ++i)
+        for (int j = 0; j < N3_; ++j) {
+            const int64_t off = child.v[(size_t) i * N3_ + j];
+            if (off != 0 && (i + off < 0 || i + off >= dcap)) throw std::runtime_error("child link out of range at node " + std::to_string(i));
+        }
     capacity = (int) dcap;
     std::printf("Data format %s, data size: %d\n", data_format.to_string().c_str(), capacity);
 }

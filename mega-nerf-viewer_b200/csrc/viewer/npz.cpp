@@ -2,6 +2,8 @@
 
 #include <zlib.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -43,6 +45,24 @@ std::vector<uint8_t> inflate_raw(const uint8_t *src, size_t n_src, size_t n_dst)
     return out;
 }
 
+// CRC-32 of the member as recorded in the central directory (cnpy does not look at it; a flipped bit in a
+// deflate stream can inflate "successfully").  Members above 1 GiB are checked only with MNV_NPZ_VERIFY=1:
+// the check costs about as much as reading them.
+void check_crc(const uint8_t *p, size_t n, uint32_t want, const std::string &name) {
+    if (n > (size_t(1) << 30)) {
+        const char *v = std::getenv("MNV_NPZ_VERIFY");
+        if (!v || v[0] != '1') return;
+    }
+    uLong c = crc32(0L, Z_NULL, 0);
+    while (n) {
+        const size_t k = std::min<size_t>(n, 1u << 30);
+        c = crc32(c, p, (uInt) k);
+        p += k;
+        n -= k;
+    }
+    if ((uint32_t) c != want) fail("CRC mismatch in member " + name);
+}
+
 }  // namespace
 
 Array parse_npy(const uint8_t *buf, size_t len) {
@@ -60,40 +80,63 @@ Array parse_npy(const uint8_t *buf, size_t len) {
     if (hoff + hlen > len) fail("truncated npy header");
     const std::string h(reinterpret_cast<const char *>(buf + hoff), hlen);
     Array a;
+    const auto value_of = [&](const char *key) -> size_t {  // index of the first character after "key:" and blanks
+        size_t p = h.find(key);
+        if (p == std::string::npos) fail(std::string("npy header without ") + key);
+        p = h.find(':', p);
+        if (p == std::string::npos) fail(std::string("npy header: no value for ") + key);
+        ++p;
+        while (p < h.size() && h[p] == ' ') ++p;
+        if (p >= h.size()) fail(std::string("npy header: no value for ") + key);
+        return p;
+    };
     // 'descr': '<f4'
-    size_t p = h.find("'descr'");
-    if (p == std::string::npos) fail("npy header without descr");
-    p = h.find('\'', h.find(':', p));
+    size_t p = value_of("'descr'");
+    if (h[p] != '\'') fail("npy header: structured dtypes are not supported");
     const size_t q = h.find('\'', p + 1);
+    if (q == std::string::npos) fail("npy header: unterminated descr");
     const std::string descr = h.substr(p + 1, q - p - 1);
-    if (descr.size() < 2) fail("bad descr " + descr);
+    if (descr.size() < 2 || descr.size() > 16) fail("bad descr " + descr);
     size_t t = (descr[0] == '<' || descr[0] == '>' || descr[0] == '|' || descr[0] == '=') ? 1 : 0;
     if (descr[0] == '>') fail("big-endian arrays are not supported");
     a.kind = descr[t];
-    a.word_size = (size_t) std::atoi(descr.c_str() + t + 1);
-    if (a.kind == 'U') a.word_size *= 4;  // UCS-4 (the reference patches cnpy the same way, cnpy.cpp:113)
-    if (a.kind == '?') a.word_size = 1;
+    if (std::string("fiub?US").find(a.kind) == std::string::npos) fail("unsupported dtype " + descr);
+    size_t ws = 0;
+    for (size_t i = t + 1; i < descr.size(); ++i) {
+        if (!std::isdigit(static_cast<unsigned char>(descr[i]))) fail("bad descr " + descr);
+        ws = ws * 10 + (size_t) (descr[i] - '0');
+        if (ws > (1u << 20)) fail("bad descr " + descr);
+    }
+    if (a.kind == '?') ws = 1;
+    const bool text = a.kind == 'U' || a.kind == 'S';
+    if (ws == 0 || (!text && ws != 1 && ws != 2 && ws != 4 && ws != 8)) fail("bad item size in " + descr);
+    a.word_size = a.kind == 'U' ? ws * 4 : ws;  // UCS-4 (the reference patches cnpy the same way, cnpy.cpp:113)
     // 'fortran_order': False
-    p = h.find("'fortran_order'");
-    a.fortran_order = p != std::string::npos && h.compare(h.find(':', p) + 1 + (h[h.find(':', p) + 1] == ' '), 4, "True") == 0;
+    a.fortran_order = h.compare(value_of("'fortran_order'"), 4, "True") == 0;
     // 'shape': (a, b, ...)
-    p = h.find("'shape'");
-    if (p == std::string::npos) fail("npy header without shape");
-    p = h.find('(', p);
+    p = value_of("'shape'");
+    if (h[p] != '(') fail("npy header: shape is not a tuple");
     const size_t e = h.find(')', p);
-    std::string dims = h.substr(p + 1, e - p - 1);
-    size_t pos = 0;
+    if (e == std::string::npos) fail("npy header: unterminated shape");
+    const std::string dims = h.substr(p + 1, e - p - 1);
+    size_t pos = 0, count = 1;
     while (pos < dims.size()) {
         while (pos < dims.size() && (dims[pos] == ' ' || dims[pos] == ',')) ++pos;
         if (pos >= dims.size()) break;
-        size_t end = pos;
-        while (end < dims.size() && std::isdigit(static_cast<unsigned char>(dims[end]))) ++end;
-        if (end == pos) fail("bad shape " + dims);
-        a.shape.push_back((size_t) std::stoull(dims.substr(pos, end - pos)));  // 64-bit dims
+        size_t end = pos, v = 0;
+        while (end < dims.size() && std::isdigit(static_cast<unsigned char>(dims[end]))) {
+            v = v * 10 + (size_t) (dims[end] - '0');
+            if (v > (size_t(1) << 48)) fail("bad shape " + dims);
+            ++end;
+        }
+        if (end == pos || a.shape.size() >= 32) fail("bad shape " + dims);
+        a.shape.push_back(v);  // 64-bit dims
+        if (v != 0 && count > (size_t(1) << 56) / v) fail("bad shape " + dims);
+        count *= v;
         pos = end;
     }
-    const size_t nbytes = a.num_vals() * a.word_size;
-    if (hoff + hlen + nbytes > len) fail("npy payload shorter than its shape");
+    if (count > (len - hoff - hlen) / a.word_size) fail("npy payload shorter than its shape");
+    const size_t nbytes = count * a.word_size;
     a.bytes.assign(buf + hoff + hlen, buf + hoff + hlen + nbytes);
     return a;
 }
@@ -127,11 +170,13 @@ Archive load(const std::string &path) {
     Archive out;
     size_t p = (size_t) cd_off;
     for (uint64_t i = 0; i < n_entries; ++i) {
-        if (p + 46 > size || rd32(&buf[p]) != 0x02014b50) fail("bad central directory entry");
+        if (p > size || size - p < 46 || rd32(&buf[p]) != 0x02014b50) fail("bad central directory entry");
         const uint16_t method = rd16(&buf[p + 10]);
+        const uint32_t want_crc = rd32(&buf[p + 16]);
         uint64_t csize = rd32(&buf[p + 20]), usize = rd32(&buf[p + 24]);
         const uint16_t nlen = rd16(&buf[p + 28]), xlen = rd16(&buf[p + 30]), clen = rd16(&buf[p + 32]);
         uint64_t lho = rd32(&buf[p + 42]);
+        if (size - p - 46 < (size_t) nlen + xlen + clen) fail("central directory entry runs past the end of the file");
         std::string name(reinterpret_cast<const char *>(&buf[p + 46]), nlen);
         // ZIP64 extended information (header id 0x0001): present fields in fixed order
         size_t x = p + 46 + nlen;
@@ -140,21 +185,31 @@ Archive load(const std::string &path) {
             const uint16_t id = rd16(&buf[x]), sz = rd16(&buf[x + 2]);
             if (id == 0x0001) {
                 size_t y = x + 4;
-                if (usize == 0xffffffffu) { usize = rd64(&buf[y]); y += 8; }
-                if (csize == 0xffffffffu) { csize = rd64(&buf[y]); y += 8; }
-                if (lho == 0xffffffffu) { lho = rd64(&buf[y]); }
+                const size_t yend = std::min(xend, y + sz);
+                const auto next64 = [&](uint64_t &v) {
+                    if (y + 8 > yend) fail("short ZIP64 extra field in " + name);
+                    v = rd64(&buf[y]);
+                    y += 8;
+                };
+                if (usize == 0xffffffffu) next64(usize);
+                if (csize == 0xffffffffu) next64(csize);
+                if (lho == 0xffffffffu) next64(lho);
             }
             x += 4 + sz;
         }
         p = xend + clen;
-        if (lho + 30 > size || rd32(&buf[lho]) != 0x04034b50) fail("bad local header for " + name);
+        if (lho > size || size - lho < 30 || rd32(&buf[lho]) != 0x04034b50) fail("bad local header for " + name);
         const size_t data = (size_t) lho + 30 + rd16(&buf[lho + 26]) + rd16(&buf[lho + 28]);
-        if (data + csize > size) fail("member " + name + " runs past the end of the file");
+        if (data > size || csize > size - data) fail("member " + name + " runs past the end of the file");
+        if (method == 0 && usize != csize) fail("stored member " + name + " with different sizes");
+        if (usize > (uint64_t(1) << 40)) fail("member " + name + " is implausibly large");
         if (name.size() > 4 && name.compare(name.size() - 4, 4, ".npy") == 0) name.resize(name.size() - 4);
         if (method == 0) {
+            check_crc(&buf[data], (size_t) usize, want_crc, name);
             out[name] = parse_npy(&buf[data], (size_t) usize);
         } else if (method == 8) {
             const std::vector<uint8_t> raw = inflate_raw(&buf[data], (size_t) csize, (size_t) usize);
+            check_crc(raw.data(), raw.size(), want_crc, name);
             out[name] = parse_npy(raw.data(), raw.size());
         } else {
             fail("unsupported compression method in " + name);

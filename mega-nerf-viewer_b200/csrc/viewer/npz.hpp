@@ -5,6 +5,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,15 @@ struct Array {
     }
     template <typename T>
     const T *data() const { return reinterpret_cast<const T *>(bytes.data()); }
+    // Size- and width-checked view: at least n elements of sizeof(T) bytes each, else std::runtime_error.
+    template <typename T>
+    const T *checked(size_t n, const char *what) const {
+        if (word_size != sizeof(T) || n > bytes.size() / sizeof(T) || num_vals() < n)
+            throw std::runtime_error(std::string("npz: ") + what + ": expected at least " + std::to_string(n) + " elements of " +
+                                     std::to_string(sizeof(T)) + " bytes, found " + std::to_string(num_vals()) + " of " +
+                                     std::to_string(word_size));
+        return data<T>();
+    }
 };
 
 using Archive = std::map<std::string, Array>;

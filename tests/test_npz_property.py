@@ -80,3 +80,81 @@ def test_damaged_archives_fail_cleanly(mnv, tmp_path_factory, cut, flip):
     (d / "flip.npz").write_bytes(bytes(blob))
     r = _run(mnv, d / "flip.npz", "--selftest-load")
     assert r.returncode in (0, 1), (r.returncode, r.stderr[-300:])
+
+
+def _load_rc(mnv, path):
+    import subprocess
+
+    r = subprocess.run([mnv.HEADLESS_BIN, str(path), "--selftest-load"], capture_output=True, timeout=30)
+    return r.returncode, r.stderr[-200:].decode("latin1")
+
+
+def test_npy_header_damage_behind_a_valid_crc(mnv, tmp_path):
+    """Members re-zipped with correct CRCs but damaged .npy headers, truncated payloads or absurd header lengths:
+    the loader must reject (or load) them, never crash — the parser may not lean on the CRC check."""
+    import random
+    import zipfile
+
+    mnv.build_library()
+    rnd = random.Random(7)
+    tree = mnv.synth.make_tree(depth=3)
+    src = tmp_path / "a.npz"
+    tree.save_npz(str(src), compressed=False)
+    with zipfile.ZipFile(src) as z:
+        members = {n: z.read(n) for n in z.namelist()}
+    alphabet = b"0123456789(),' <>|fiuUS:{}x\x00\xff"
+    for k in range(150):
+        m = dict(members)
+        name = rnd.choice(sorted(m))
+        b = bytearray(m[name])
+        mode = rnd.random()
+        if mode < 0.6:
+            hl = b[8] | (b[9] << 8)
+            for _ in range(rnd.choice((1, 2, 3))):
+                b[10 + rnd.randrange(hl)] = rnd.choice(alphabet)
+        elif mode < 0.8:
+            b = b[: rnd.randrange(6, len(b))]
+        else:
+            b[8], b[9] = rnd.randrange(256), rnd.randrange(256)
+        m[name] = bytes(b)
+        dst = tmp_path / "y.npz"
+        with zipfile.ZipFile(dst, "w", zipfile.ZIP_DEFLATED if k % 2 else zipfile.ZIP_STORED) as z:
+            for n, v in m.items():
+                z.writestr(n, v)
+        rc, err = _load_rc(mnv, dst)
+        assert rc in (0, 1), (k, name, rc, err, bytes(b[:100]))
+
+
+def test_well_formed_archives_with_hostile_contents(mnv, tmp_path):
+    """Arrays numpy wrote correctly but that do not describe a tree: every one must be refused with a message
+    (reference: std::runtime_error on bad dtype / shape, src/n3tree/n3tree.cpp:114,121,180,196,200)."""
+    mnv.build_library()
+    tree = mnv.synth.make_tree(depth=3)
+    src = tmp_path / "a.npz"
+    tree.save_npz(str(src))
+    base = dict(np.load(src))
+
+    def variant(**kw):
+        c = dict(base)
+        c.update(kw)
+        return c
+
+    far, back = base["child"].copy(), base["child"].copy()
+    far[0, 0, 0, 0] = 10 ** 6
+    back[-1, 1, 1, 1] = -(10 ** 6)
+    cases = {
+        "child link out of range": [variant(child=far), variant(child=back)],
+        "data_dim": [variant(data_dim=np.int64(10 ** 6)), variant(data_dim=np.int64(-1))],
+        "child must be": [variant(child=base["child"][:, :, :, :1]), variant(child=np.zeros((0, 2, 2, 2), np.int32))],
+        "not aligned": [variant(parent_depth=base["parent_depth"][:3])],
+        "data shape": [variant(data=base["data"][..., :5])],
+        "invradius3": [variant(invradius3=np.zeros(1, np.float32))],
+        "offset": [variant(offset=np.zeros(3, np.float64))],
+        "half precision": [variant(data=base["data"].astype(np.float32))],
+    }
+    for msg, variants in cases.items():
+        for i, arrays in enumerate(variants):
+            dst = tmp_path / "z.npz"
+            np.savez(dst, **arrays)
+            rc, err = _load_rc(mnv, dst)
+            assert rc == 1 and msg in err, (msg, i, rc, err)
