@@ -119,14 +119,17 @@ __device__ __forceinline__ Leaf march_step(const uint32_t *__restrict__ cells, c
     ms.pqz = qz;
     int lvl = min(__clz((int) diff) - 9, ms.pdepth - 1);
     uint32_t node = lvl > 0 ? (uint32_t) s_path[lvl * path_stride] : 0u;
+    // level-lvl child bit of each axis at bit 31; three funnel shifts append them to node: node * 8 + child
+    // (same slot arithmetic as render_pixel, mnv_render.cu)
     uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
     Leaf lf;
+    uint32_t slot;
     for (;;) {
         if (VISIT) {
             if (visited[node] == 0) visited[node] = 1;
         }
-        lf.cidx = ((sx >> 31) << 2) | ((sy >> 31) << 1) | (sz >> 31);
-        lf.cw = __ldg(cells + (node * 8u + lf.cidx));
+        slot = __funnelshift_l(sz, __funnelshift_l(sy, __funnelshift_l(sx, node, 1), 1), 1);
+        lf.cw = __ldg(cells + slot);
         if ((int32_t) lf.cw < 0 || lvl >= max_level) break;
         node = lf.cw;
         ++lvl;
@@ -136,6 +139,7 @@ __device__ __forceinline__ Leaf march_step(const uint32_t *__restrict__ cells, c
         s_path[lvl * path_stride] = (int32_t) node;
     }
     lf.node = node;
+    lf.cidx = slot & 7u;
     lf.depth = lvl + 1;
     ms.pdepth = lf.depth;
     const float cube = __uint_as_float((uint32_t) (127 + lf.depth) << 23);

@@ -35,6 +35,15 @@ namespace {
 #ifndef MNV_TILE_H
 #define MNV_TILE_H 8   // CTA tile = 16 x MNV_TILE_H pixels (8 -> 4 warps, 16 -> 8 warps)
 #endif
+#ifndef MNV_FUNNEL_SLOT
+#define MNV_FUNNEL_SLOT 1  // child slot by bit merge + funnel shift (0: shift / mask / or per axis)
+#endif
+#ifndef MNV_UNROLL2
+#define MNV_UNROLL2 1  // two steps per loop trip: the previous-cell registers rotate instead of being copied
+#endif
+#ifndef MNV_UNROLL_TRACK
+#define MNV_UNROLL_TRACK 0  // also unroll the candidate-tracking variants
+#endif
 #ifndef MNV_SMEM_STATE
 #define MNV_SMEM_STATE 1  // park SH basis + shaded-only ray state in shared memory
 #endif
@@ -236,6 +245,10 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         const float clamp_hi = f_from_bits(0x3F7FFFEFu);  // 1.f - 1e-6f
         const uint32_t *__restrict__ cells = p.tree.cell;
 
+        // two steps per loop trip (the previous-cell registers rotate instead of being copied); the tracking
+        // variants are register-bound and keep one
+        constexpr int kUnroll = MNV_UNROLL2 && (MNV_UNROLL_TRACK || !TRACK) ? 2 : 1;
+#pragma unroll kUnroll
         while (t < tmax) {
             // pos = cen + t*dir (FFMA), clamp to [0, 1-1e-6] (rt_core.cuh:221-223,125-127);
             // .SAT gives the clamp to [0,1] for free, min() finishes it.
@@ -254,15 +267,17 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             // number of leading (from bit 22) bits shared with the previous cell
             int lvl = min(__clz((int) diff) - 9, pdepth - 1);
             uint32_t node = lvl > 0 ? (uint32_t) s_path[lvl * kThreads] : 0u;
-            // level-lvl child bit of each axis moved to bit 31
+#if MNV_FUNNEL_SLOT
+            // level-lvl child bit of each axis moved to bit 31; three funnel shifts append the x, y, z bits to
+            // node: slot = node * 8 + child in 3 ALU instructions per level instead of 6
             uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
-            uint32_t cw, cidx;
+            uint32_t cw, slot;
             for (;;) {
                 if (VISIT) {
                     if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
                 }
-                cidx = ((sx >> 31) << 2) | ((sy >> 31) << 1) | (sz >> 31);
-                cw = __ldg(cells + (node * 8u + cidx));
+                slot = __funnelshift_l(sz, __funnelshift_l(sy, __funnelshift_l(sx, node, 1), 1), 1);
+                cw = __ldg(cells + slot);
                 if ((int32_t) cw < 0 || lvl >= p.max_level) break;
                 node = cw;
                 ++lvl;
@@ -271,13 +286,32 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 sz <<= 1;
                 s_path[lvl * kThreads] = (int32_t) node;
             }
+#else
+            // level-lvl child bit of each axis moved to bit 31
+            uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
+            uint32_t cw, slot;
+            for (;;) {
+                if (VISIT) {
+                    if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
+                }
+                slot = node * 8u + (((sx >> 31) << 2) | ((sy >> 31) << 1) | (sz >> 31));
+                cw = __ldg(cells + slot);
+                if ((int32_t) cw < 0 || lvl >= p.max_level) break;
+                node = cw;
+                ++lvl;
+                sx <<= 1;
+                sy <<= 1;
+                sz <<= 1;
+                s_path[lvl * kThreads] = (int32_t) node;
+            }
+#endif
             const int depth = lvl + 1;
             pdepth = depth;
             const float sigma = __half2float(__ushort_as_half((unsigned short) (cw & 0xffffu)));
             const bool shaded = (int32_t) cw < 0 && sigma > opt.sigma_thresh;
-            const uint4 *rec = p.tree.payload + (size_t) (node * 8u + cidx) * (REC_W / 4);
+            const uint4 *rec = p.tree.payload + (size_t) slot * (REC_W / 4);
             if (LOGV) {
-                const long long packed = (long long) (node * 8u + cidx);
+                const long long packed = (long long) slot;
                 vhash = (vhash ^ (unsigned long long) packed) * 0x100000001b3ULL;
                 if (p.tg.visit_log && nvis < p.tg.log_cap)
                     p.tg.visit_log[(size_t) idx * p.tg.log_cap + nvis] = (int32_t) packed;
@@ -314,13 +348,13 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 const float weight = __fmul_rn(T, __fadd_rn(1.f, -att));
                 if (TRACK) {
                     if (weight > RS(kRsMaxW) && depth < opt.max_depth) {
-                        RSI(kRsSplitId) = (int32_t) (node * 8u + cidx);
+                        RSI(kRsSplitId) = (int32_t) slot;
                         RSI(kRsSplitPrio) = depth;
                         RS(kRsMaxW) = weight;
                         flags |= 1u;
                     }
                     if (weight > RS(kRsMaxSW) && scount < opt.max_sample_count) {
-                        RSI(kRsSampId) = (int32_t) (node * 8u + cidx);
+                        RSI(kRsSampId) = (int32_t) slot;
                         RSI(kRsSampPrio) = scount;
                         RS(kRsMaxSW) = weight;
                         flags |= 2u;
@@ -373,11 +407,11 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 RS(kRsOut2) = out2;
             } else if (TRACK) {
                 if (!(flags & 1u) && depth < opt.max_depth) {
-                    RSI(kRsSplitId) = (int32_t) (node * 8u + cidx);
+                    RSI(kRsSplitId) = (int32_t) slot;
                     RSI(kRsSplitPrio) = depth;
                 }
                 if (!(flags & 2u) && scount < opt.max_sample_count) {
-                    RSI(kRsSampId) = (int32_t) (node * 8u + cidx);
+                    RSI(kRsSampId) = (int32_t) slot;
                     RSI(kRsSampPrio) = scount;
                 }
             }
