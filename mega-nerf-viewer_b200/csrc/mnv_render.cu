@@ -44,6 +44,9 @@ namespace {
 #ifndef MNV_UNROLL_TRACK
 #define MNV_UNROLL_TRACK 0  // also unroll the candidate-tracking variants
 #endif
+#ifndef MNV_TRACK_REGS
+#define MNV_TRACK_REGS 0  // candidate trackers in registers instead of shared memory (round-2 experiment)
+#endif
 #ifndef MNV_SMEM_STATE
 #define MNV_SMEM_STATE 1  // park SH basis + shaded-only ray state in shared memory
 #endif
@@ -141,6 +144,17 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
     RS(kRsOut1) = 0.f;
     RS(kRsOut2) = 0.f;
     float out3 = 0.f;
+    // candidate trackers: shared memory like the rest of the shaded-only state, or (MNV_TRACK_REGS) plain registers —
+    // the compiler keeps register copies of them anyway and then pays the stores on top
+#if MNV_TRACK_REGS
+    float trk_f[2];
+    int32_t trk_i[4];
+#define TS(k) trk_f[(k) - kRsMaxW]
+#define TSI(k) trk_i[(k) - kRsSplitId]
+#else
+#define TS(k) RS(k)
+#define TSI(k) RSI(k)
+#endif
 
     // ---- ray generation: screen2worlddir, renderer_kernel.cu:30-38 ----------
     const float *m = p.cam.c2w;
@@ -168,12 +182,12 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 
     // ---- render_voxels_trace_ray, rt_core.cuh:162-332 ----------------------
     if (TRACK) {
-        RSI(kRsSplitPrio) = opt.max_depth + 1;  // priorities stay integers during the march, converted once per ray
-        RSI(kRsSampPrio) = opt.max_sample_count + 1;
-        RSI(kRsSplitId) = -1;  // packed leaf id node*8 + child
-        RSI(kRsSampId) = -1;
-        RS(kRsMaxW) = -1.f;
-        RS(kRsMaxSW) = -1.f;
+        TSI(kRsSplitPrio) = opt.max_depth + 1;  // priorities stay integers during the march, converted once per ray
+        TSI(kRsSampPrio) = opt.max_sample_count + 1;
+        TSI(kRsSplitId) = -1;  // packed leaf id node*8 + child
+        TSI(kRsSampId) = -1;
+        TS(kRsMaxW) = -1.f;
+        TS(kRsMaxSW) = -1.f;
     }
     unsigned long long vhash = 0xcbf29ce484222325ULL;
     int nvis = 0, nshaded = 0;
@@ -347,16 +361,16 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                         ref_expf(__fmul_rn(__fmul_rn(RS(kRsDeltaScale), -delta_t), sigma));
                 const float weight = __fmul_rn(T, __fadd_rn(1.f, -att));
                 if (TRACK) {
-                    if (weight > RS(kRsMaxW) && depth < opt.max_depth) {
-                        RSI(kRsSplitId) = (int32_t) slot;
-                        RSI(kRsSplitPrio) = depth;
-                        RS(kRsMaxW) = weight;
+                    if (weight > TS(kRsMaxW) && depth < opt.max_depth) {
+                        TSI(kRsSplitId) = (int32_t) slot;
+                        TSI(kRsSplitPrio) = depth;
+                        TS(kRsMaxW) = weight;
                         flags |= 1u;
                     }
-                    if (weight > RS(kRsMaxSW) && scount < opt.max_sample_count) {
-                        RSI(kRsSampId) = (int32_t) slot;
-                        RSI(kRsSampPrio) = scount;
-                        RS(kRsMaxSW) = weight;
+                    if (weight > TS(kRsMaxSW) && scount < opt.max_sample_count) {
+                        TSI(kRsSampId) = (int32_t) slot;
+                        TSI(kRsSampPrio) = scount;
+                        TS(kRsMaxSW) = weight;
                         flags |= 2u;
                     }
                 }
@@ -407,12 +421,12 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 RS(kRsOut2) = out2;
             } else if (TRACK) {
                 if (!(flags & 1u) && depth < opt.max_depth) {
-                    RSI(kRsSplitId) = (int32_t) slot;
-                    RSI(kRsSplitPrio) = depth;
+                    TSI(kRsSplitId) = (int32_t) slot;
+                    TSI(kRsSplitPrio) = depth;
                 }
                 if (!(flags & 2u) && scount < opt.max_sample_count) {
-                    RSI(kRsSampId) = (int32_t) slot;
-                    RSI(kRsSampPrio) = scount;
+                    TSI(kRsSampId) = (int32_t) slot;
+                    TSI(kRsSampPrio) = scount;
                 }
             }
             t = __fadd_rn(t, delta_t);
@@ -461,18 +475,20 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 
     if (TRACK) {
         // (priority, chunk, child) as floats, like the reference's trackers
-        const int32_t sid = RSI(kRsSplitId), pid = RSI(kRsSampId);
+        const int32_t sid = TSI(kRsSplitId), pid = TSI(kRsSampId);
         float *ts = p.tg.to_split + (size_t) idx * 3;
-        ts[0] = (float) RSI(kRsSplitPrio);
+        ts[0] = (float) TSI(kRsSplitPrio);
         ts[1] = sid < 0 ? -1.f : (float) (sid >> 3);
         ts[2] = sid < 0 ? -1.f : (float) (sid & 7);
         float *tp = p.tg.to_sample + (size_t) idx * 3;
-        tp[0] = (float) RSI(kRsSampPrio);
+        tp[0] = (float) TSI(kRsSampPrio);
         tp[1] = pid < 0 ? -1.f : (float) (pid >> 3);
         tp[2] = pid < 0 ? -1.f : (float) (pid & 7);
     }
 #undef RS
 #undef RSI
+#undef TS
+#undef TSI
     if (LOGV) {
         if (p.tg.visit_hash) p.tg.visit_hash[idx] = vhash;
         if (p.tg.visit_count) p.tg.visit_count[idx] = nvis;
