@@ -44,6 +44,9 @@ namespace {
 #ifndef MNV_UNROLL_TRACK
 #define MNV_UNROLL_TRACK 0  // also unroll the candidate-tracking variants
 #endif
+#ifndef MNV_LAZY_EMPTY
+#define MNV_LAZY_EMPTY 0  // candidates from empty leaves kept in registers and committed once per ray (round-2 experiment)
+#endif
 #ifndef MNV_TRACK_REGS
 #define MNV_TRACK_REGS 0  // candidate trackers in registers instead of shared memory (round-2 experiment)
 #endif
@@ -253,6 +256,12 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         // bit 0 / 1: a shaded leaf already set the split / re-sample candidate
         // (max_weight / max_sample_weight != -1 in rt_core.cuh:308-321); bit 2: stopped early
         uint32_t flags = 0;
+#if MNV_LAZY_EMPTY
+        // last empty leaf that qualifies as split / re-sample candidate, whatever the flags say: read only if no
+        // shaded leaf ever set the candidate (rt_core.cuh:308-321 updates them while max_weight == -1)
+        uint32_t e_split = 0xffffffffu, e_samp = 0xffffffffu;
+        int e_depth = 0;
+#endif
         // raw bits of (floor(pos * 2^23) + 2^23) as float: 0x4B000000 | q, q = 23-bit cell coords
         uint32_t pqx = 0x4B000000u, pqy = 0x4B000000u, pqz = 0x4B000000u;
         int pdepth = 1;  // previous leaf depth: path valid for levels < pdepth
@@ -420,6 +429,13 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 RS(kRsOut1) = out1;
                 RS(kRsOut2) = out2;
             } else if (TRACK) {
+#if MNV_LAZY_EMPTY
+                if (depth < opt.max_depth) {
+                    e_split = slot;
+                    e_depth = depth;
+                }
+                if (scount < opt.max_sample_count) e_samp = slot;
+#else
                 if (!(flags & 1u) && depth < opt.max_depth) {
                     TSI(kRsSplitId) = (int32_t) slot;
                     TSI(kRsSplitPrio) = depth;
@@ -428,9 +444,22 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                     TSI(kRsSampId) = (int32_t) slot;
                     TSI(kRsSampPrio) = scount;
                 }
+#endif
             }
             t = __fadd_rn(t, delta_t);
         }
+#if MNV_LAZY_EMPTY
+        if (TRACK) {
+            if (!(flags & 1u) && e_split != 0xffffffffu) {
+                TSI(kRsSplitId) = (int32_t) e_split;
+                TSI(kRsSplitPrio) = e_depth;
+            }
+            if (!(flags & 2u) && e_samp != 0xffffffffu) {
+                TSI(kRsSampId) = (int32_t) e_samp;
+                TSI(kRsSampPrio) = (int) ((__ldg(cells + e_samp) >> 16) & 0x7fffu);
+            }
+        }
+#endif
         if (!(flags & 4u)) {
             if (opt.render_depth) {
                 const float dv = fminf(__fmul_rn(RS(kRsOut0), 0.3f), 1.0f);
