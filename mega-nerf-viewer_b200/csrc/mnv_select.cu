@@ -230,13 +230,9 @@ int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int
                 thrust::copy_if(pol, thrust::make_transform_iterator(zb, SplitRank()),
                                 thrust::make_transform_iterator(zb + uniq, SplitRank()), cnt, k, CountAtLeast2()) - k;
         const int n = (int) std::min<long long>(kept, max_n);
-        if (kept > max_n && kept > 4 * (long long) max_n) {
-            // only the first max_n ranks are needed: a full sort of ~10^5..10^6 candidates for 4096 of them
-            // is wasted work, but selection algorithms need several passes too; radix sort stays the simplest
-            thrust::sort(pol, k, k + kept);
-        } else {
-            thrust::sort(pol, k, k + kept);
-        }
+        // only the first max_n ranks are needed; a full radix sort of the ~10^5..10^6 candidates is still cheaper
+        // than the several passes a selection algorithm takes
+        thrust::sort(pol, k, k + kept);
         if (n > 0) write_nodes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, 1, nodes_dev);
         if (n_selected) *n_selected = n;
         if (n_candidates) *n_candidates = (int) kept;
