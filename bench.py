@@ -407,30 +407,40 @@ def main():
     clocks = sampler.stop(t_start, t_end) if sampler else None
     ms_nt = timed(lambda i: launch(i, False), max(args.steps // 4, 3), 3)
 
-    # e2e: the host-buffer C-ABI call, wall clock around K synchronous frames
-    def e2e_frame(i):
-        cam = cams[i % N_POSES]
-        if world == 1:
-            dt.render_frame_host(cam, opt, host)
-        else:
-            dt.render_frame_host(cam, opt, host, bands=(BAND_ROWS, world, rank))
+    # e2e: the host-buffer C-ABI call, wall clock around K synchronous frames.  Like `value` (and like the
+    # reference arm, which fills and writes both candidate trackers every frame as cuda_renderer.cpp:97-98,141
+    # does) the frame is marched WITH candidate tracking (opt.use_splitting routes the tree-owned trackers into
+    # the launch); the tracker-less call is timed next to it as e2e_no_trackers.
+    opt_track = mnv.default_options(use_splitting=True, **opt_kw)
 
-    for i in range(max(args.warmup, 3)):
-        e2e_frame(i)
-    barrier()
-    e2e_ms = []
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        e2e_frame(i)
-        e2e_ms.append((time.perf_counter() - t0) * 1e3)
-    barrier()
-    e2e_ms = np.array(e2e_ms)
-    if dist is not None:
-        t = torch.tensor(e2e_ms, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = t.cpu().numpy()
+    def e2e_run(o):
+        def frame(i):
+            cam = cams[i % N_POSES]
+            if world == 1:
+                dt.render_frame_host(cam, o, host)
+            else:
+                dt.render_frame_host(cam, o, host, bands=(BAND_ROWS, world, rank))
+
+        for i in range(max(args.warmup, 3)):
+            frame(i)
+        barrier()
+        out_ms = []
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            frame(i)
+            out_ms.append((time.perf_counter() - t0) * 1e3)
+        barrier()
+        out_ms = np.array(out_ms)
+        if dist is not None:
+            t = torch.tensor(out_ms, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out_ms = t.cpu().numpy()
+        return out_ms
+
+    e2e_ms = e2e_run(opt_track)
+    e2e_nt_ms = e2e_run(opt)
 
     if rank != 0:
         dist.destroy_process_group()
@@ -457,7 +467,10 @@ def main():
         "e2e": {"value": P / (float(e2e_ms.mean()) * 1e-3) / 1e6, "unit": "Mrays/s",
                 "ms_per_step": float(e2e_ms.mean()),
                 "h2d_bytes_per_step": 72 + 104,  # mnv_camera + mnv_render_options (kernel params)
-                "d2h_bytes_per_step": P * 4 // world, "api": "mnv_render_frame_host (C-ABI)"},
+                "d2h_bytes_per_step": P * 4 // world,
+                "api": "mnv_render_frame_host (C-ABI), candidate tracking on (use_splitting) like the reference arm"},
+        "e2e_no_trackers": {"value": P / (float(e2e_nt_ms.mean()) * 1e-3) / 1e6, "unit": "Mrays/s",
+                            "ms_per_step": float(e2e_nt_ms.mean())},
         "gpu_launches": args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,

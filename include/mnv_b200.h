@@ -329,6 +329,25 @@ int mnv_select_split_candidates(const float *to_split_dev, int64_t n_rays, int m
 int mnv_select_sample_candidates(const float *to_sample_dev, int64_t n_rays, int max_n,
                                  int32_t *nodes_dev, int *n_selected, int *n_candidates, void *stream);
 
+/* Multi-GPU refinement: instead of exchanging the raw [P][3] float tracker rows, each GPU
+ * reduces its rows to vote records — u32 x 3 = (leaf id = chunk*8+child, priority, votes), unordered — which
+ * are all-gathered and merged.  mnv_vote_reduce writes at most cap_records records into records_dev and
+ * returns their number in *n_records (host); MNV_ERR_FULL if they do not fit (nothing is lost: *n_records
+ * is still the true count).  mnv_select_candidates_from_votes is the selection of
+ * mnv_select_split_candidates (kind 0) / mnv_select_sample_candidates (kind 1) over the union of optional
+ * local tracker rows and n_records gathered records (records with votes == 0 are padding). */
+int mnv_vote_reduce(const float *tracker_dev, int64_t n_rays, uint32_t *records_dev, int64_t cap_records,
+                    int64_t *n_records, void *stream);
+int mnv_select_candidates_from_votes(int kind, const float *tracker_dev, int64_t n_rays,
+                                     const uint32_t *records_dev, int64_t n_records, int max_n,
+                                     int32_t *nodes_dev, int *n_selected, int *n_candidates, void *stream);
+
+/* The chunk column of the trackers: the reference's float VALUE while that is exact (chunk < 2^24, the
+ * reference's own rows bit for bit), the id's raw integer BITS above (the reference's float rows lose odd
+ * node ids beyond 16.7 M nodes, rt_core.cuh:238-240 with src/opts.cpp:24).  Host helpers for consumers. */
+float mnv_tracker_encode_chunk(int32_t chunk);
+int32_t mnv_tracker_decode_chunk(float column_value);
+
 /* Device pointers of the tree-owned candidate buffers filled by the host frame
  * calls when opt->use_splitting is set: f32 [P][3] each (valid until the next
  * frame call with a different size). */

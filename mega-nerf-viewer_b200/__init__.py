@@ -165,6 +165,12 @@ def lib() -> C.CDLL:
     L.mnv_query_submodules.argtypes = [vp, vp, vp, i32, i64, vp, i32, vp]
     L.mnv_select_split_candidates.argtypes = [vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
     L.mnv_select_sample_candidates.argtypes = [vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
+    L.mnv_vote_reduce.argtypes = [vp, i64, vp, i64, C.POINTER(i64), vp]
+    L.mnv_select_candidates_from_votes.argtypes = [i32, vp, i64, vp, i64, i32, vp, C.POINTER(i32), C.POINTER(i32), vp]
+    L.mnv_tracker_encode_chunk.argtypes = [i32]
+    L.mnv_tracker_encode_chunk.restype = C.c_float
+    L.mnv_tracker_decode_chunk.argtypes = [C.c_float]
+    L.mnv_tracker_decode_chunk.restype = i32
     L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
@@ -565,6 +571,36 @@ def select_candidates(tracker, max_n: int, kind: str = "split", stream=None):
     fn = lib().mnv_select_split_candidates if kind == "split" else lib().mnv_select_sample_candidates
     _check(fn(_dptr(tracker), tracker.shape[0], max_n, _dptr(nodes), C.byref(n), C.byref(nc), _stream_ptr(stream)))
     return nodes[: n.value], nc.value
+
+
+def vote_reduce(tracker, cap_records: int | None = None, stream=None):
+    """tracker: CUDA f32 [P, 3] -> vote records u32 [n, 3] = (leaf id, priority, votes) on the device (unordered)."""
+    torch = _torch()
+    cap = int(cap_records or tracker.shape[0])
+    rec = torch.empty((cap, 3), dtype=torch.int32, device=tracker.device)
+    n = C.c_int64(0)
+    _check(lib().mnv_vote_reduce(_dptr(tracker), tracker.shape[0], _dptr(rec), cap, C.byref(n), _stream_ptr(stream)))
+    return rec[: n.value]
+
+
+def select_from_votes(records, max_n: int, kind: str = "split", tracker=None, stream=None):
+    """Selection over gathered vote records (i32/u32 [n, 3], votes == 0 rows are padding) and optional local rows."""
+    torch = _torch()
+    nodes = torch.empty((max_n, 2), dtype=torch.int32, device=records.device)
+    n, nc = C.c_int(0), C.c_int(0)
+    _check(lib().mnv_select_candidates_from_votes(
+        0 if kind == "split" else 1, _dptr(tracker) if tracker is not None else None,
+        tracker.shape[0] if tracker is not None else 0, _dptr(records), records.shape[0], max_n, _dptr(nodes),
+        C.byref(n), C.byref(nc), _stream_ptr(stream)))
+    return nodes[: n.value], nc.value
+
+
+def decode_tracker_chunks(col: np.ndarray) -> np.ndarray:
+    """Chunk column of a tracker (f32) -> node ids (i64; -1 = none), see mnv_tracker_decode_chunk."""
+    col = np.ascontiguousarray(col, np.float32)
+    bits = col.view(np.int32).astype(np.int64)
+    big = (bits >= (1 << 24)) & (bits < (1 << 28))
+    return np.where(big, bits, np.where(col >= 0, col, -1).astype(np.int64))
 
 
 class MlpModel:

@@ -1,4 +1,5 @@
 // extern "C" surface of libmnv_b200.so (include/mnv_b200.h).
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -289,6 +290,12 @@ int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *d, int64_t max_capacity
         delete h;
         return cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__);
     }
+    {
+        // anchor grid level: 7 (2 M entries, 16 MiB) unless the tree is shallower; MNV_ANCHOR_LEVEL=0..8 overrides
+        int a = 7;
+        if (const char *env = std::getenv("MNV_ANCHOR_LEVEL")) a = std::atoi(env);
+        t.anchor_level = std::max(0, std::min(std::min(a, 8), std::max(t.max_leaf_depth, 1)));
+    }
     rc = build_device_tree(t, *d);
     if (rc != MNV_OK) {
         mnv_tree_destroy(h);
@@ -314,6 +321,10 @@ int mnv_tree_destroy(mnv_tree *h) {
     cudaFree(t.sample_dev);
     cudaFree(t.stats_dev);
     cudaFree(t.partial_table_dev);
+    cudaFree(t.anchor);
+    cudaFree(t.max_depth_dev);
+    if (t.max_depth_host) cudaFreeHost(t.max_depth_host);
+    if (t.depth_event) cudaEventDestroy(t.depth_event);
     if (t.stream) cudaStreamDestroy(t.stream);
     delete h;
     return MNV_OK;
@@ -857,6 +868,25 @@ int mnv_select_sample_candidates(const float *to_sample_dev, int64_t n_rays, int
     return select_sample_candidates(to_sample_dev, n_rays, max_n, nodes_dev, n_selected, n_candidates,
                                     static_cast<cudaStream_t>(stream));
 }
+
+int mnv_vote_reduce(const float *tracker_dev, int64_t n_rays, uint32_t *records_dev, int64_t cap_records,
+                    int64_t *n_records, void *stream) {
+    if (!tracker_dev || !records_dev || n_rays <= 0 || cap_records <= 0) return MNV_ERR_INVALID;
+    return vote_reduce(tracker_dev, n_rays, records_dev, cap_records, n_records, static_cast<cudaStream_t>(stream));
+}
+
+int mnv_select_candidates_from_votes(int kind, const float *tracker_dev, int64_t n_rays,
+                                     const uint32_t *records_dev, int64_t n_records, int max_n,
+                                     int32_t *nodes_dev, int *n_selected, int *n_candidates, void *stream) {
+    if ((kind != 0 && kind != 1) || !nodes_dev || max_n <= 0 || n_rays < 0 || n_records < 0 ||
+        (n_rays > 0 && !tracker_dev) || (n_records > 0 && !records_dev))
+        return MNV_ERR_INVALID;
+    return select_candidates(kind, n_rays > 0 ? tracker_dev : nullptr, n_rays, n_records > 0 ? records_dev : nullptr,
+                             n_records, max_n, nodes_dev, n_selected, n_candidates, static_cast<cudaStream_t>(stream));
+}
+
+float mnv_tracker_encode_chunk(int32_t chunk) { return tracker_encode_chunk(chunk); }
+int32_t mnv_tracker_decode_chunk(float v) { return tracker_decode_chunk(v); }
 
 int mnv_tree_trackers(mnv_tree *h, float **to_split_dev, float **to_sample_dev) {
     if (!h) return MNV_ERR_INVALID;

@@ -244,11 +244,11 @@ __global__ void __launch_bounds__(kGThreads, 8) guided_samples_kernel(const Guid
     if (TRACK) {
         float *ts = p.to_split + (size_t) idx * 3;
         ts[0] = split_prio;
-        ts[1] = split_id < 0 ? -1.f : (float) (split_id >> 3);
+        ts[1] = split_id < 0 ? -1.f : tracker_encode_chunk(split_id >> 3);
         ts[2] = split_id < 0 ? -1.f : (float) (split_id & 7);
         float *tp = p.to_sample + (size_t) idx * 3;
         tp[0] = samp_prio;
-        tp[1] = samp_id < 0 ? -1.f : (float) (samp_id >> 3);
+        tp[1] = samp_id < 0 ? -1.f : tracker_encode_chunk(samp_id >> 3);
         tp[2] = samp_id < 0 ? -1.f : (float) (samp_id & 7);
     }
 }

@@ -59,7 +59,20 @@ struct DeviceTree {
     float offset[3] = {0, 0, 0};
     int device = 0;
     int pending_children = 0;  // nodes linked by add_children, not yet committed
-    int max_leaf_depth = 1;  // deepest leaf (reference counting: root's children are depth 1)
+    int max_leaf_depth = 1;  // deepest leaf (reference counting: root's children are depth 1); an upper bound
+                             // while a refinement step's exact depth is still in flight (depth_pending)
+    int *max_depth_dev = nullptr;   // exact deepest leaf, atomicMax'ed by add_children_kernel
+    int *max_depth_host = nullptr;  // pinned copy, valid once depth_event has completed
+    cudaEvent_t depth_event = nullptr;
+    bool depth_pending = false;
+    // Anchor grid (mnv_tree.cu): a dense 2^A x 2^A x 2^A table over the unit cube.  Entry (ix, iy, iz) tells the
+    // march where the point's descent stands at level A: either the leaf itself when the tree ends at depth <= A
+    // there (x = its cell word, y = depth-1 << 28 | slot) or the level-A node to continue from (x = node,
+    // y = A << 28).  One 8-byte load replaces the A top levels of query_single_from_root (rt_core.cuh:117-159).
+    // Rebuilt lazily (anchor_dirty) after any kernel that rewrites the cell plane.
+    uint2 *anchor = nullptr;
+    int anchor_level = 0;  // A (0: disabled)
+    bool anchor_dirty = true;
     // scratch for mnv_render_frame_host
     int32_t *count_dev = nullptr;  // [P] per-ray sample counts (guided sampling)
     int64_t count_cap = 0;
@@ -81,6 +94,35 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 __host__ __device__ inline uint32_t make_leaf_cell(uint16_t sigma_bits, int sample_count) {
     const uint32_t sc = (uint32_t) (sample_count < 0 ? 0 : (sample_count > 32767 ? 32767 : sample_count));
     return kLeafBit | (sc << 16) | sigma_bits;
+}
+
+// ---- candidate trackers -------------------------------------------------------------------
+// The reference's trackers are float rows (priority, chunk, child) (rt_core.cuh:238-252), and fp32 holds
+// integers exactly only below 2^24 — while its own default capacity is 2*10^7 nodes (src/opts.cpp:24;
+// SURVEY.md quirk 2): above 16.7 M nodes odd node ids silently round to a neighbour.  The column keeps the
+// reference's encoding wherever that is exact (chunk < 2^24: the float VALUE, bit-identical to the
+// reference's rows) and carries larger ids as their raw integer BITS.  The two ranges cannot collide:
+// ids in [2^24, 2^28) are the bit patterns 0x01000000..0x0FFFFFFF — positive floats below 1e-29 — whereas
+// every float-encoded id >= 1 has bits >= 0x3F800000, 0 is 0 and "none" is -1.f (sign bit set).
+__host__ __device__ inline float tracker_encode_chunk(int32_t chunk) {
+    if (chunk < (1 << 24)) return (float) chunk;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(chunk);
+#else
+    union { int32_t i; float f; } u;
+    u.i = chunk;
+    return u.f;
+#endif
+}
+__host__ __device__ inline int32_t tracker_decode_chunk(float v) {
+#ifdef __CUDA_ARCH__
+    const int32_t bits = __float_as_int(v);
+#else
+    union { float f; int32_t i; } u;
+    u.f = v;
+    const int32_t bits = u.i;
+#endif
+    return (bits >= (1 << 24) && bits < (1 << 28)) ? bits : (int32_t) v;
 }
 
 // Kernel-side view, passed by value.
@@ -140,9 +182,15 @@ struct RenderTargets {
     float cell_box[6] = {0, 0, 0, 1, 1, 1};
 };
 
-int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
+int launch_render_voxels(DeviceTree &tree, const mnv_camera &cam,
                          const mnv_render_options &opt, const RenderTargets &tg,
                          cudaStream_t stream);
+// (re)builds tree.anchor on `stream` when the cell plane changed since the last build
+int ensure_anchor(DeviceTree &tree, cudaStream_t stream);
+// picks up the exact deepest-leaf level of the last refinement step once its copy has landed
+void refresh_max_leaf_depth(DeviceTree &tree);
+// ancestors of visited nodes become visited (the reference marks every node of the root path per query)
+int launch_propagate_visited(const DeviceTree &tree, int32_t *visited, cudaStream_t stream);
 
 int launch_query_points(const DeviceTree &tree, const float *xyz, int64_t n, int32_t *out,
                         cudaStream_t stream);
@@ -232,11 +280,16 @@ int launch_composite_partials(const DeviceTree &tree, const mnv_camera &cam, con
                               int64_t first_pixel, int n_pixels, uint8_t *rgba_dev, const uint32_t *flags_dev,
                               uint32_t wait_value, cudaStream_t stream, bool guided = false);
 
-// ---- candidate selection / sub-module dispatch (mnv_select.cu) ------------------
+// ---- candidate selection (mnv_vote.cu) / sub-module dispatch (mnv_select.cu) ------------------
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
                             int *n_selected, int *n_candidates, cudaStream_t stream);
 int select_sample_candidates(const float *to_sample_dev, int64_t P, int max_n, int32_t *nodes_dev,
                              int *n_selected, int *n_candidates, cudaStream_t stream);
+// rows: tracker [P][3] (may be null); pairs: vote records (id, priority, count) u32 x 3 (may be null)
+int select_candidates(int kind, const float *rows_dev, int64_t P, const uint32_t *pairs_dev, int64_t n_pairs, int max_n,
+                      int32_t *nodes_dev, int *n_selected, int *n_candidates, cudaStream_t stream);
+int vote_reduce(const float *rows_dev, int64_t P, uint32_t *pairs_out_dev, int64_t cap, int64_t *n_out,
+                cudaStream_t stream);
 int query_submodules(MlpModel *const *subs, int n_subs, const int16_t *cluster_dev, const float *rows_dev,
                      int in_dim, int64_t V, float *out_dev, int out_stride, cudaStream_t stream);
 

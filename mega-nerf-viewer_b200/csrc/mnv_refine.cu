@@ -39,7 +39,7 @@ __device__ __forceinline__ int cluster_of(const ClusterRule &c, float y, float z
 // generate_samples_inner, renderer_kernel.cu:88-168.  `packed` = node*8 + child of the voxel;
 // for a voxel of a node that is being created, `first_parent` is that node's packed parent
 // slot (else -1: read the parent plane).
-__device__ __forceinline__ void generate_samples_inner(
+__device__ __forceinline__ int generate_samples_inner(
         const int32_t *__restrict__ parent, const float *scale, const float *offset,
         const mnv_render_options &opt, float *__restrict__ samples /* [c][rand_dim] */,
         int16_t *__restrict__ cluster /* [c] */, int rand_dim, const ClusterRule &cr, int64_t packed,
@@ -80,6 +80,7 @@ __device__ __forceinline__ void generate_samples_inner(
     }
     for (int s = 0; s < opt.samples_per_corner; ++s)
         cluster[s] = (int16_t) cluster_of(cr, samples[s * rand_dim + 1], samples[s * rand_dim + 2]);
+    return depth + 1;  // depth of the voxel in the reference's counting (root's children: 1)
 }
 
 struct RefineParams {
@@ -92,6 +93,7 @@ struct RefineParams {
     int64_t capacity;
     mnv_render_options opt;
     ClusterRule cr;
+    int *max_depth;  // deepest leaf of the tree (device), raised by add_children
 };
 
 __global__ void add_children_kernel(RefineParams p, const int32_t *__restrict__ parent_nodes, int n,
@@ -111,8 +113,9 @@ __global__ void add_children_kernel(RefineParams p, const int32_t *__restrict__ 
     // a new leaf: sigma 0 / count 0 until mnv_tree_commit_children fills it
     p.cell[abs_node * 8 + child] = make_leaf_cell(0, 0);
     const int c = p.opt.samples_per_corner;
-    generate_samples_inner(p.parent, p.scale, p.offset, p.opt, samples + (size_t) tid * c * rand_dim,
-                           cluster + (size_t) tid * c, rand_dim, p.cr, abs_node * 8 + child, pslot);
+    const int depth = generate_samples_inner(p.parent, p.scale, p.offset, p.opt, samples + (size_t) tid * c * rand_dim,
+                                             cluster + (size_t) tid * c, rand_dim, p.cr, abs_node * 8 + child, pslot);
+    if (child == 0 && p.max_depth) atomicMax(p.max_depth, depth);
 }
 
 __global__ void generate_samples_kernel(RefineParams p, const int32_t *__restrict__ nodes, int m,
@@ -252,6 +255,7 @@ RefineParams make_params(const DeviceTree &t, const mnv_render_options &opt, con
     }
     p.capacity = t.capacity;
     p.opt = opt;
+    p.max_depth = t.max_depth_dev;
     p.cr.grid0 = grid_dim ? grid_dim[0] : 1;
     p.cr.grid1 = grid_dim ? grid_dim[1] : 1;
     p.cr.min1 = min_position ? min_position[1] : 0.f;
@@ -272,6 +276,14 @@ int refine_add_children(DeviceTree &t, const mnv_render_options &opt, const int3
                         const int32_t *grid_dim, const float *min_position, const float *range,
                         cudaStream_t stream) {
     if (n <= 0) return MNV_OK;
+    refresh_max_leaf_depth(t);
+    if (!t.max_depth_dev) {  // first refinement step of this tree
+        MNV_CUDA(cudaMalloc(&t.max_depth_dev, sizeof(int)));
+        MNV_CUDA(cudaMallocHost(&t.max_depth_host, sizeof(int)));
+        MNV_CUDA(cudaEventCreateWithFlags(&t.depth_event, cudaEventDisableTiming));
+        *t.max_depth_host = t.max_leaf_depth;
+        MNV_CUDA(cudaMemcpyAsync(t.max_depth_dev, t.max_depth_host, sizeof(int), cudaMemcpyHostToDevice, stream));
+    }
     if (t.capacity + n > t.max_capacity) {
         set_error("Full: capacity %lld + %d > max %lld", (long long) t.capacity, n, (long long) t.max_capacity);
         return MNV_ERR_FULL;  // cuda_renderer.cpp:228-231
@@ -282,7 +294,15 @@ int refine_add_children(DeviceTree &t, const mnv_render_options &opt, const int3
                                                                   cluster_dev, rand_dim_of(opt), visited_dev);
     MNV_CUDA(cudaGetLastError());
     t.pending_children = n;
-    t.max_leaf_depth = std::min(23, t.max_leaf_depth + 1);  // each split deepens by at most one level
+    t.anchor_dirty = true;
+    // each split deepens the tree by at most one level: the bound holds until the exact value (the kernel's
+    // atomicMax over the new leaves' depths) has reached the host — no synchronisation here
+    t.max_leaf_depth = std::min(23, t.max_leaf_depth + 1);
+    if (t.max_depth_host && t.depth_event) {
+        MNV_CUDA(cudaMemcpyAsync(t.max_depth_host, t.max_depth_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        MNV_CUDA(cudaEventRecord(t.depth_event, stream));
+        t.depth_pending = true;
+    }
     return MNV_OK;
 }
 
@@ -300,6 +320,7 @@ int refine_commit_children(DeviceTree &t, const mnv_render_options &opt, int n, 
     MNV_CUDA(cudaGetLastError());
     t.capacity += n;  // cuda_renderer.cpp:275
     t.pending_children = 0;
+    t.anchor_dirty = true;
     return MNV_OK;
 }
 
@@ -323,12 +344,14 @@ int refine_update_samples(DeviceTree &t, const mnv_render_options &opt, const in
     update_samples_kernel<<<(m + th - 1) / th, th, 0, stream>>>(p, nodes_dev, m, results_dev, result_stride,
                                                                 opt.samples_per_corner);
     MNV_CUDA(cudaGetLastError());
+    t.anchor_dirty = true;
     return MNV_OK;
 }
 
 int refine_prune(DeviceTree &t, const uint8_t *to_delete_dev, const int32_t *index_shifts_dev,
                  int first_shift_index, int64_t num_deleted, cudaStream_t stream) {
     if (num_deleted <= 0) return MNV_OK;
+    t.anchor_dirty = true;
     mnv_render_options dummy{};
     const RefineParams p = make_params(t, dummy, nullptr, nullptr, nullptr);
     const int th = 256;

@@ -35,14 +35,14 @@ namespace {
 #ifndef MNV_TILE_H
 #define MNV_TILE_H 8   // CTA tile = 16 x MNV_TILE_H pixels (8 -> 4 warps, 16 -> 8 warps)
 #endif
-#ifndef MNV_FUNNEL_SLOT
-#define MNV_FUNNEL_SLOT 1  // child slot by bit merge + funnel shift (0: shift / mask / or per axis)
-#endif
 #ifndef MNV_UNROLL2
 #define MNV_UNROLL2 1  // two steps per loop trip: the previous-cell registers rotate instead of being copied
 #endif
 #ifndef MNV_UNROLL_TRACK
 #define MNV_UNROLL_TRACK 0  // also unroll the candidate-tracking variants
+#endif
+#ifndef MNV_UNROLL_ANCHOR
+#define MNV_UNROLL_ANCHOR 1  // loop trips unrolled in the anchor-grid variants
 #endif
 #ifndef MNV_LAZY_EMPTY
 #define MNV_LAZY_EMPTY 0  // candidates from empty leaves kept in registers and committed once per ray (round-2 experiment)
@@ -73,7 +73,15 @@ struct RenderParams {
     int mtiles_x;   // partition tiles per row (multi-GPU partition)
     int tiles_x;    // 16x8-pixel CTA tiles per row
     int max_level;  // deepest level a descent may reach (tree max leaf depth - 1, <= 22)
-    int path_levels;  // rows of the shared-memory node path (= max_level + 1)
+    int path_levels;  // rows of the shared-memory node path (= max_level + 1; 0 with the anchor grid)
+    int split_limit;  // min(opt.max_depth, 23): leaves at depth 23 cannot be split (23-bit cell coordinates)
+    // anchor grid (mnv_internal.cuh): entry index = ((ax * dim + ay) * dim + az) - bias with a? the raw bits of
+    // fma_rd(p?, 2^A, 2^23) — the 0x4B000000 exponents of the three terms fold into one constant
+    const uint2 *anchor;
+    int anchor_level;
+    float anchor_scale;    // 2^A
+    uint32_t anchor_dim;   // 2^A
+    uint32_t anchor_bias;
 };
 
 template <int R>
@@ -121,7 +129,7 @@ __device__ __forceinline__ float sh_channel(const float (&B)[TERMS], const uint3
 // TERMS: 0 = RGBA, else SH basis dimension (1,4,9,16,25).
 // TRACK: produce split / re-sample candidates.  LOGV: visit hash/count/log/stats.
 // VISIT: mark visited nodes (track_visit).
-template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
+template <int TERMS, bool TRACK, bool LOGV, bool VISIT, bool ANCHOR>
 __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x, const int y,
                                              int32_t *__restrict__ s_path,
                                              float *__restrict__ s_basis,
@@ -270,7 +278,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 
         // two steps per loop trip (the previous-cell registers rotate instead of being copied); the tracking
         // variants are register-bound and keep one
-        constexpr int kUnroll = MNV_UNROLL2 && (MNV_UNROLL_TRACK || !TRACK) ? 2 : 1;
+        constexpr int kUnroll = ANCHOR ? MNV_UNROLL_ANCHOR : (MNV_UNROLL2 && (MNV_UNROLL_TRACK || !TRACK) ? 2 : 1);
 #pragma unroll kUnroll
         while (t < tmax) {
             // pos = cen + t*dir (FFMA), clamp to [0, 1-1e-6] (rt_core.cuh:221-223,125-127);
@@ -278,56 +286,74 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             const float px = fminf(__saturatef(__fmaf_rn(t, d0, c0)), clamp_hi);
             const float py = fminf(__saturatef(__fmaf_rn(t, d1, c1)), clamp_hi);
             const float pz = fminf(__saturatef(__fmaf_rn(t, d2, c2)), clamp_hi);
-            // exact integer cell coordinates at level 23: floor(p * 2^23) sits in the
-            // mantissa of fma_rd(p, 2^23, 2^23)
-            const uint32_t qx = __float_as_uint(__fmaf_rd(px, 8388608.f, 8388608.f));
-            const uint32_t qy = __float_as_uint(__fmaf_rd(py, 8388608.f, 8388608.f));
-            const uint32_t qz = __float_as_uint(__fmaf_rd(pz, 8388608.f, 8388608.f));
-            const uint32_t diff = (qx ^ pqx) | (qy ^ pqy) | (qz ^ pqz);  // exponent bits cancel
-            pqx = qx;
-            pqy = qy;
-            pqz = qz;
-            // number of leading (from bit 22) bits shared with the previous cell
-            int lvl = min(__clz((int) diff) - 9, pdepth - 1);
-            uint32_t node = lvl > 0 ? (uint32_t) s_path[lvl * kThreads] : 0u;
-#if MNV_FUNNEL_SLOT
-            // level-lvl child bit of each axis moved to bit 31; three funnel shifts append the x, y, z bits to
-            // node: slot = node * 8 + child in 3 ALU instructions per level instead of 6
-            uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
             uint32_t cw, slot;
-            for (;;) {
-                if (VISIT) {
-                    if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
+            int lvl;
+            if constexpr (ANCHOR) {
+                // One 8-byte load of the anchor grid resolves the top A levels: either the leaf itself (tree ends at
+                // depth <= A here) or the level-A node, from which at most (depth - A) cell words remain.  No per-ray
+                // node path, no previous-cell registers: with 32 rays per warp the old path cache paid the deepest
+                // lane's re-descent (warp-max 3.4-4 rounds per step) on almost every step.
+                const uint32_t ax = __float_as_uint(__fmaf_rd(px, p.anchor_scale, 8388608.f));
+                const uint32_t ay = __float_as_uint(__fmaf_rd(py, p.anchor_scale, 8388608.f));
+                const uint32_t az = __float_as_uint(__fmaf_rd(pz, p.anchor_scale, 8388608.f));
+                const uint2 e = __ldg(p.anchor + ((ax * p.anchor_dim + ay) * p.anchor_dim + az - p.anchor_bias));
+                lvl = (int) (e.y >> 28);
+                cw = e.x;
+                slot = e.y & 0x0fffffffu;
+                if ((int32_t) e.x >= 0) {
+                    // exact integer cell coordinates at level 23: floor(p * 2^23) sits in the mantissa of
+                    // fma_rd(p, 2^23, 2^23); the level-lvl child bit of each axis moves to bit 31
+                    uint32_t node = e.x;
+                    uint32_t sx = __float_as_uint(__fmaf_rd(px, 8388608.f, 8388608.f)) << (9 + lvl);
+                    uint32_t sy = __float_as_uint(__fmaf_rd(py, 8388608.f, 8388608.f)) << (9 + lvl);
+                    uint32_t sz = __float_as_uint(__fmaf_rd(pz, 8388608.f, 8388608.f)) << (9 + lvl);
+                    for (;;) {
+                        slot = __funnelshift_l(sz, __funnelshift_l(sy, __funnelshift_l(sx, node, 1), 1), 1);
+                        cw = __ldg(cells + slot);
+                        if ((int32_t) cw < 0 || lvl >= p.max_level) break;
+                        node = cw;
+                        ++lvl;
+                        sx <<= 1;
+                        sy <<= 1;
+                        sz <<= 1;
+                    }
                 }
-                slot = __funnelshift_l(sz, __funnelshift_l(sy, __funnelshift_l(sx, node, 1), 1), 1);
-                cw = __ldg(cells + slot);
-                if ((int32_t) cw < 0 || lvl >= p.max_level) break;
-                node = cw;
-                ++lvl;
-                sx <<= 1;
-                sy <<= 1;
-                sz <<= 1;
-                s_path[lvl * kThreads] = (int32_t) node;
-            }
-#else
-            // level-lvl child bit of each axis moved to bit 31
-            uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
-            uint32_t cw, slot;
-            for (;;) {
                 if (VISIT) {
-                    if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
+                    // the node holding the leaf; its ancestors are marked by launch_propagate_visited afterwards
+                    // (the reference marks every node of the root path at every query, rt_core.cuh:132-135)
+                    if (p.tg.visited[slot >> 3] == 0) p.tg.visited[slot >> 3] = 1;
                 }
-                slot = node * 8u + (((sx >> 31) << 2) | ((sy >> 31) << 1) | (sz >> 31));
-                cw = __ldg(cells + slot);
-                if ((int32_t) cw < 0 || lvl >= p.max_level) break;
-                node = cw;
-                ++lvl;
-                sx <<= 1;
-                sy <<= 1;
-                sz <<= 1;
-                s_path[lvl * kThreads] = (int32_t) node;
+            } else {
+                // exact integer cell coordinates at level 23: floor(p * 2^23) sits in the
+                // mantissa of fma_rd(p, 2^23, 2^23)
+                const uint32_t qx = __float_as_uint(__fmaf_rd(px, 8388608.f, 8388608.f));
+                const uint32_t qy = __float_as_uint(__fmaf_rd(py, 8388608.f, 8388608.f));
+                const uint32_t qz = __float_as_uint(__fmaf_rd(pz, 8388608.f, 8388608.f));
+                const uint32_t diff = (qx ^ pqx) | (qy ^ pqy) | (qz ^ pqz);  // exponent bits cancel
+                pqx = qx;
+                pqy = qy;
+                pqz = qz;
+                // number of leading (from bit 22) bits shared with the previous cell
+                lvl = min(__clz((int) diff) - 9, pdepth - 1);
+                uint32_t node = lvl > 0 ? (uint32_t) s_path[lvl * kThreads] : 0u;
+                // level-lvl child bit of each axis moved to bit 31; three funnel shifts append the x, y, z bits to
+                // node: slot = node * 8 + child in 3 ALU instructions per level instead of 6
+                uint32_t sx = qx << (9 + lvl), sy = qy << (9 + lvl), sz = qz << (9 + lvl);
+                for (;;) {
+                    if (VISIT) {
+                        if (p.tg.visited[node] == 0) p.tg.visited[node] = 1;
+                    }
+                    slot = __funnelshift_l(sz, __funnelshift_l(sy, __funnelshift_l(sx, node, 1), 1), 1);
+                    cw = __ldg(cells + slot);
+                    if ((int32_t) cw < 0 || lvl >= p.max_level) break;
+                    node = cw;
+                    ++lvl;
+                    sx <<= 1;
+                    sy <<= 1;
+                    sz <<= 1;
+                    s_path[lvl * kThreads] = (int32_t) node;
+                }
             }
-#endif
             const int depth = lvl + 1;
             pdepth = depth;
             const float sigma = __half2float(__ushort_as_half((unsigned short) (cw & 0xffffu)));
@@ -370,7 +396,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                         ref_expf(__fmul_rn(__fmul_rn(RS(kRsDeltaScale), -delta_t), sigma));
                 const float weight = __fmul_rn(T, __fadd_rn(1.f, -att));
                 if (TRACK) {
-                    if (weight > TS(kRsMaxW) && depth < opt.max_depth) {
+                    if (weight > TS(kRsMaxW) && depth < p.split_limit) {
                         TSI(kRsSplitId) = (int32_t) slot;
                         TSI(kRsSplitPrio) = depth;
                         TS(kRsMaxW) = weight;
@@ -430,13 +456,13 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 RS(kRsOut2) = out2;
             } else if (TRACK) {
 #if MNV_LAZY_EMPTY
-                if (depth < opt.max_depth) {
+                if (depth < p.split_limit) {
                     e_split = slot;
                     e_depth = depth;
                 }
                 if (scount < opt.max_sample_count) e_samp = slot;
 #else
-                if (!(flags & 1u) && depth < opt.max_depth) {
+                if (!(flags & 1u) && depth < p.split_limit) {
                     TSI(kRsSplitId) = (int32_t) slot;
                     TSI(kRsSplitPrio) = depth;
                 }
@@ -503,15 +529,15 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         surf2Dwrite(rgba, p.tg.image_surf, x * 4, y, cudaBoundaryModeZero);
 
     if (TRACK) {
-        // (priority, chunk, child) as floats, like the reference's trackers
+        // (priority, chunk, child) as floats, like the reference's trackers (ids >= 2^24: tracker_encode_chunk)
         const int32_t sid = TSI(kRsSplitId), pid = TSI(kRsSampId);
         float *ts = p.tg.to_split + (size_t) idx * 3;
         ts[0] = (float) TSI(kRsSplitPrio);
-        ts[1] = sid < 0 ? -1.f : (float) (sid >> 3);
+        ts[1] = sid < 0 ? -1.f : tracker_encode_chunk(sid >> 3);
         ts[2] = sid < 0 ? -1.f : (float) (sid & 7);
         float *tp = p.tg.to_sample + (size_t) idx * 3;
         tp[0] = (float) TSI(kRsSampPrio);
-        tp[1] = pid < 0 ? -1.f : (float) (pid >> 3);
+        tp[1] = pid < 0 ? -1.f : tracker_encode_chunk(pid >> 3);
         tp[2] = pid < 0 ? -1.f : (float) (pid & 7);
     }
 #undef RS
@@ -542,7 +568,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 // TERMS: 0 = RGBA, else SH basis dimension (1,4,9,16,25).
 // TRACK: produce split / re-sample candidates.  LOGV: visit hash/count/log/stats.
 // VISIT: mark visited nodes (track_visit).
-template <int TERMS, bool TRACK, bool LOGV, bool VISIT>
+template <int TERMS, bool TRACK, bool LOGV, bool VISIT, bool ANCHOR>
 __global__ void __launch_bounds__(kThreads, MNV_MIN_BLOCKS)
 render_voxels_kernel(const RenderParams p) {
     // [path_levels][kThreads] node path | [TERMS][kThreads] SH basis | [words][kThreads] ray state
@@ -557,7 +583,7 @@ render_voxels_kernel(const RenderParams p) {
     const int x = btx * kTileW + (warp & 1) * 8 + (lane & 7);
     const int y = bty * kTileH + (warp >> 1) * 4 + (lane >> 3);
     if (x >= p.cam.width || y >= p.cam.height) return;
-    render_pixel<TERMS, TRACK, LOGV, VISIT>(
+    render_pixel<TERMS, TRACK, LOGV, VISIT, ANCHOR>(
             p, x, y, s_dyn + threadIdx.x,
             reinterpret_cast<float *>(s_dyn + p.path_levels * kThreads) + threadIdx.x,
             reinterpret_cast<float *>(s_dyn + (p.path_levels + TERMS) * kThreads) + threadIdx.x);
@@ -590,11 +616,11 @@ __global__ void query_points_kernel(TreeView tree, const float *__restrict__ xyz
     out[3 * i + 2] = lvl + 1;
 }
 
-template <int TERMS>
+template <int TERMS, bool ANCHOR>
 int dispatch(const RenderParams &p, bool track, bool logv, bool visit, dim3 grid, size_t smem,
              cudaStream_t stream) {
 #define MNV_LAUNCH(T, L, V) \
-    render_voxels_kernel<TERMS, T, L, V><<<grid, kThreads, smem, stream>>>(p)
+    render_voxels_kernel<TERMS, T, L, V, ANCHOR><<<grid, kThreads, smem, stream>>>(p)
     if (logv) {
         if (track) MNV_LAUNCH(true, true, false);
         else MNV_LAUNCH(false, true, false);
@@ -612,7 +638,7 @@ int dispatch(const RenderParams &p, bool track, bool logv, bool visit, dim3 grid
 
 }  // namespace
 
-int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
+int launch_render_voxels(DeviceTree &tree, const mnv_camera &cam,
                          const mnv_render_options &opt, const RenderTargets &tg,
                          cudaStream_t stream) {
     if (cam.width <= 0 || cam.height <= 0) {
@@ -637,6 +663,11 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
         set_error("track_visit needs a visited buffer");
         return MNV_ERR_INVALID;
     }
+    refresh_max_leaf_depth(tree);
+    {
+        const int rc = ensure_anchor(tree, stream);
+        if (rc != MNV_OK) return rc;
+    }
     RenderParams p;
     p.tree = make_view(tree);
     p.cam = cam;
@@ -646,7 +677,14 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
     const int tiles_y = (cam.height + kTileH - 1) / kTileH;
     // a leaf at depth d is found in a node of level d-1; refinement may deepen the tree
     p.max_level = std::min(kMaxLevel, std::max(tree.max_leaf_depth, 1) - 1);
-    p.path_levels = p.max_level + 1;
+    const bool anchored = tree.anchor_level > 0 && tree.anchor != nullptr;
+    p.path_levels = anchored ? 0 : p.max_level + 1;
+    p.split_limit = std::min(opt.max_depth, 23);
+    p.anchor = tree.anchor;
+    p.anchor_level = tree.anchor_level;
+    p.anchor_dim = 1u << tree.anchor_level;
+    p.anchor_scale = (float) p.anchor_dim;
+    p.anchor_bias = (0x4B000000u * p.anchor_dim + 0x4B000000u) * p.anchor_dim + 0x4B000000u;
     if (p.tg.tile_mod > 1) {
         if (p.tg.tile_w < kTileW || p.tg.tile_h < kTileH || p.tg.tile_w % kTileW ||
             p.tg.tile_h % kTileH) {
@@ -673,17 +711,25 @@ int launch_render_voxels(const DeviceTree &tree, const mnv_camera &cam,
     const size_t smem = (size_t) (p.path_levels +
                                   (MNV_SMEM_STATE ? terms + (track ? kRsWordsTrack : kRsWordsBase) : 0)) *
                         kThreads * sizeof(int32_t);
+    int rc;
+#define MNV_TERMS(N) rc = anchored ? dispatch<N, true>(p, track, logv, visit, grid, smem, stream) \
+                                   : dispatch<N, false>(p, track, logv, visit, grid, smem, stream)
     switch (terms) {
-        case 0: return dispatch<0>(p, track, logv, visit, grid, smem, stream);
-        case 1: return dispatch<1>(p, track, logv, visit, grid, smem, stream);
-        case 4: return dispatch<4>(p, track, logv, visit, grid, smem, stream);
-        case 9: return dispatch<9>(p, track, logv, visit, grid, smem, stream);
-        case 16: return dispatch<16>(p, track, logv, visit, grid, smem, stream);
-        case 25: return dispatch<25>(p, track, logv, visit, grid, smem, stream);
+        case 0: MNV_TERMS(0); break;
+        case 1: MNV_TERMS(1); break;
+        case 4: MNV_TERMS(4); break;
+        case 9: MNV_TERMS(9); break;
+        case 16: MNV_TERMS(16); break;
+        case 25: MNV_TERMS(25); break;
         default:
             set_error("unsupported SH basis_dim %d", terms);
             return MNV_ERR_INVALID;
     }
+#undef MNV_TERMS
+    // the reference marks every node of the root path at each query; the anchored march marks the node holding
+    // the leaf and the ancestors follow here (same visited set)
+    if (rc == MNV_OK && visit && anchored) rc = launch_propagate_visited(tree, tg.visited, stream);
+    return rc;
 }
 
 int launch_query_points(const DeviceTree &tree, const float *xyz, int64_t n, int32_t *out,

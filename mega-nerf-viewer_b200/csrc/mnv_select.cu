@@ -1,31 +1,20 @@
 // Device-side replacements for the LibTorch glue around the refinement kernels
-// (SURVEY.md §2d): candidate selection (unique_dim / cat / sort of
-// Impl::expand_voxels, cuda_renderer.cpp:205-226, and Impl::get_more_samples,
-// :281-293) and the per-sub-module dispatch of Impl::query_submodules (:165-203:
-// sort + unique_consecutive + .item() loops + index gather + scatter_).
+// (SURVEY.md §2d): the per-sub-module dispatch of Impl::query_submodules
+// (cuda_renderer.cpp:165-203: sort + unique_consecutive + .item() loops + index gather +
+// scatter_), the random sample source, and Impl::prune_tree's mask / cumsum (:343-381).
+// Candidate selection (unique_dim / sort of expand_voxels / get_more_samples) lives in mnv_vote.cu.
 //
-// Everything stays on the device; each call returns one or two small counts to the
-// host (the reference syncs once per cluster per batch).  Sorting uses Thrust/CUB
-// (library code for a non-hot op); the MLP runs with a row-index indirection so
-// the gather / scatter copies of the reference disappear.
-#include <thrust/copy.h>
-#include <thrust/iterator/transform_iterator.h>
-#include <thrust/iterator/zip_iterator.h>
+// Everything stays on the device; the MLP runs with a row-index indirection so the
+// gather / scatter copies of the reference disappear.
 #include <thrust/device_ptr.h>
 #include <thrust/execution_policy.h>
-#include <thrust/iterator/counting_iterator.h>
-#include <thrust/iterator/constant_iterator.h>
-#include <thrust/reduce.h>
-#include <thrust/remove.h>
-#include <thrust/sequence.h>
-#include <thrust/sort.h>
-#include <thrust/binary_search.h>
-#include <thrust/unique.h>
-#include <thrust/transform.h>
-#include <thrust/scan.h>
 #include <thrust/functional.h>
+#include <thrust/iterator/counting_iterator.h>
+#include <thrust/scan.h>
+#include <thrust/transform.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -33,41 +22,6 @@
 
 namespace mnv {
 namespace {
-
-// tracker rows are (priority, chunk, child) floats (rt_core.cuh:238-252); chunk < 0 = none.
-// id = chunk*8 + child identifies the leaf (and therefore its depth / sample count).
-struct RowToKey {
-    const float *rows;
-    __device__ unsigned long long operator()(long long i) const {
-        const float chunk = rows[3 * i + 1];
-        if (!(chunk >= 0.f)) return ~0ull;
-        const unsigned long long id = (unsigned long long) ((long long) chunk * 8 + (long long) rows[3 * i + 2]);
-        const unsigned long long prio = (unsigned long long) (long long) rows[3 * i + 0];
-        return (prio << 32) | id;  // (priority, id): priority is a function of id
-    }
-};
-struct IsSome {
-    __device__ bool operator()(unsigned long long k) const { return k != ~0ull; }
-};
-struct SplitRank {  // order of unique_dim on rows (-count, depth, chunk, child)
-    __device__ unsigned long long operator()(const thrust::tuple<unsigned long long, int> &t) const {
-        const unsigned long long key = thrust::get<0>(t);
-        const unsigned long long count = (unsigned long long) thrust::get<1>(t);
-        const unsigned long long depth = key >> 32, id = key & 0xffffffffull;
-        return ((0x3ffffffull - count) << 37) | ((depth & 0x3full) << 31) | (id & 0x7fffffffull);
-    }
-};
-struct CountAtLeast2 {
-    __device__ bool operator()(int count) const { return count >= 2; }  // "< -1" on the negated counts, cuda_renderer.cpp:214
-};
-__global__ void write_nodes_kernel(const unsigned long long *ranked, int n, int shift_is_rank,
-                                   int32_t *nodes) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned long long id = shift_is_rank ? (ranked[i] & 0x7fffffffull) : (ranked[i] & 0xffffffffull);
-    nodes[2 * i] = (int32_t) (id >> 3);
-    nodes[2 * i + 1] = (int32_t) (id & 7);
-}
 
 template <typename T>
 __global__ void fill_kernel(T *p, T v, int64_t n) {
@@ -145,11 +99,12 @@ int prune_unvisited(DeviceTree &t, int32_t *visited_dev, int64_t *num_deleted, c
 }
 
 // ---- scratch arena ---------------------------------------------------------------------
-// cudaMalloc / cudaFree per call cost more than the sorts they serve (and synchronise the
-// device): all temporaries of this file, Thrust's internal ones included, are bump-allocated from
-// one per-device arena that grows to the high-water mark after the first frames.
+// cudaMalloc / cudaFree per call cost more than the passes they serve (and synchronise the
+// device): the temporaries of query_submodules are bump-allocated from one per-device arena that
+// grows to the high-water mark after the first frames.
 namespace {
 struct Arena {
+    std::mutex mu;  // one user at a time per device (two host threads may drive one GPU)
     char *base = nullptr;
     size_t cap = 0, off = 0, want = 0;
     std::vector<void *> overflow;
@@ -187,90 +142,17 @@ Arena &arena_for_current_device() {
     cudaGetDevice(&dev);
     return arenas[dev & 15];
 }
-struct ArenaAllocator {
-    typedef char value_type;
-    Arena *a;
-    char *allocate(std::ptrdiff_t n) { return static_cast<char *>(a->take((size_t) n)); }
-    void deallocate(char *, size_t) {}
-};
-struct ArenaScope {  // resets the arena when the call is over (stream synchronised by then)
+struct ArenaScope {  // owns the arena for one call; resets it when the call is over (stream synchronised by then)
     Arena &a;
     cudaStream_t stream;
+    ArenaScope(Arena &arena, cudaStream_t s) : a(arena), stream(s) { a.mu.lock(); }
     ~ArenaScope() {
         cudaStreamSynchronize(stream);
         a.reset();
+        a.mu.unlock();
     }
 };
 }  // namespace
-
-int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
-                            int *n_selected, int *n_candidates, cudaStream_t stream) {
-    Arena &A = arena_for_current_device();
-    ArenaScope scope{A, stream};
-    ArenaAllocator alloc{&A};
-    auto pol = thrust::cuda::par(alloc).on(stream);
-    int rc = MNV_OK;
-    try {
-        auto *keys = static_cast<unsigned long long *>(A.take(P * sizeof(unsigned long long)));
-        thrust::device_ptr<unsigned long long> k(keys);
-        // rows with a candidate -> (priority, id) keys, compacted in one pass
-        const long long valid =
-                thrust::copy_if(pol, thrust::make_transform_iterator(thrust::counting_iterator<long long>(0), RowToKey{to_split_dev}),
-                                thrust::make_transform_iterator(thrust::counting_iterator<long long>(P), RowToKey{to_split_dev}),
-                                k, IsSome()) - k;
-        thrust::sort(pol, k, k + valid);
-        auto *ukeys = static_cast<unsigned long long *>(A.take(std::max<long long>(valid, 1) * sizeof(unsigned long long)));
-        auto *counts = static_cast<int *>(A.take(std::max<long long>(valid, 1) * sizeof(int)));
-        thrust::device_ptr<unsigned long long> uk(ukeys);
-        thrust::device_ptr<int> cnt(counts);
-        const long long uniq = thrust::reduce_by_key(pol, k, k + valid, thrust::constant_iterator<int>(1), uk, cnt).first - uk;
-        auto zb = thrust::make_zip_iterator(thrust::make_tuple(uk, cnt));
-        // rank = (-count, depth, chunk, child) of the rows voted by >= 2 rays; reuse `keys` for the ranks
-        const long long kept =
-                thrust::copy_if(pol, thrust::make_transform_iterator(zb, SplitRank()),
-                                thrust::make_transform_iterator(zb + uniq, SplitRank()), cnt, k, CountAtLeast2()) - k;
-        const int n = (int) std::min<long long>(kept, max_n);
-        // only the first max_n ranks are needed; a full radix sort of the ~10^5..10^6 candidates is still cheaper
-        // than the several passes a selection algorithm takes
-        thrust::sort(pol, k, k + kept);
-        if (n > 0) write_nodes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, 1, nodes_dev);
-        if (n_selected) *n_selected = n;
-        if (n_candidates) *n_candidates = (int) kept;
-    } catch (const std::exception &e) {
-        set_error("select_split_candidates: %s", e.what());
-        cudaGetLastError();
-        rc = MNV_ERR_CUDA;
-    }
-    return rc;
-}
-
-int select_sample_candidates(const float *to_sample_dev, int64_t P, int max_n, int32_t *nodes_dev,
-                             int *n_selected, int *n_candidates, cudaStream_t stream) {
-    Arena &A = arena_for_current_device();
-    ArenaScope scope{A, stream};
-    ArenaAllocator alloc{&A};
-    auto pol = thrust::cuda::par(alloc).on(stream);
-    int rc = MNV_OK;
-    try {
-        auto *keys = static_cast<unsigned long long *>(A.take(P * sizeof(unsigned long long)));
-        thrust::device_ptr<unsigned long long> k(keys);
-        const long long valid =
-                thrust::copy_if(pol, thrust::make_transform_iterator(thrust::counting_iterator<long long>(0), RowToKey{to_sample_dev}),
-                                thrust::make_transform_iterator(thrust::counting_iterator<long long>(P), RowToKey{to_sample_dev}),
-                                k, IsSome()) - k;
-        thrust::sort(pol, k, k + valid);  // (sample count, chunk, child) == unique_dim order
-        const long long uniq = thrust::unique(pol, k, k + valid) - k;
-        const int n = (int) std::min<long long>(uniq, max_n);
-        if (n > 0) write_nodes_kernel<<<(n + 255) / 256, 256, 0, stream>>>(keys, n, 0, nodes_dev);
-        if (n_selected) *n_selected = n;
-        if (n_candidates) *n_candidates = (int) uniq;
-    } catch (const std::exception &e) {
-        set_error("select_sample_candidates: %s", e.what());
-        cudaGetLastError();
-        rc = MNV_ERR_CUDA;
-    }
-    return rc;
-}
 
 // ---- Impl::query_submodules ---------------------------------------------------------------
 // Rows are bucketed by sub-module id with a counting pass and a warp-aggregated scatter of the row

@@ -147,6 +147,76 @@ int build_device_tree(DeviceTree &t, const mnv_tree_desc &d) {
     return rc;
 }
 
+// ---- anchor grid ------------------------------------------------------------------------------------------
+namespace {
+__global__ void anchor_build_kernel(const uint32_t *__restrict__ cell, int A, uint2 *__restrict__ out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (1u << (3 * A))) return;
+    const uint32_t m = (1u << A) - 1;
+    const uint32_t iz = idx & m, iy = (idx >> A) & m, ix = idx >> (2 * A);
+    uint32_t node = 0;
+    for (int l = 0;; ++l) {
+        const int bit = A - 1 - l;
+        const uint32_t c = (((ix >> bit) & 1u) << 2) | (((iy >> bit) & 1u) << 1) | ((iz >> bit) & 1u);
+        const uint32_t slot = node * 8u + c;
+        const uint32_t cw = cell[slot];
+        if (cw & kLeafBit) {
+            // the leaf itself, unless its slot does not fit 28 bits (trees beyond 2^25 nodes): then the node holding it
+            out[idx] = slot < (1u << 28) ? make_uint2(cw, ((uint32_t) l << 28) | slot) : make_uint2(node, (uint32_t) l << 28);
+            return;
+        }
+        node = cw;
+        if (l == A - 1) {
+            out[idx] = make_uint2(node, (uint32_t) A << 28);
+            return;
+        }
+    }
+}
+
+__global__ void propagate_visited_kernel(const int32_t *__restrict__ parent, int64_t capacity, int32_t *visited) {
+    const int64_t node = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (node <= 0 || node >= capacity || visited[node] == 0) return;
+    int64_t n = parent[node] >> 3;
+    for (int guard = 0; guard < 32; ++guard) {
+        if (visited[n] != 0) break;  // whoever marked it walks (or walked) the rest of the chain
+        visited[n] = 1;
+        if (n == 0) break;
+        n = parent[n] >> 3;
+    }
+}
+}  // namespace
+
+int ensure_anchor(DeviceTree &t, cudaStream_t stream) {
+    if (t.anchor_level <= 0) return MNV_OK;
+    const size_t n = (size_t) 1 << (3 * t.anchor_level);
+    if (!t.anchor) {
+        MNV_CUDA(cudaMalloc(&t.anchor, n * sizeof(uint2)));
+        t.anchor_dirty = true;
+    }
+    if (!t.anchor_dirty) return MNV_OK;
+    anchor_build_kernel<<<(unsigned) ((n + 255) / 256), 256, 0, stream>>>(t.cell, t.anchor_level, t.anchor);
+    MNV_CUDA(cudaGetLastError());
+    t.anchor_dirty = false;
+    return MNV_OK;
+}
+
+void refresh_max_leaf_depth(DeviceTree &t) {
+    if (!t.depth_pending || !t.depth_event) return;
+    if (cudaEventQuery(t.depth_event) != cudaSuccess) {
+        cudaGetLastError();  // not ready: keep the upper bound
+        return;
+    }
+    t.max_leaf_depth = std::min(23, std::max(1, *t.max_depth_host));
+    t.depth_pending = false;
+}
+
+int launch_propagate_visited(const DeviceTree &t, int32_t *visited, cudaStream_t stream) {
+    if (t.capacity <= 1) return MNV_OK;
+    propagate_visited_kernel<<<(unsigned) ((t.capacity + 255) / 256), 256, 0, stream>>>(t.parent, t.capacity, visited);
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+
 int download_device_tree(const DeviceTree &t, int64_t first, int64_t count, uint16_t *data,
                          int32_t *child, int32_t *parent, int16_t *sample_counts) {
     if (first < 0 || count < 0 || first + count > t.capacity) {

@@ -94,11 +94,89 @@ OPT_KEYS = ["step_size", "sigma_thresh", "stop_thresh", "background_brightness",
             "basis_minmax", "rot_dirs", "render_depth", "max_depth", "max_sample_count"]
 
 
+GRID, MINP, RNG = [2, 4], [-1.0, -1.0, -1.0], [2.0, 2.0, 2.0]
+
+
+def nerf_cases():
+    """Guided-sampling compositor (render_nerf_results_kernel, renderer_kernel.cu:294-327): the samples come from
+    the reference's own get_samples_from_voxels, the per-sample values from a seeded generator."""
+    d = mnv.synth.default_camera
+    yield "nerf_sh9", dict(depth=5, fmt="SH9", sigma=(40.0, 300.0)), d(48, 27, 9), {}
+    yield "nerf_rgba", dict(depth=5, fmt="RGBA", sigma=(40.0, 300.0)), d(48, 27, 3), {}
+    yield "nerf_sh4", dict(depth=5, fmt="SH4", sigma=(40.0, 300.0)), d(48, 27, 6), {}
+    yield "nerf_sh16", dict(depth=4, fmt="SH16", sigma=(40.0, 300.0)), d(48, 27, 12), {}
+    yield "nerf_sh9_depthmode", dict(depth=5, fmt="SH9", sigma=(40.0, 300.0)), d(48, 27, 9), dict(render_depth=True)
+    yield "nerf_sh9_rot_basis", dict(depth=5, fmt="SH9", sigma=(40.0, 300.0)), d(48, 27, 1), \
+        dict(rot_dirs=[0.3, -0.2, 0.9], basis_minmax=[1, 6])
+
+
+def nerf_values(V, D, seed=11):
+    rng = np.random.default_rng(seed)
+    values = rng.standard_normal((V, D + 1)).astype(np.float32)
+    values[:, 3] = np.abs(values[:, 3]) * 30  # the column the reference reads sigma from (rt_core.cuh:365)
+    return values
+
+
+def make_nerf_goldens(out_dir):
+    n_bad = 0
+    for name, tspec, cam, okw in nerf_cases():
+        key = (tspec["depth"], tspec["fmt"], tspec["sigma"])
+        tree = mnv.synth.make_tree(depth=key[0], data_format=key[1], sigma_range=key[2])
+        path = f"/tmp/golden_nerf_tree_{name}.npz"
+        tree.save_npz(path)
+        kw = dict(background_brightness=0.0, use_guided_sampling=True, max_guided_samples=24)
+        kw.update(okw)
+        if "basis_minmax" not in kw:
+            kw["basis_minmax"] = [0, max(tree.basis_dim - 1, 0)]
+        opt = O.default_options(**kw)
+        ref = O.RefRenderer(path)
+        g = ref.get_samples(cam, opt, GRID, MINP, RNG)
+        off, z, _, _ = O.compact_samples(g["num_samples"], g["samples"], g["cluster"])
+        assert off[-1] == z.shape[0] > 0
+        values = nerf_values(z.shape[0], tree.data_dim)
+        rimg = ref.render_nerf_results(cam, opt, values, z, off)
+        assert rimg is not None, "reference compositor did not launch"
+        out = dict(**tree_fields(tree, key),
+                   cam_wh=np.array([cam["width"], cam["height"]], np.int32),
+                   cam_intr=np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32),
+                   cam_c2w=np.asarray(cam["c2w"], np.float32),
+                   z_vals=z, offsets=off, values_seed=np.int32(11), values_sha=np.array(
+                       __import__("hashlib").sha256(values.tobytes()).hexdigest()),
+                   ref_rgba=rimg)
+        for k in OPT_KEYS:
+            v = getattr(opt, k)
+            out["opt_" + k] = np.array(list(v) if hasattr(v, "__len__") else v)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **out)
+        want = O.composite_nerf(tree, cam, opt, values, z, off)
+        od = np.abs(want.astype(int) - rimg.astype(int))
+        line = f"{name:22s} samples {z.shape[0]:6d} | oracle: maxabs {od.max()} ndiff {(od > 0).sum()}"
+        try:
+            import torch
+            if torch.cuda.is_available() and os.path.exists(mnv.LIB_PATH):
+                dt = mnv.DeviceTree(tree)
+                img = dt.render_nerf_results(cam, mnv.default_options(**kw), torch.from_numpy(values).cuda(),
+                                             torch.from_numpy(z).cuda(), torch.from_numpy(off).cuda()).cpu().numpy()
+                md = np.abs(img.astype(int) - rimg.astype(int))
+                n_bad += int(md.max() != 0)
+                line += f" | native: maxabs {md.max()} ndiff {(md > 0).sum()} {'OK' if md.max() == 0 else 'MISMATCH'}"
+                dt.close()
+        except ImportError:
+            pass
+        print(line, flush=True)
+        ref.close()
+    print("native mismatching compositor cases:", n_bad)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "golden"))
+    ap.add_argument("--only", default="all", choices=["all", "voxels", "nerf"])
     args = ap.parse_args()
     os.makedirs(args.out, exist_ok=True)
+    if args.only in ("all", "nerf"):
+        make_nerf_goldens(args.out)
+    if args.only == "nerf":
+        return
     try:
         import torch
         have_native = torch.cuda.is_available() and os.path.exists(mnv.LIB_PATH)

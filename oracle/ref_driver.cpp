@@ -25,6 +25,10 @@
 extern "C" void ref_instr_set_buffers(unsigned long long *hash, int *count, int *log, int log_cap);
 #endif
 
+namespace viewer {
+extern int cuda_n_threads;  // src/cuda/renderer_kernel.cu:12 (threads per block of every launcher)
+}
+
 namespace {
 struct RefCtx {
     viewer::N3Tree tree;
@@ -260,10 +264,17 @@ int ref_render_nerf_results(void *ctx, int w, int h, const float *intr, const fl
     torch::Tensor zv = torch::from_blob((void *) z_vals, {V}, torch::kFloat32).clone().to(torch::kCUDA);
     torch::Tensor of = torch::from_blob((void *) offsets, {P}, torch::kInt64).clone().to(torch::kCUDA);
     cudaGetLastError();
-    viewer::render_nerf_results(c->tree, *c->cam, opt, c->img, c->stream, sv, zv, of, /*offscreen=*/true);
     // The reference never checks its launches.  Rebuilt for sm_100 this kernel needs 168
     // registers x 512 threads per block (auto_cuda_threads, renderer_kernel.cu:14-28) = 86016
-    // > 65536 registers per SM: the launch fails with "too many resources requested".
+    // > 65536 registers per SM: as shipped the launch fails with "too many resources requested".
+    // The block size is the reference's own global knob (viewer::cuda_n_threads,
+    // renderer_kernel.cu:12; auto_cuda_threads leaves any value other than -1 alone), so this
+    // launch runs with 256 threads per block — same sources, same arithmetic, launch geometry
+    // only — and the knob is restored afterwards.
+    const int saved_threads = viewer::cuda_n_threads;
+    viewer::cuda_n_threads = 256;
+    viewer::render_nerf_results(c->tree, *c->cam, opt, c->img, c->stream, sv, zv, of, /*offscreen=*/true);
+    viewer::cuda_n_threads = saved_threads;
     if (cudaGetLastError() != cudaSuccess) return 3;
     if (cudaDeviceSynchronize() != cudaSuccess) return 2;
     cudaMemcpy2DFromArray(rgba_out, (size_t) w * 4, c->img, 0, 0, (size_t) w * 4, h,

@@ -64,3 +64,19 @@ def test_invalid_trees_are_rejected(mnv):
     assert b"N == 2" in mnv.lib().mnv_last_error()
     d.N, d.basis_dim = 2, 7
     assert mnv.lib().mnv_tree_create(C.byref(h), C.byref(d), 0, 0) == 6  # MNV_ERR_FORMAT
+
+
+def test_tracker_chunk_encoding_roundtrip(mnv):
+    """Chunk column of the candidate trackers: the reference's float value below 2^24 (bit-identical rows),
+    integer bits above (rt_core.cuh:238-240 loses odd ids there) — host helpers of the C-ABI."""
+    L = mnv.lib()
+    vals = [0, 1, 7, 12345, (1 << 24) - 1, 1 << 24, (1 << 24) + 1, 18_200_001, (1 << 27) + 12345, (1 << 28) - 1]
+    for v in vals:
+        f = L.mnv_tracker_encode_chunk(v)
+        assert L.mnv_tracker_decode_chunk(f) == v
+        if v < (1 << 24):
+            assert f == float(v)  # exactly what the reference writes
+        else:
+            assert 0.0 < f < 1e-28  # cannot be mistaken for a float-encoded id, 0 or -1
+    col = np.array([L.mnv_tracker_encode_chunk(v) for v in vals] + [-1.0], np.float32)
+    assert np.array_equal(mnv.decode_tracker_chunks(col), np.array(vals + [-1]))

@@ -59,6 +59,21 @@ def test_guided_samples_match_oracle_and_reference(okw, mnv, oracle, tmp_path):
     dt.close()
 
 
+@pytest.mark.parametrize("name", __import__("helpers").NERF_GOLDENS)
+def test_composite_equals_reference_golden(name, mnv):
+    """A8 pinned: the native compositor through the C-ABI against the committed outputs of the reference's own
+    render_nerf_results_kernel — bit for bit."""
+    import torch
+    from helpers import load_nerf_golden
+
+    tree, cam, okw, values, z, off, ref_rgba = load_nerf_golden(name)
+    dt = mnv.DeviceTree(tree)
+    img = dt.render_nerf_results(cam, mnv.default_options(**okw), torch.from_numpy(values).cuda(),
+                                 torch.from_numpy(z).cuda(), torch.from_numpy(off).cuda()).cpu().numpy()
+    assert np.array_equal(img, ref_rgba), np.abs(img.astype(int) - ref_rgba.astype(int)).max()
+    dt.close()
+
+
 def test_guided_capacity_error(mnv):
     tree = mnv.synth.make_tree(depth=5, sigma_range=(40.0, 300.0))
     dt = mnv.DeviceTree(tree)
@@ -94,9 +109,12 @@ def test_composite_matches_oracle_and_reference(fmt, render_depth, mnv, oracle, 
         tree.save_npz(npz)
         ref = oracle.RefRenderer(npz)
         rimg = ref.render_nerf_results(cam, oopt, values, z, off)
-        # None: the reference's render_nerf_results_kernel cannot launch on sm_100 as built
-        # (168 registers x 512 threads per block > 64 K registers); the oracle is then the check
-        if rimg is not None:
-            assert np.array_equal(img, rimg), np.abs(img.astype(int) - rimg.astype(int)).max()
+        # The reference's render_nerf_results_kernel (renderer_kernel.cu:294-327) cannot launch on sm_100
+        # with the 512 threads per block its auto_cuda_threads picks (168 registers x 512 > 64 K); the
+        # driver sets the reference's own block-size knob (viewer::cuda_n_threads) to 256 for this call —
+        # unmodified sources, same arithmetic — so this pins the compositor bit for bit.
+        assert rimg is not None, "reference compositor did not launch"
+        assert np.array_equal(img, rimg), np.abs(img.astype(int) - rimg.astype(int)).max()
+        assert np.abs(want.astype(int) - rimg.astype(int)).max() <= 1  # the CPU restatement against the same pin
         ref.close()
     dt.close()

@@ -54,6 +54,94 @@ def test_candidate_selection_matches_torch_semantics(mnv):
     dt.close()
 
 
+def _random_tracker(rng, P, n_leaves, id_base=0, prio_max=9, none_frac=0.3):
+    """Rows (priority, chunk, child) as the march kernel writes them: priority is a function of the leaf."""
+    ids = id_base + rng.integers(0, n_leaves, P) * 3  # sparse leaf ids
+    ids = np.where(rng.random(P) < 0.5, ids, id_base + (rng.zipf(1.6, P) % n_leaves) * 3)  # heavy hitters
+    prio = (ids * 2654435761 % (prio_max + 1)).astype(np.float32)
+    rows = np.stack([prio, (ids >> 3).astype(np.float32), (ids & 7).astype(np.float32)], 1).astype(np.float32)
+    rows[rng.random(P) < none_frac] = -1.0
+    return rows
+
+
+@pytest.mark.parametrize("P,n_leaves,max_n", [(200_000, 50_000, 4096), (70_001, 300, 4192), (5000, 4000, 16384),
+                                               (1_000_000, 400_000, 1), (33, 5, 8)])
+def test_vote_selection_random_rows(P, n_leaves, max_n, mnv):
+    """Hash-count + radix-select selection (csrc/mnv_vote.cu) against the unique_dim chain in numpy."""
+    import torch
+
+    rng = np.random.default_rng(P + max_n)
+    rows = _random_tracker(rng, P, n_leaves)
+    t = torch.from_numpy(rows).cuda()
+    for _ in range(2):  # the table must be left clean by the first call
+        nodes, nc = mnv.select_candidates(t, max_n, "split")
+        want, wc = ref_select_split(rows, max_n)
+        assert nc == wc
+        assert np.array_equal(nodes.cpu().numpy(), want)
+        nodes, nc = mnv.select_candidates(t, max_n, "sample")
+        want, wc = ref_select_sample(rows, max_n)
+        assert nc == wc
+        assert np.array_equal(nodes.cpu().numpy(), want)
+
+
+def test_vote_records_merge_equals_global_selection(mnv):
+    """Multi-GPU refinement: per-rank vote records, gathered and merged, select exactly what the raw rows do."""
+    import torch
+
+    rng = np.random.default_rng(77)
+    rows = _random_tracker(rng, 300_000, 40_000)
+    parts = np.array_split(rows, [90_000, 90_001, 210_000])  # four uneven "ranks"
+    recs = [mnv.vote_reduce(torch.from_numpy(np.ascontiguousarray(p)).cuda()) for p in parts]
+    # every rank's records: unique leaves with their multiplicities
+    r0 = recs[0].cpu().numpy().astype(np.int64)
+    v0 = parts[0][parts[0][:, 1] >= 0]
+    u, c = np.unique((v0[:, 1].astype(np.int64) * 8 + v0[:, 2].astype(np.int64)), return_counts=True)
+    order = np.argsort(r0[:, 0])
+    assert np.array_equal(r0[order, 0], u) and np.array_equal(r0[order, 2], c)
+    pad = torch.zeros((1000, 3), dtype=torch.int32, device="cuda")  # all-gather padding: votes == 0
+    gathered = torch.cat([recs[0], pad, recs[1], recs[2], pad, recs[3]])
+    for kind, ref in (("split", ref_select_split), ("sample", ref_select_sample)):
+        nodes, nc = mnv.select_from_votes(gathered, 4096, kind)
+        want, wc = ref(rows, 4096)
+        assert nc == wc and np.array_equal(nodes.cpu().numpy(), want)
+    # records of the other ranks + own raw rows
+    nodes, nc = mnv.select_from_votes(torch.cat(recs[1:]), 4096, "split",
+                                      tracker=torch.from_numpy(np.ascontiguousarray(parts[0])).cuda())
+    want, wc = ref_select_split(rows, 4096)
+    assert nc == wc and np.array_equal(nodes.cpu().numpy(), want)
+    with pytest.raises(mnv.MnvError) as ei:
+        mnv.vote_reduce(torch.from_numpy(np.ascontiguousarray(parts[2])).cuda(), cap_records=100)
+    assert ei.value.code == 7  # MNV_ERR_FULL
+
+
+def test_vote_selection_node_ids_above_2_pow_24(mnv):
+    """float trackers are exact only below 2^24 nodes; larger ids travel as integer bits."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    P = 50_000
+    ids = (1 << 27) + 1 + rng.integers(0, 2000, P) * 2 + (rng.integers(0, 8, P) << 0) * 0  # odd node ids > 2^24
+    child = rng.integers(0, 8, P)
+    small = rng.random(P) < 0.3
+    node = np.where(small, rng.integers(0, 1000, P), ids).astype(np.int64)
+    col = np.array([mnv.lib().mnv_tracker_encode_chunk(int(v)) for v in node], np.float32)
+    assert np.array_equal(mnv.decode_tracker_chunks(col), node)
+    assert all(mnv.lib().mnv_tracker_decode_chunk(float(c)) == int(v) for c, v in zip(col[:200], node[:200]))
+    prio = (node % 7).astype(np.float32)
+    rows = np.stack([prio, col, child.astype(np.float32)], 1)
+    nodes, nc = mnv.select_candidates(torch.from_numpy(rows).cuda(), 4096, "split")
+    # numpy restatement on exact integers
+    key = node * 8 + child
+    u, c = np.unique(key, return_counts=True)
+    keep = c >= 2
+    u, c = u[keep], c[keep]
+    pr = (u >> 3) % 7
+    order = np.lexsort((u, pr, -c))
+    want = np.stack([u[order] >> 3, u[order] & 7], 1)[:4096].astype(np.int32)
+    assert nc == len(u) and np.array_equal(nodes.cpu().numpy(), want)
+    assert (nodes.cpu().numpy()[:, 0] > (1 << 24)).any()
+
+
 def test_query_submodules_dispatch(mnv):
     import torch
     from mlp_reference import MegaNerfMLP
