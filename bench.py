@@ -61,7 +61,10 @@ def parse():
                     help="N > 1: image tiles with the tree replicated (default) or one spatial cell per GPU with "
                          "partials composited over NVLink peer stores; guided: the guided-sampling frame (configs[4]) "
                          "with the sub-modules sharded by cell, timed next to the row-block / replicated variant")
-    ap.add_argument("--max-nodes", type=int, default=16_000_000, help="node budget of the mill19 tree")
+    ap.add_argument("--max-nodes", type=int, default=24_000_000, help="node budget of the mill19 tree")
+    ap.add_argument("--no-target", action="store_true",
+                    help="skip the target_4k sections (BASELINE.json configs[2..4] at 3840x2160 on the Mill-19-scale tree)")
+    ap.add_argument("--target-max-nodes", type=int, default=24_000_000, help="node budget of the target_4k tree")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-headless", action="store_true", help="skip the config 4 / 5 sections (C++ driver)")
     return ap.parse_args()
@@ -258,30 +261,52 @@ def headless_sections(mnv, tree, W, H):
     return out
 
 
-def shared_tree(make, rank, world, dist, mnv):
-    """Multi-GB trees are generated once (rank 0) and mapped by the other ranks from /dev/shm."""
-    if world == 1:
-        return make()
+MILL19_DEPTHS = [12, 11, 11, 12, 12, 11, 11, 12]
+
+
+def mill19_params(max_nodes):
+    """BASELINE.json configs[2]: 8 spatial blocks on a 2x4 (y, z) grid, depth <= 12, ~1.8*10^7 nodes (8-9 GB of
+    leaves).  The height field is tilted across the whole z extent so that every block holds surface (round 1's
+    flat field left four of the eight cells empty)."""
+    return dict(depth=12, data_format=FMT, blocks_yz=(2, 4), block_depths=MILL19_DEPTHS, max_nodes=int(max_nodes),
+                tilt=0.75, amp_scale=0.4, fast_data=True)
+
+
+def shared_tree(params, rank, world, dist, mnv):
+    """Multi-GB trees are generated once per box — by rank 0, into /dev/shm, keyed by their parameters — and
+    mapped by every rank (and by later bench.py runs on the same box) from there."""
+    import hashlib
     import shutil
-    d = "/dev/shm/mnv_bench_tree"
-    reuse = os.environ.get("MNV_BENCH_REUSE_TREE") == "1" and os.path.exists(os.path.join(d, "meta.json"))
-    if rank == 0 and not reuse:  # MNV_BENCH_REUSE_TREE=1: back-to-back runs on one box keep the generated tree
-        shutil.rmtree(d, ignore_errors=True)
+    key = hashlib.sha1(json.dumps(params, sort_keys=True).encode()).hexdigest()[:12]
+    d = f"/dev/shm/mnv_bench_tree_{key}"
+    done = os.path.join(d, "meta.json")
+    if rank == 0 and not os.path.exists(done):
+        for old in [p for p in os.listdir("/dev/shm") if p.startswith("mnv_bench_tree")]:
+            shutil.rmtree(os.path.join("/dev/shm", old), ignore_errors=True)
         os.makedirs(d)
-        t = make()
+        t = mnv.synth.make_tree(**params)
         for k in ("child", "parent", "depth", "data", "scale", "offset"):
             np.save(os.path.join(d, k + ".npy"), getattr(t, k))
-        with open(os.path.join(d, "meta.json"), "w") as f:
-            json.dump({"data_dim": t.data_dim, "data_format": t.data_format}, f)
-    dist.barrier()
-    if rank != 0 or reuse:
-        with open(os.path.join(d, "meta.json")) as f:
-            meta = json.load(f)
-        a = {k: np.load(os.path.join(d, k + ".npy"), mmap_mode="r") for k in ("child", "parent", "depth", "data", "scale", "offset")}
-        t = mnv.HostTree(N=2, data_dim=meta["data_dim"], data_format=meta["data_format"], child=a["child"],
-                         parent=a["parent"], depth=a["depth"], data=a["data"], scale=np.array(a["scale"]),
-                         offset=np.array(a["offset"]))
-    return t
+        with open(done + ".tmp", "w") as f:
+            json.dump({"data_dim": t.data_dim, "data_format": t.data_format, "params": params}, f)
+        os.replace(done + ".tmp", done)
+        del t
+    if dist is not None:
+        dist.barrier()
+    with open(done) as f:
+        meta = json.load(f)
+    a = {k: np.load(os.path.join(d, k + ".npy"), mmap_mode="r") for k in ("child", "parent", "depth", "data", "scale", "offset")}
+    return mnv.HostTree(N=2, data_dim=meta["data_dim"], data_format=meta["data_format"], child=a["child"],
+                        parent=a["parent"], depth=a["depth"], data=a["data"], scale=np.array(a["scale"]),
+                        offset=np.array(a["offset"]))
+
+
+def frame_parity(got: np.ndarray, want: np.ndarray) -> dict:
+    """RGBA8 frames -> {bit_exact, max_abs, frac_within_1, psnr} (north_star: <= 1/255 max-abs, >= 50 dB)."""
+    d = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    mse = float(np.mean(d.astype(np.float64) ** 2))
+    return {"bit_exact": bool(d.max() == 0), "max_abs": int(d.max()), "frac_within_1": float((d <= 1).mean()),
+            "psnr": 99.0 if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))}
 
 
 def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
@@ -299,6 +324,170 @@ def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
         n += 1
     return {"value": rays / t_all / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": "port",
             "sample": f"{n} full {cams[0]['width']}x{cams[0]['height']} frame(s) of the orbit, {t_all:.1f} s"}
+
+
+def target_sections(args, mnv, torch, dist, rank, world, local_rank):
+    """The north-star target case inside the default line: 3840x2160 on the Mill-19-scale octree (BASELINE.json
+    configs[2..4]) — image tiles, frames with dynamic refinement ON, and guided sampling — each timed on the device /
+    host as its own section, with its own clock record, at the N GPUs of this run.  Rank 0 returns the dict."""
+    W, H = 3840, 2160
+    P = W * H
+    dev = torch.device("cuda", local_rank)
+    tree = shared_tree(mill19_params(args.target_max_nodes), rank, world, dist, mnv)
+    cams = [mnv.synth.default_camera(W, H, pose=i, n_poses=N_POSES) for i in range(N_POSES)]
+    opt_kw = dict(background_brightness=0.0, basis_minmax=[0, 8])
+    opt = mnv.default_options(**opt_kw)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"workload": f"Mill-19-scale: {W}x{H}, 8 spatial blocks (2x4 on y,z), depth <= 12, {tree.capacity} nodes, "
+                       f"{tree.nbytes() / 1e9:.2f} GB AoS, {N_POSES}-pose orbit", "tree_nodes": int(tree.capacity)}
+
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxed(ms):
+        t = torch.tensor(ms, device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy()
+
+    # ---- (a) image tiles, tree replicated (configs[2]) ----
+    dt = mnv.DeviceTree(tree, device=local_rank)
+    img = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+    ts = torch.empty((P, 3), device=dev)
+    tp = torch.empty((P, 3), device=dev)
+    tile = (((W + 15) // 16) * 16, BAND_ROWS, world, rank)
+
+    def launch(i):
+        if world == 1:
+            dt.render(cams[i % N_POSES], opt, out=img, to_split=ts, to_sample=tp)
+        else:
+            dt.render_tiles(cams[i % N_POSES], opt, img, *tile, to_split=ts, to_sample=tp)
+
+    for i in range(3):
+        launch(i)
+    sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.time()
+    evs = []
+    steps = 24
+    for i in range(steps):
+        flush.fill_(i & 0xff)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch(i)
+        e1.record()
+        evs.append((e0, e1))
+    sync()
+    clocks = sampler.stop(t0, time.time()) if sampler else None
+    ms = maxed([a.elapsed_time(b) for a, b in evs])
+    par = None
+    if world > 1:  # union of the ranks' bands against rank 0's own full frame
+        img.zero_()
+        launch(5)
+        torch.cuda.synchronize()
+        dist.all_reduce(img)  # bands are disjoint, the rest is zero
+        if rank == 0:
+            full = torch.zeros_like(img)
+            dt.render(cams[5], opt, out=full)
+            torch.cuda.synchronize()
+            par = frame_parity(img.cpu().numpy(), full.cpu().numpy())
+            del full
+    m = float(ms.mean())
+    out["tiles"] = {"ms_per_frame": m, "fps": 1e3 / m, "mrays_per_s": P / m / 1e3, "steps": steps, "candidate_tracking": True,
+                    "timing": "CUDA events on the launching stream, max over ranks per frame, L2 flushed between frames",
+                    "parallelism": "one GPU" if world == 1 else f"interleaved {BAND_ROWS}-row bands over {world} GPUs, tree replicated",
+                    "parity_vs_one_gpu": par, "clocks": clocks}
+    dt.close()
+    del img, ts, tp
+    torch.cuda.empty_cache()
+
+    # ---- (b) dynamic refinement ON (configs[3]) and guided sampling (configs[4]) on replicas ----
+    subs = [mnv.synth.make_mlp_weights(seed=3 + i) for i in range(8)]
+    n_ref = 16
+    ropt = mnv.default_options(use_splitting=True, appearance_embedding=0, split_batch_size=4096, **opt_kw)
+    pipe = mnv.multigpu.ReplicatedPipeline(tree, subs, (2, 4), (-1, -1, -1), (1, 1, 1), rank=rank, world=world,
+                                           device=local_rank, dist=dist, max_capacity=tree.capacity + (n_ref + 4) * 4096)
+    cap0 = tree.capacity
+    added = 0
+    for i in range(3):
+        added += pipe.refine_frame(cams[i % N_POSES], ropt)[1]
+    sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.time()
+    ms = []
+    for i in range(n_ref):
+        flush.fill_(i & 0xff)
+        sync()
+        t1 = time.perf_counter()
+        _, k = pipe.refine_frame(cams[i % N_POSES], ropt)
+        torch.cuda.synchronize()
+        ms.append((time.perf_counter() - t1) * 1e3)
+        added += k
+    clocks = sampler.stop(t0, time.time()) if sampler else None
+    ms = maxed(ms)
+    # replicas must hold the same refined tree: checksum of every node added since the start
+    import zlib
+    crc = 0
+    for a in pipe.dt.download(first=cap0):
+        crc = zlib.crc32(np.ascontiguousarray(a).tobytes(), crc)
+    same = True
+    if dist is not None:
+        c = torch.tensor([crc], device=dev, dtype=torch.int64)
+        lst = [torch.zeros_like(c) for _ in range(world)]
+        dist.all_gather(lst, c)
+        same = all(int(x.item()) == crc for x in lst)
+    m = float(np.median(ms))
+    out["refinement"] = {"ms_per_frame_median": m, "fps": 1e3 / m, "mrays_per_s": P / m / 1e3, "steps": n_ref,
+                         "nodes_added": int(added), "mlp_rows_per_frame": 4096 * 8 * 8,
+                         "refined_nodes_crc32": f"{crc:08x}", "replicas_identical": bool(same),
+                         "timing": "host clock around the frame (march with vote tracking -> vote exchange -> selection -> "
+                                   "4096 splits x 8 children x 8 samples -> 8 sub-MLPs -> commit), max over ranks, median",
+                         "parallelism": "one GPU" if world == 1 else
+                         f"row blocks over {world} GPUs, tree + sub-MLPs replicated; vote records and fp16 payloads "
+                         "all-gathered (NCCL), MLP rows sharded by child",
+                         "exchange_bytes_per_frame": None if world == 1 else
+                         {"vote_records_all_gather": getattr(pipe, "vote_bytes", None),
+                          "payload_records_all_gather": getattr(pipe, "payload_bytes", None)},
+                         "clocks": clocks}
+    # guided sampling, row blocks, replicated (no exchange)
+    gopt = mnv.default_options(use_guided_sampling=True, appearance_embedding=0, **opt_kw)
+    first, n = mnv.multigpu.row_block(H, world, rank)
+    cap = int(max(1 << 20, n * W * 12))
+    n_g = 4
+    rows = 0
+    for i in range(1):
+        pipe.guided_block(cams[i], gopt, capacity_rows=cap)
+    sync()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.time()
+    ms = []
+    for i in range(n_g):
+        flush.fill_(i & 0xff)
+        sync()
+        t1 = time.perf_counter()
+        _, r = pipe.guided_block(cams[i % N_POSES], gopt, capacity_rows=cap)
+        torch.cuda.synchronize()
+        ms.append((time.perf_counter() - t1) * 1e3)
+        rows += r
+    clocks = sampler.stop(t0, time.time()) if sampler else None
+    ms = maxed(ms)
+    rt = torch.tensor([rows], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(rt)
+    m = float(np.median(ms))
+    rows_frame = float(rt.item()) / n_g
+    out["guided_sampling"] = {"ms_per_frame_median": m, "fps": 1e3 / m, "mrays_per_s": P / m / 1e3, "steps": n_g,
+                              "mlp_rows_per_frame": rows_frame, "mrows_per_s": rows_frame / m / 1e3,
+                              "mlp_tflops": rows_frame * 1210624.0 / (m * 1e-3) / 1e12,
+                              "timing": "host clock around the frame (emission -> per-sample MLP over 8 sub-modules -> "
+                                        "per-ray compositing) incl. the row-count sync, max over ranks, median",
+                              "parallelism": "one GPU" if world == 1 else
+                              f"row blocks over {world} GPUs, tree + sub-MLPs replicated, no exchange",
+                              "clocks": clocks}
+    pipe.close()
+    return out
 
 
 def main():
@@ -328,9 +517,7 @@ def main():
         if (args.width, args.height) == (WIDTH, HEIGHT):
             W, H = 3840, 2160
             P = W * H
-        tree = shared_tree(lambda: mnv.synth.make_tree(depth=12, data_format=FMT, blocks_yz=(2, 4),
-                                                        block_depths=[12, 11, 11, 12, 11, 12, 12, 11],
-                                                        max_nodes=args.max_nodes), rank, world, dist, mnv)
+        tree = shared_tree(mill19_params(args.max_nodes), rank, world, dist, mnv)
         wl = f"Mill-19-scale: headless {W}x{H} frame, 8 spatial blocks (2x4 on y,z), depth <= 12"
     else:
         tree = mnv.synth.make_tree(depth=args.depth, data_format=FMT)
@@ -442,6 +629,31 @@ def main():
     e2e_ms = e2e_run(opt_track)
     e2e_nt_ms = e2e_run(opt)
 
+    # multi-GPU parity, verified by the run that is timed: the union of the ranks' bands against the frame rank 0
+    # renders alone (bit-exact by construction: rays are independent)
+    parity = None
+    if dist is not None:
+        worst = None
+        for pose in (0, 7):
+            out.zero_()
+            dt.render_tiles(cams[pose], opt, out, *tile)
+            torch.cuda.synchronize()
+            dist.all_reduce(out)  # bands are disjoint, the rest is zero
+            if rank == 0:
+                full = torch.zeros_like(out)
+                dt.render(cams[pose], opt, out=full)
+                torch.cuda.synchronize()
+                pr = frame_parity(out.cpu().numpy(), full.cpu().numpy())
+                if worst is None or pr["max_abs"] > worst["max_abs"]:
+                    worst = pr
+        parity = worst and dict(worst, against="the whole frame rendered by rank 0 alone, poses 0 and 7")
+
+    target = None
+    if not args.no_target and args.workload == "1080p" and args.mode == "tiles":
+        dt_keep = dt
+        target = target_sections(args, mnv, torch, dist, rank, world, local_rank)
+        dt = dt_keep
+
     if rank != 0:
         dist.destroy_process_group()
         return 0
@@ -480,6 +692,10 @@ def main():
                      "gvisits_per_s": visits / (ms_step * 1e-3) / 1e9},
         "clocks": clocks,
     }
+    if parity is not None:
+        line["parity"] = parity
+    if target is not None:
+        line["target_4k"] = target
     line["mlp"] = mlp_section(mnv, torch, dev)
     if world == 1 and not args.no_cpu_baseline:
         line["point_query"] = point_query_section(mnv, torch, dev, dt, tree)

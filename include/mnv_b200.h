@@ -276,6 +276,17 @@ int mnv_add_children_and_generate_samples(mnv_tree *tree, const mnv_render_optio
  * capacity += n. */
 int mnv_tree_commit_children(mnv_tree *tree, const mnv_render_options *opt, int n,
                              const float *results_dev, int result_stride, void *stream);
+/* Multi-GPU form of the same tail (MLP rows sharded across the replicas, 1.8 MB of fp16
+ * payloads exchanged instead of 30 MB of fp32 results).  mnv_tree_reduce_children turns the MLP outputs of
+ * n_children consecutive new leaves (results_dev f32 [n_children][samples_per_corner][result_stride]) into their
+ * payload records — records_dev, mnv_tree_record_bytes() bytes each, the device layout of one leaf — without
+ * touching the tree; after the all-gather every replica calls mnv_tree_commit_children_records with the
+ * records of all n * 8 children in child order.  Equal, bit for bit, to mnv_tree_commit_children. */
+int mnv_tree_record_bytes(const mnv_tree *tree, int *bytes);
+int mnv_tree_reduce_children(mnv_tree *tree, const mnv_render_options *opt, int n_children,
+                             const float *results_dev, int result_stride, void *records_dev, void *stream);
+int mnv_tree_commit_children_records(mnv_tree *tree, const mnv_render_options *opt, int n,
+                                     const void *records_dev, void *stream);
 /* viewer::generate_samples, renderer_kernel.cu:513-535 (kernel :200-213): sample rows for m
  * existing leaves (nodes_dev i32 [m][2]). */
 int mnv_generate_samples(mnv_tree *tree, const mnv_render_options *opt, const int32_t *nodes_dev, int m,

@@ -159,6 +159,9 @@ def lib() -> C.CDLL:
                                           vp, vp, C.c_bool, vp]
     L.mnv_add_children_and_generate_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.mnv_tree_commit_children.argtypes = [vp, C.POINTER(RenderOptions), i32, vp, i32, vp]
+    L.mnv_tree_record_bytes.argtypes = [vp, C.POINTER(i32)]
+    L.mnv_tree_reduce_children.argtypes = [vp, C.POINTER(RenderOptions), i32, vp, i32, vp, vp]
+    L.mnv_tree_commit_children_records.argtypes = [vp, C.POINTER(RenderOptions), i32, vp, vp]
     L.mnv_generate_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, vp, vp, vp, vp, vp]
     L.mnv_tree_update_samples.argtypes = [vp, C.POINTER(RenderOptions), vp, i32, vp, i32, vp]
     L.mnv_tree_prune.argtypes = [vp, vp, vp, i32, i64, vp]
@@ -422,6 +425,25 @@ class DeviceTree:
     def commit_children(self, opt, n, results, stream=None):
         _check(lib().mnv_tree_commit_children(self._h, C.byref(opt), n, _dptr(results), results.shape[-1],
                                               _stream_ptr(stream)))
+
+    @property
+    def record_bytes(self) -> int:
+        b = C.c_int(0)
+        _check(lib().mnv_tree_record_bytes(self._h, C.byref(b)))
+        return b.value
+
+    def reduce_children(self, opt, results, stream=None):
+        """results f32 [n_children, samples_per_corner, stride] -> payload records uint8 [n_children, record_bytes]."""
+        torch = _torch()
+        n = results.shape[0]
+        rec = torch.empty((n, self.record_bytes), dtype=torch.uint8, device=results.device)
+        _check(lib().mnv_tree_reduce_children(self._h, C.byref(opt), n, _dptr(results), results.shape[-1], _dptr(rec),
+                                              _stream_ptr(stream)))
+        return rec
+
+    def commit_children_records(self, opt, n, records, stream=None):
+        assert records.shape[0] >= n * 8 and records.is_contiguous()
+        _check(lib().mnv_tree_commit_children_records(self._h, C.byref(opt), n, _dptr(records), _stream_ptr(stream)))
 
     def generate_samples(self, opt, nodes, samples, cluster, grid_dim, min_position, rng, stream=None):
         keep, g = self._grid_args(grid_dim, min_position, rng)

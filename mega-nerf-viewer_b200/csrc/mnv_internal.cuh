@@ -245,6 +245,10 @@ int refine_add_children(DeviceTree &t, const mnv_render_options &opt, const int3
                         cudaStream_t stream);
 int refine_commit_children(DeviceTree &t, const mnv_render_options &opt, int n, const float *results_dev,
                            int result_stride, cudaStream_t stream);
+int refine_reduce_children(const DeviceTree &t, const mnv_render_options &opt, int n_children,
+                           const float *results_dev, int result_stride, uint4 *records_dev, cudaStream_t stream);
+int refine_commit_records(DeviceTree &t, const mnv_render_options &opt, int n, const uint4 *records_dev,
+                          cudaStream_t stream);
 int refine_generate_samples(DeviceTree &t, const mnv_render_options &opt, const int32_t *nodes_dev, int m,
                             float *samples_dev, int16_t *cluster_dev, const int32_t *grid_dim,
                             const float *min_position, const float *range, cudaStream_t stream);

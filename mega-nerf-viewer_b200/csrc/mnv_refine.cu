@@ -131,25 +131,46 @@ __global__ void generate_samples_kernel(RefineParams p, const int32_t *__restric
 
 // new leaf payload = mean over the c MLP outputs (torch::mean_out into the fp16 tensor,
 // cuda_renderer.cpp:270), sample_counts = c (:272).  One thread per new leaf slot.
-__global__ void commit_children_kernel(RefineParams p, int n, const float *__restrict__ results,
-                                       int result_stride, int c) {
+// `records` null: the record goes straight into the tree (slot capacity*8 + tid) together with its cell word and
+// count; else only the payload record of child first_child + tid is produced, into records[tid] (multi-GPU: every
+// rank reduces the children whose MLP rows it evaluated, the records are all-gathered and committed everywhere).
+__global__ void commit_children_kernel(RefineParams p, int n_children, const float *__restrict__ results,
+                                       int result_stride, int c, uint4 *__restrict__ records) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n * 8) return;
+    if (tid >= n_children) return;
     const int64_t slot = p.capacity * 8 + tid;
     const float *r = results + (size_t) tid * c * result_stride;
-    __half *rec = reinterpret_cast<__half *>(p.payload + slot * p.rec_u4);
-    const float inv = 1.f / (float) c;
+    __half *rec = reinterpret_cast<__half *>(records ? records + (size_t) tid * p.rec_u4 : p.payload + slot * p.rec_u4);
     __half sig = __float2half(0.f);
     for (int k = 0; k < p.rec_u4 * 8; ++k) {
         float acc = 0.f;
         if (k < p.data_dim)
             for (int s = 0; s < c; ++s) acc += r[s * result_stride + k];
-        const __half h = __float2half_rn(acc * inv);
+        const __half h = __float2half_rn(acc / (float) c);  // torch::mean: sum / c
         rec[k] = k < p.data_dim ? h : __float2half(0.f);
         if (k == p.data_dim - 1) sig = h;
     }
+    if (records) return;
     p.counts[slot] = (int16_t) c;
     p.cell[slot] = make_leaf_cell(__half_as_ushort(sig), c);
+}
+
+// payload records produced elsewhere (commit_children_kernel with `records`) -> the tree's new leaves
+__global__ void commit_records_kernel(RefineParams p, int n_children, const uint4 *__restrict__ records, int c) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;  // one uint4 of one record
+    if (i >= (int64_t) n_children * p.rec_u4) return;
+    const int64_t child = i / p.rec_u4;
+    const int part = (int) (i - child * p.rec_u4);
+    const int64_t slot = p.capacity * 8 + child;
+    const uint4 v = records[i];
+    p.payload[slot * p.rec_u4 + part] = v;
+    const int sig_part = (p.data_dim - 1) / 8, sig_half = (p.data_dim - 1) % 8;
+    if (part == sig_part) {
+        const uint32_t w = sig_half < 2 ? v.x : sig_half < 4 ? v.y : sig_half < 6 ? v.z : v.w;
+        const uint16_t sig = (uint16_t) ((sig_half & 1) ? (w >> 16) : (w & 0xffffu));
+        p.counts[slot] = (int16_t) c;
+        p.cell[slot] = make_leaf_cell(sig, c);
+    }
 }
 
 // running mean: data += (sum(new) - c*data) / (count + c); count += c (cuda_renderer.cpp:318-339)
@@ -315,10 +336,42 @@ int refine_commit_children(DeviceTree &t, const mnv_render_options &opt, int n, 
     }
     const RefineParams p = make_params(t, opt, nullptr, nullptr, nullptr);
     const int th = 128;
-    commit_children_kernel<<<(n * 8 + th - 1) / th, th, 0, stream>>>(p, n, results_dev, result_stride,
-                                                                     opt.samples_per_corner);
+    commit_children_kernel<<<(n * 8 + th - 1) / th, th, 0, stream>>>(p, n * 8, results_dev, result_stride,
+                                                                     opt.samples_per_corner, nullptr);
     MNV_CUDA(cudaGetLastError());
     t.capacity += n;  // cuda_renderer.cpp:275
+    t.pending_children = 0;
+    t.anchor_dirty = true;
+    return MNV_OK;
+}
+
+// Multi-GPU refinement: the mean -> fp16 payload records of n_children new leaves whose MLP
+// rows this rank evaluated (results_dev holds exactly those children's rows); the tree is not touched.
+int refine_reduce_children(const DeviceTree &t, const mnv_render_options &opt, int n_children,
+                           const float *results_dev, int result_stride, uint4 *records_dev, cudaStream_t stream) {
+    if (n_children <= 0) return MNV_OK;
+    const RefineParams p = make_params(t, opt, nullptr, nullptr, nullptr);
+    const int th = 128;
+    commit_children_kernel<<<(n_children + th - 1) / th, th, 0, stream>>>(p, n_children, results_dev, result_stride,
+                                                                          opt.samples_per_corner, records_dev);
+    MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+
+// ... and the gathered records of all n * 8 children committed into this replica.
+int refine_commit_records(DeviceTree &t, const mnv_render_options &opt, int n, const uint4 *records_dev,
+                          cudaStream_t stream) {
+    if (n <= 0) return MNV_OK;
+    if (n != t.pending_children) {
+        set_error("commit of %d children, %d pending", n, t.pending_children);
+        return MNV_ERR_INVALID;
+    }
+    const RefineParams p = make_params(t, opt, nullptr, nullptr, nullptr);
+    const int64_t work = (int64_t) n * 8 * t.rec_u4;
+    commit_records_kernel<<<(unsigned) ((work + 255) / 256), 256, 0, stream>>>(p, n * 8, records_dev,
+                                                                               opt.samples_per_corner);
+    MNV_CUDA(cudaGetLastError());
+    t.capacity += n;
     t.pending_children = 0;
     t.anchor_dirty = true;
     return MNV_OK;

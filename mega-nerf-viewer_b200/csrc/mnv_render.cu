@@ -45,10 +45,10 @@ namespace {
 #define MNV_UNROLL_ANCHOR 1  // loop trips unrolled in the anchor-grid variants
 #endif
 #ifndef MNV_LAZY_EMPTY
-#define MNV_LAZY_EMPTY 0  // candidates from empty leaves kept in registers and committed once per ray (round-2 experiment)
+#define MNV_LAZY_EMPTY 1  // candidates from empty leaves kept in registers and committed once per ray
 #endif
 #ifndef MNV_TRACK_REGS
-#define MNV_TRACK_REGS 0  // candidate trackers in registers instead of shared memory (round-2 experiment)
+#define MNV_TRACK_REGS 1  // candidate trackers in registers instead of shared memory
 #endif
 #ifndef MNV_SMEM_STATE
 #define MNV_SMEM_STATE 1  // park SH basis + shaded-only ray state in shared memory
@@ -56,6 +56,11 @@ namespace {
 constexpr int kThreads = 16 * MNV_TILE_H;  // each warp owns an 8x4-pixel tile
 #ifndef MNV_MIN_BLOCKS
 #define MNV_MIN_BLOCKS (1024 / (16 * MNV_TILE_H))  // resident CTAs per SM the register allocation targets
+#endif
+#ifndef MNV_MIN_BLOCKS_PLAIN
+// without candidate tracking the anchored march fits 56 registers: 9 CTAs per SM (measured 0.940 -> 0.906 ms;
+// the tracking variant spills at that budget and is slower, 1.004 -> 1.036 ms)
+#define MNV_MIN_BLOCKS_PLAIN (MNV_TILE_H == 8 ? 9 : MNV_MIN_BLOCKS)
 #endif
 constexpr int kTileW = 16, kTileH = MNV_TILE_H;  // CTA tile; the multi-GPU partition is a multiple of 16x8
 constexpr int kMaxLevel = 22;    // q carries 23 bits per axis: leaf depth <= 23
@@ -569,7 +574,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
 // TRACK: produce split / re-sample candidates.  LOGV: visit hash/count/log/stats.
 // VISIT: mark visited nodes (track_visit).
 template <int TERMS, bool TRACK, bool LOGV, bool VISIT, bool ANCHOR>
-__global__ void __launch_bounds__(kThreads, MNV_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (ANCHOR && !TRACK && !LOGV && !VISIT) ? MNV_MIN_BLOCKS_PLAIN : MNV_MIN_BLOCKS)
 render_voxels_kernel(const RenderParams p) {
     // [path_levels][kThreads] node path | [TERMS][kThreads] SH basis | [words][kThreads] ray state
     extern __shared__ int32_t s_dyn[];

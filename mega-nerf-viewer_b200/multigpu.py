@@ -236,25 +236,38 @@ class ReplicatedPipeline:
         return self.dt.render_nerf_results(wc, opt, vals, g["z_vals"], g["offsets"], sigma_col=self.data_dim - 1), g["total"]
 
     def refine_frame(self, cam: dict, opt):
-        """One frame with refinement on: own rows rendered with vote tracking, votes all-gathered, the identical
-        split / MLP / commit on every replica.  Returns (RGBA8 block of this rank, nodes added)."""
+        """One frame with refinement on.  Returns (RGBA8 block of this rank, nodes added).
+
+        Per rank: own rows rendered with vote tracking -> the votes reduced to (leaf, priority, count) records
+        (mnv_vote_reduce; a fraction of the rays) -> ONE all-gather of the records (NCCL) -> the identical selection
+        on every replica -> children linked on every replica -> the n*8*c MLP rows SHARDED by child across the
+        ranks -> each rank reduces its children to fp16 payload records -> ONE all-gather of the records (64 B per
+        child) -> committed on every replica.  Replicas stay bit-identical to each other and to the one-GPU
+        sequence (per-row MLP results do not depend on the batch they are evaluated in)."""
         import torch
 
-        from . import select_candidates
+        from . import select_candidates, select_from_votes, vote_reduce
 
         dev = f"cuda:{self.device}"
         W, H = cam["width"], cam["height"]
         first, n = row_block(H, self.world, self.rank)
-        per = row_block(H, self.world, 0)[1]
         wc = window_camera(cam, first, n)
-        ts = torch.full((per * W, 3), -1.0, device=dev)
-        tp = torch.full((per * W, 3), -1.0, device=dev)
+        ts = torch.full((max(n * W, 1), 3), -1.0, device=dev)
+        tp = torch.full((max(n * W, 1), 3), -1.0, device=dev)
         img = self.dt.render(wc, opt, to_split=ts[: n * W], to_sample=tp[: n * W]) if n else None
         if self.world > 1:
-            all_ts = torch.empty((self.world * per * W, 3), device=dev)
-            self.dist.all_gather_into_tensor(all_ts, ts)
-            ts = all_ts
-        nodes, _ = select_candidates(ts, opt.split_batch_size, "split")
+            rec = vote_reduce(ts)  # [r, 3] i32, r known on the host
+            cnt = torch.tensor([rec.shape[0]], device=dev, dtype=torch.int64)
+            self.dist.all_reduce(cnt, op=self.dist.ReduceOp.MAX)
+            rmax = max(int(cnt.item()), 1)
+            send = torch.zeros((rmax, 3), dtype=torch.int32, device=dev)  # votes == 0: padding
+            send[: rec.shape[0]] = rec
+            allrec = torch.empty((self.world * rmax, 3), dtype=torch.int32, device=dev)
+            self.dist.all_gather_into_tensor(allrec, send)
+            self.vote_bytes = int(allrec.numel() * 4)
+            nodes, _ = select_from_votes(allrec, opt.split_batch_size, "split")
+        else:
+            nodes, _ = select_candidates(ts, opt.split_batch_size, "split")
         k = nodes.shape[0]
         self.steps += 1
         if k == 0 or self.dt.capacity + k > self.dt.max_capacity:
@@ -265,9 +278,23 @@ class ReplicatedPipeline:
         samples = torch.rand((k * 8, c, rd), device=dev, generator=g)
         cluster = torch.zeros((k * 8, c), dtype=torch.int16, device=dev)
         self.dt.add_children(opt, nodes, samples, cluster, self.grid_dim, self.min_position, self.range)
-        results = torch.empty((k * 8 * c, self.data_dim + 1), device=dev)
-        self.model.query_submodules(cluster.view(-1), samples.view(-1, rd), results)
-        self.dt.commit_children(opt, k, results.view(k * 8, c, -1))
+        if self.world == 1:
+            results = torch.empty((k * 8 * c, self.data_dim + 1), device=dev)
+            self.model.query_submodules(cluster.view(-1), samples.view(-1, rd), results)
+            self.dt.commit_children(opt, k, results.view(k * 8, c, -1))
+            return img, k
+        per = (k * 8 + self.world - 1) // self.world  # children per rank
+        lo, hi = min(self.rank * per, k * 8), min((self.rank + 1) * per, k * 8)
+        rb = self.dt.record_bytes
+        mine = torch.zeros((per, rb), dtype=torch.uint8, device=dev)
+        if hi > lo:
+            results = torch.empty(((hi - lo) * c, self.data_dim + 1), device=dev)
+            self.model.query_submodules(cluster[lo:hi].reshape(-1), samples[lo:hi].reshape(-1, rd), results)
+            mine[: hi - lo] = self.dt.reduce_children(opt, results.view(hi - lo, c, -1))
+        allp = torch.empty((self.world * per, rb), dtype=torch.uint8, device=dev)
+        self.dist.all_gather_into_tensor(allp, mine)
+        self.payload_bytes = int(allp.numel())
+        self.dt.commit_children_records(opt, k, allp)
         return img, k
 
     def tree_checksum(self) -> int:

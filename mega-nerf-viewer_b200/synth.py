@@ -91,8 +91,10 @@ class HostTree:
         )
 
 
-def height_field(x: np.ndarray, y: np.ndarray, seed: int = 0) -> np.ndarray:
-    """z = f(x, y): sum of 6 seeded sinusoids, |z| <= ~0.55 in world units."""
+def height_field(x: np.ndarray, y: np.ndarray, seed: int = 0, tilt: float = 0.0, amp_scale: float = 1.0) -> np.ndarray:
+    """z = f(x, y): sum of 6 seeded sinusoids, |z| <= ~0.55 in world units (times amp_scale), plus tilt * x.
+    With tilt ~0.75 and amp_scale ~0.4 the surface crosses the whole z extent, so the cells of a (y, z)
+    sub-module grid hold equal shares of it (the flat default leaves the outer z cells empty)."""
     rng = np.random.default_rng(seed)
     amp = rng.uniform(0.04, 0.14, 6)
     kx = rng.uniform(-7.0, 7.0, 6)
@@ -101,10 +103,14 @@ def height_field(x: np.ndarray, y: np.ndarray, seed: int = 0) -> np.ndarray:
     z = np.zeros_like(x, dtype=np.float64)
     for a, u, v, p in zip(amp, kx, ky, ph):
         z += a * np.sin(u * x + v * y + p)
+    if amp_scale != 1.0:
+        z *= amp_scale
+    if tilt != 0.0:
+        z += tilt * x
     return z
 
 
-def _near_surface(ix, iy, iz, level, seed, margin=1.5):
+def _near_surface(ix, iy, iz, level, seed, margin=1.5, tilt=0.0, amp_scale=1.0):
     """Cells (integer coords at `level`) whose centre is within `margin`
     cell-diagonals (vertical distance) of the height field. World box [-1,1]^3."""
     size = 2.0 / (1 << level)
@@ -112,7 +118,7 @@ def _near_surface(ix, iy, iz, level, seed, margin=1.5):
     cy = (iy + 0.5) * size - 1.0
     cz = (iz + 0.5) * size - 1.0
     diag = np.sqrt(3.0) * size
-    return np.abs(cz - height_field(cx, cy, seed)) < margin * diag
+    return np.abs(cz - height_field(cx, cy, seed, tilt, amp_scale)) < margin * diag
 
 
 def make_tree(
@@ -123,6 +129,9 @@ def make_tree(
     block_depths: list[int] | None = None,
     sigma_range: tuple[float, float] = (5.0, 50.0),
     max_nodes: int | None = None,
+    tilt: float = 0.0,
+    amp_scale: float = 1.0,
+    fast_data: bool = False,
 ) -> HostTree:
     """Build the synthetic octree.
 
@@ -130,6 +139,10 @@ def make_tree(
                   are depth 1), i.e. internal nodes exist on levels 0..depth-1.
     blocks_yz     config 3: (gy, gz) grid of Mega-NeRF spatial blocks on the
                   (y, z) axes; block b may use its own ``block_depths[b]``.
+    tilt, amp_scale  shape of the height field (see height_field).
+    fast_data     multi-GB trees: the N(0,1) coefficients repeat a 2^16-node random block (rolled per
+                  chunk) instead of drawing ~4*10^9 normals; sigma is still per leaf.  Traversal does not
+                  depend on the coefficients.
     """
     basis = "".join(ch for ch in data_format if ch.isdigit())
     is_sh = data_format.upper().startswith("SH")
@@ -147,7 +160,7 @@ def make_tree(
         cx = (ix[:, None] * 2 + oi[None, :])
         cy = (iy[:, None] * 2 + oj[None, :])
         cz = (iz[:, None] * 2 + ok[None, :])
-        near = _near_surface(cx, cy, cz, level + 1, seed)
+        near = _near_surface(cx, cy, cz, level + 1, seed, tilt=tilt, amp_scale=amp_scale)
         lim = depth
         if blocks_yz is not None and block_depths is not None:
             gy, gz = blocks_yz
@@ -192,10 +205,16 @@ def make_tree(
 
     rng = np.random.default_rng(seed + 1)
     data = np.empty((cap, 8, data_dim), np.float16)
-    step = 1 << 18
+    step = 1 << (16 if fast_data else 18)
+    base = None
     for s in range(0, cap, step):
         e = min(cap, s + step)
-        blk = rng.standard_normal((e - s, 8, data_dim), dtype=np.float32)
+        if fast_data:
+            if base is None:
+                base = rng.standard_normal((step, 8, data_dim), dtype=np.float32)
+            blk = np.roll(base, (s // step) * 977, axis=0)[: e - s].copy()
+        else:
+            blk = rng.standard_normal((e - s, 8, data_dim), dtype=np.float32)
         if not is_sh:
             blk[..., :3] = 1.0 / (1.0 + np.exp(-blk[..., :3]))  # RGBA stores colours directly
         sig = rng.uniform(sigma_range[0], sigma_range[1], (e - s, 8)).astype(np.float32)

@@ -142,6 +142,51 @@ def test_vote_selection_node_ids_above_2_pow_24(mnv):
     assert (nodes.cpu().numpy()[:, 0] > (1 << 24)).any()
 
 
+def test_sharded_commit_equals_fused_commit(mnv):
+    """Multi-GPU refinement: children reduced in rank-sized pieces and committed from the gathered payload records
+    give the tree the fused mnv_tree_commit_children gives — data, child, parent and counts bit for bit."""
+    import torch
+
+    tree = mnv.synth.make_tree(depth=5)
+    opt = mnv.default_options(background_brightness=0.0, samples_per_corner=6)  # 6: mean is not an exact scale
+    k, c, D = 37, 6, tree.data_dim
+    rng = np.random.default_rng(9)
+    dts = [mnv.DeviceTree(tree, max_capacity=tree.capacity + 64) for _ in range(2)]
+    cam = mnv.synth.default_camera(160, 90, pose=1)
+    ts = torch.empty((160 * 90, 3), device="cuda")
+    tp = torch.empty((160 * 90, 3), device="cuda")
+    dts[0].render(cam, opt, to_split=ts, to_sample=tp)
+    nodes, _ = mnv.select_candidates(ts, k, "split")
+    k = nodes.shape[0]
+    assert k > 8
+    results = torch.from_numpy(rng.standard_normal((k * 8, c, D + 1)).astype(np.float32)).cuda()
+    for dt in dts:
+        samples = torch.rand((k * 8, c, 3), device="cuda")
+        cluster = torch.zeros((k * 8, c), dtype=torch.int16, device="cuda")
+        dt.add_children(opt, nodes, samples, cluster, [1, 1], [-1.0] * 3, [2.0] * 3)
+    dts[0].commit_children(opt, k, results)
+    world = 3
+    per = (k * 8 + world - 1) // world
+    pieces = []
+    for r in range(world):
+        lo, hi = min(r * per, k * 8), min((r + 1) * per, k * 8)
+        piece = torch.zeros((per, dts[1].record_bytes), dtype=torch.uint8, device="cuda")
+        if hi > lo:
+            piece[: hi - lo] = dts[1].reduce_children(opt, results[lo:hi].contiguous())
+        pieces.append(piece)
+    dts[1].commit_children_records(opt, k, torch.cat(pieces))
+    a, b = dts[0].download(), dts[1].download()
+    assert dts[0].capacity == dts[1].capacity == tree.capacity + k
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    # and the march sees the same leaves
+    ia = dts[0].render_logged(cam, opt)
+    ib = dts[1].render_logged(cam, opt)
+    assert np.array_equal(ia["hash"], ib["hash"]) and np.array_equal(ia["rgba"], ib["rgba"])
+    for dt in dts:
+        dt.close()
+
+
 def test_query_submodules_dispatch(mnv):
     import torch
     from mlp_reference import MegaNerfMLP

@@ -20,6 +20,7 @@ ap.add_argument("--steps", type=int, default=48)
 ap.add_argument("--mill19", action="store_true")
 ap.add_argument("--max-nodes", type=int, default=16_000_000)
 ap.add_argument("--tag", default="")
+ap.add_argument("--order", default="rows", choices=["rows", "morton", "cols", "snake"], help="launch order of the 16x8 CTA tiles")
 args = ap.parse_args()
 if args.lib:
     os.environ["MNV_B200_LIB"] = os.path.abspath(args.lib)
@@ -60,6 +61,22 @@ def timed(dt, trackers, steps):
 for a in [int(x) for x in args.anchor.split(",")]:
     os.environ["MNV_ANCHOR_LEVEL"] = str(a)
     dt = mnv.DeviceTree(tree, device=0)
+    if args.order != "rows":
+        tx, ty = (W + 15) // 16, (H + 7) // 8
+        yy, xx = np.mgrid[0:ty, 0:tx]
+        ids = (yy * tx + xx).ravel()
+        if args.order == "cols":
+            key = (xx * ty + yy).ravel()
+        elif args.order == "snake":  # 8x8-tile super blocks, row-major inside
+            key = (((yy // 8) * ((tx + 7) // 8) + xx // 8) * 64 + (yy % 8) * 8 + xx % 8).ravel()
+        else:
+            def spread(v):
+                v = v.astype(np.int64); r = np.zeros_like(v)
+                for b in range(10):
+                    r |= ((v >> b) & 1) << (2 * b)
+                return r
+            key = (spread(xx) | (spread(yy) << 1)).ravel()
+        dt.set_tile_order(torch.from_numpy(ids[np.argsort(key, kind="stable")].astype(np.int32)).cuda())
     crc = 0
     for i in range(16 if not args.mill19 else 4):
         dt.render(cams[i], opt, out=out, to_split=ts, to_sample=tp)
