@@ -454,11 +454,18 @@ def target_sections(args, mnv, torch, dist, rank, world, local_rank):
     # guided sampling, row blocks, replicated (no exchange)
     gopt = mnv.default_options(use_guided_sampling=True, appearance_embedding=0, **opt_kw)
     first, n = mnv.multigpu.row_block(H, world, rank)
-    cap = int(max(1 << 20, n * W * 12))
+    cap = int(max(1 << 20, n * W * 14))
     n_g = 4
     rows = 0
-    for i in range(1):
-        pipe.guided_block(cams[i], gopt, capacity_rows=cap)
+    while True:  # sample-row capacity: the densest pose of the orbit decides
+        try:
+            for i in range(n_g):
+                pipe.guided_block(cams[i], gopt, capacity_rows=cap)
+            break
+        except mnv.MnvError as e:
+            if e.code != 7 or cap > n * W * 40:
+                raise
+            cap = int(cap * 1.5)
     sync()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t0 = time.time()

@@ -95,6 +95,21 @@ typedef struct mnv_tree_desc {
     float offset[3];
 } mnv_tree_desc;
 
+/* VQ-compressed leaf colours (svox `quant_colors` / `quant_map` / `data_retained` / `sigma`,
+ * src/n3tree/n3tree.cpp:109-175): SH basis functions [n_retain, n_retain + n_quant) come from one 65536-entry
+ * codebook each, the first n_retain are stored plainly, sigma is separate.  The reference decodes on the CPU with a
+ * scalar triple loop (and writes `channel * n_basis` without `+ basis`, :145,:161); mnv_tree_create_vq uploads the
+ * compressed arrays (2 B per basis function and leaf instead of 6) and decodes them on the device into the payload
+ * plane, destination index channel * n_basis + basis. */
+typedef struct mnv_vq_desc {
+    int n_quant;                   /* quantised basis functions */
+    int n_retain;                  /* plainly stored ones (0: data_retained may be NULL) */
+    const uint16_t *quant_colors;  /* fp16 bits [n_quant][65536][3] */
+    const uint16_t *quant_map;     /* u16 [n_quant][capacity][8] */
+    const uint16_t *data_retained; /* fp16 bits [n_retain][capacity][8][3] */
+    const uint16_t *sigma;         /* fp16 bits [capacity][8] */
+} mnv_vq_desc;
+
 typedef struct mnv_tree mnv_tree;   /* opaque device tree (SoA planes) */
 typedef struct mnv_model mnv_model; /* opaque Mega-NeRF MLP container */
 
@@ -169,6 +184,10 @@ int mnv_array_download(void *dst_host, void *array, size_t row_bytes, int height
 
 /* ---- tree: N3Tree::move_to_device, src/n3tree/n3tree.cpp:207-246 --------- */
 int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *desc, int64_t max_capacity, int device);
+/* As mnv_tree_create with desc->data == NULL: the leaf payloads come from the VQ arrays, decoded on the device
+ * (SH trees only; desc->data_dim == 3 * (n_quant + n_retain) + 1). */
+int mnv_tree_create_vq(mnv_tree **out, const mnv_tree_desc *desc, const mnv_vq_desc *vq, int64_t max_capacity,
+                       int device);
 int mnv_tree_destroy(mnv_tree *tree);
 int mnv_tree_capacity(const mnv_tree *tree, int64_t *capacity, int64_t *max_capacity);
 int mnv_tree_device_bytes(const mnv_tree *tree, uint64_t *bytes);
@@ -443,6 +462,31 @@ int mnv_composite_partials_guided(mnv_tree *tree, const mnv_camera *cam, const m
 int mnv_ipc_export(void *ptr_dev, uint8_t handle[64]);
 int mnv_ipc_open(const uint8_t handle[64], void **ptr_dev, int device);
 int mnv_ipc_close(void *ptr_dev);
+
+/* ---- replica group: image tiles over the GPUs of one box, driven by ONE process (the viewer's shape) -----------
+ * SURVEY.md §8(e), first mode; the reference is single-GPU (renderer_kernel.cu:17).  The tree is replicated on
+ * every device; replica i marches the interleaved band_rows-row bands b % n == i; finished bands reach devices[0]
+ * as one strided NVLink peer copy per replica, ordered by events on the device (no host synchronisation, no
+ * collective).  The gathered frame — bit-identical to the one-GPU frame — lands in a linear RGBA8 buffer on
+ * devices[0] and / or in the cudaArray behind the GL renderbuffer (image_arr_dev0; cuda_renderer.cpp:432-457). */
+typedef struct mnv_group mnv_group;
+int mnv_group_create(mnv_group **out, const mnv_tree_desc *desc, int64_t max_capacity, const int *devices,
+                     int n_devices);
+int mnv_group_destroy(mnv_group *group);
+int mnv_group_size(const mnv_group *group, int *n);
+int mnv_group_tree(mnv_group *group, int i, mnv_tree **tree); /* replica i, owned by the group */
+int mnv_group_render_frame(mnv_group *group, const mnv_camera *cam, const mnv_render_options *opt,
+                           uint8_t *image_linear_dev0, void *image_arr_dev0, int band_rows);
+int mnv_group_render_frame_host(mnv_group *group, const mnv_camera *cam, const mnv_render_options *opt,
+                                uint8_t *rgba_host, int band_rows);
+int mnv_group_synchronize(mnv_group *group);
+/* One frame with dynamic refinement ON across the group (Impl::render + expand_voxels, cuda_renderer.cpp:68-163,
+ * :205-278): votes of each replica's bands reduced to records and exchanged with peer copies, identical selection
+ * and linking everywhere, MLP rows sharded by child (models[i] lives on replica i's device), fp16 payload records
+ * exchanged and committed everywhere.  All replicas hold the same tree afterwards.  rgba_host may be NULL. */
+int mnv_group_refine_frame(mnv_group *group, mnv_model *const *models, const mnv_camera *cam,
+                           const mnv_render_options *opt, const int32_t grid_dim[2], const float min_position[3],
+                           const float range[3], uint64_t seed, uint8_t *rgba_host, int band_rows, int *nodes_added);
 
 #ifdef __cplusplus
 }

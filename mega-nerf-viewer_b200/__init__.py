@@ -83,6 +83,11 @@ class TreeDesc(C.Structure):
     ]
 
 
+class VqDesc(C.Structure):
+    _fields_ = [("n_quant", C.c_int), ("n_retain", C.c_int), ("quant_colors", C.c_void_p), ("quant_map", C.c_void_p),
+                ("data_retained", C.c_void_p), ("sigma", C.c_void_p)]
+
+
 class FrameStats(C.Structure):
     _fields_ = [("rays", C.c_uint64), ("visits", C.c_uint64), ("shaded_visits", C.c_uint64),
                 ("rays_hit", C.c_uint64)]
@@ -135,6 +140,7 @@ def lib() -> C.CDLL:
     L.mnv_render_options_default.argtypes = [C.POINTER(RenderOptions)]
     L.mnv_render_options_default.restype = None
     L.mnv_tree_create.argtypes = [C.POINTER(vp), C.POINTER(TreeDesc), i64, i32]
+    L.mnv_tree_create_vq.argtypes = [C.POINTER(vp), C.POINTER(TreeDesc), C.POINTER(VqDesc), i64, i32]
     L.mnv_tree_destroy.argtypes = [vp]
     L.mnv_tree_capacity.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     L.mnv_tree_device_bytes.argtypes = [vp, C.POINTER(C.c_uint64)]
@@ -174,6 +180,15 @@ def lib() -> C.CDLL:
     L.mnv_tracker_encode_chunk.restype = C.c_float
     L.mnv_tracker_decode_chunk.argtypes = [C.c_float]
     L.mnv_tracker_decode_chunk.restype = i32
+    L.mnv_group_create.argtypes = [C.POINTER(vp), C.POINTER(TreeDesc), i64, C.POINTER(i32), i32]
+    L.mnv_group_destroy.argtypes = [vp]
+    L.mnv_group_size.argtypes = [vp, C.POINTER(i32)]
+    L.mnv_group_tree.argtypes = [vp, i32, C.POINTER(vp)]
+    L.mnv_group_render_frame.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, i32]
+    L.mnv_group_render_frame_host.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32]
+    L.mnv_group_synchronize.argtypes = [vp]
+    L.mnv_group_refine_frame.argtypes = [vp, C.POINTER(vp), C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp,
+                                         C.c_uint64, vp, i32, C.POINTER(i32)]
     L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
@@ -260,7 +275,10 @@ class DeviceTree:
     """Device-resident N3Tree in the SoA layout (csrc/mnv_internal.cuh)."""
 
     def __init__(self, tree: HostTree, max_capacity: int = 0, device: int = 0,
-                 sample_counts: np.ndarray | None = None):
+                 sample_counts: np.ndarray | None = None, vq: dict | None = None):
+        """vq: dict(quant_colors f16 [n_q, 65536, 3], quant_map u16 [n_q, cap, 8], data_retained f16 [n_r, cap, 8, 3] or
+        None, sigma f16 [cap, 8]) -> the leaf payloads are decoded on the device (mnv_tree_create_vq); tree.data is
+        not read."""
         d = TreeDesc()
         d.N = tree.N
         d.data_dim = tree.data_dim
@@ -280,7 +298,21 @@ class DeviceTree:
         self.data_dim = tree.data_dim
         self.device = device
         self._h = C.c_void_p()
-        _check(lib().mnv_tree_create(C.byref(self._h), C.byref(d), max_capacity, device))
+        if vq is not None:
+            q = VqDesc()
+            book = np.ascontiguousarray(vq["quant_colors"]).view(np.uint16)
+            qmap = np.ascontiguousarray(vq["quant_map"], np.uint16)
+            ret = vq.get("data_retained")
+            ret = None if ret is None or len(ret) == 0 else np.ascontiguousarray(ret).view(np.uint16)
+            sig = np.ascontiguousarray(vq["sigma"]).view(np.uint16)
+            self._keep += [book, qmap, ret, sig]
+            q.n_quant, q.n_retain = qmap.shape[0], 0 if ret is None else ret.shape[0]
+            q.quant_colors, q.quant_map, q.sigma = book.ctypes.data, qmap.ctypes.data, sig.ctypes.data
+            q.data_retained = None if ret is None else ret.ctypes.data
+            d.data = None
+            _check(lib().mnv_tree_create_vq(C.byref(self._h), C.byref(d), C.byref(q), max_capacity, device))
+        else:
+            _check(lib().mnv_tree_create(C.byref(self._h), C.byref(d), max_capacity, device))
         self._keep = None  # host arrays are not referenced after the upload
 
     def close(self):
@@ -583,6 +615,71 @@ class DeviceTree:
             return rgba_host, dict(rays=st.rays, visits=st.visits, shaded_visits=st.shaded_visits,
                                    rays_hit=st.rays_hit)
         return rgba_host
+
+
+class ReplicaGroup:
+    """mnv_group: the tree replicated on several GPUs of one box, driven from this one process (image tiles:
+    interleaved bands per replica, NVLink peer copies into devices[0]; refinement with vote / payload records
+    exchanged by peer copies).  devices may repeat (tests on one GPU)."""
+
+    def __init__(self, tree: HostTree, devices, max_capacity: int = 0):
+        d = TreeDesc()
+        d.N, d.data_dim = tree.N, tree.data_dim
+        d.format = 1 if tree.data_format.upper().startswith("SH") else 0
+        d.basis_dim, d.capacity = tree.basis_dim, tree.capacity
+        keep = [np.ascontiguousarray(tree.data.view(np.uint16)), np.ascontiguousarray(tree.child, np.int32),
+                np.ascontiguousarray(tree.parent, np.int32)]
+        d.data, d.child, d.parent = (a.ctypes.data for a in keep)
+        d.scale[:] = [float(v) for v in tree.scale]
+        d.offset[:] = [float(v) for v in tree.offset]
+        self.devices = [int(x) for x in devices]
+        self.data_dim = tree.data_dim
+        dv = (C.c_int32 * len(self.devices))(*self.devices)
+        self._h = C.c_void_p()
+        _check(lib().mnv_group_create(C.byref(self._h), C.byref(d), max_capacity, dv, len(self.devices)))
+
+    def close(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value and _lib is not None:
+            _lib.mnv_group_destroy(h)
+        self._h = None
+
+    __del__ = close
+
+    def replica(self, i: int) -> "DeviceTree":
+        """Non-owning DeviceTree view of replica i (download / capacity)."""
+        t = DeviceTree.__new__(DeviceTree)
+        h = C.c_void_p()
+        _check(lib().mnv_group_tree(self._h, i, C.byref(h)))
+        t._h, t.device, t.data_dim, t._keep = h, self.devices[i], self.data_dim, None
+        t.close = lambda: None  # owned by the group
+        return t
+
+    def render_frame_host(self, cam, opt, band_rows: int = 8) -> np.ndarray:
+        cam = make_camera(cam)
+        out = np.empty((cam.height, cam.width, 4), np.uint8)
+        _check(lib().mnv_group_render_frame_host(self._h, C.byref(cam), C.byref(opt), out.ctypes.data, band_rows))
+        return out
+
+    def render_frame(self, cam, opt, out, band_rows: int = 8):
+        """out: CUDA uint8 [H, W, 4] on devices[0]; asynchronous (ordered on replica 0's stream)."""
+        cam = make_camera(cam)
+        _check(lib().mnv_group_render_frame(self._h, C.byref(cam), C.byref(opt), _dptr(out), None, band_rows))
+
+    def synchronize(self):
+        _check(lib().mnv_group_synchronize(self._h))
+
+    def refine_frame(self, models, cam, opt, grid_dim, min_position, rng, seed: int = 0x5eed, band_rows: int = 8,
+                     want_frame: bool = True):
+        """models: one MlpModel per replica (on that replica's device) -> (RGBA8 frame or None, leaves split)."""
+        cam = make_camera(cam)
+        out = np.empty((cam.height, cam.width, 4), np.uint8) if want_frame else None
+        keep, g = DeviceTree._grid_args(grid_dim, min_position, rng)
+        mh = (C.c_void_p * len(models))(*[m._h for m in models])
+        k = C.c_int(0)
+        _check(lib().mnv_group_refine_frame(self._h, mh, C.byref(cam), C.byref(opt), g[0], g[1], g[2], seed,
+                                            None if out is None else out.ctypes.data, band_rows, C.byref(k)))
+        return out, k.value
 
 
 def select_candidates(tracker, max_n: int, kind: str = "split", stream=None):

@@ -21,6 +21,10 @@ struct mnv_tree {
     std::map<void *, cudaSurfaceObject_t> surfaces;  // cudaArray_t -> surface, created once
 };
 
+namespace mnv {
+DeviceTree &device_tree_of(mnv_tree *h) { return h->t; }  // for mnv_group.cu
+}  // namespace mnv
+
 namespace {
 
 int check_device(int device) {
@@ -225,14 +229,37 @@ void mnv_render_options_default(mnv_render_options *o) {
     o->max_guided_samples = 128;
 }
 
+static int tree_create_impl(mnv_tree **out, const mnv_tree_desc *d, const mnv_vq_desc *vq, int64_t max_capacity,
+                            int device);
+
 int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *d, int64_t max_capacity, int device) {
+    return tree_create_impl(out, d, nullptr, max_capacity, device);
+}
+
+int mnv_tree_create_vq(mnv_tree **out, const mnv_tree_desc *d, const mnv_vq_desc *vq, int64_t max_capacity, int device) {
+    if (!vq || !d) return MNV_ERR_INVALID;
+    if (vq->n_quant < 0 || vq->n_retain < 0 || vq->n_quant + vq->n_retain < 1 || !vq->sigma ||
+        (vq->n_quant > 0 && (!vq->quant_colors || !vq->quant_map)) || (vq->n_retain > 0 && !vq->data_retained)) {
+        set_error("VQ tree: missing arrays");
+        return MNV_ERR_INVALID;
+    }
+    if (d->format != MNV_FORMAT_SH || d->basis_dim != vq->n_quant + vq->n_retain) {
+        set_error("VQ tree: SH format with basis_dim == n_quant + n_retain expected (got %d, %d + %d)", d->basis_dim,
+                  vq->n_quant, vq->n_retain);
+        return MNV_ERR_FORMAT;
+    }
+    return tree_create_impl(out, d, vq, max_capacity, device);
+}
+
+static int tree_create_impl(mnv_tree **out, const mnv_tree_desc *d, const mnv_vq_desc *vq, int64_t max_capacity,
+                            int device) {
     if (!out || !d) return MNV_ERR_INVALID;
     *out = nullptr;
     if (d->N != 2) {
         set_error("only N == 2 octrees are supported (got N = %d)", d->N);
         return MNV_ERR_INVALID;
     }
-    if (d->capacity <= 0 || !d->data || !d->child || d->data_dim <= 0) {
+    if (d->capacity <= 0 || (!d->data && !vq) || !d->child || d->data_dim <= 0) {
         set_error("empty tree / missing arrays");
         return MNV_ERR_INVALID;
     }
@@ -297,7 +324,7 @@ int mnv_tree_create(mnv_tree **out, const mnv_tree_desc *d, int64_t max_capacity
         if (const char *env = std::getenv("MNV_ANCHOR_LEVEL")) a = std::atoi(env);
         t.anchor_level = std::max(0, std::min(std::min(a, 8), std::max(t.max_leaf_depth, 1)));
     }
-    rc = build_device_tree(t, *d);
+    rc = build_device_tree(t, *d, vq);
     if (rc != MNV_OK) {
         mnv_tree_destroy(h);
         return rc;

@@ -196,7 +196,7 @@ int launch_query_points(const DeviceTree &tree, const float *xyz, int64_t n, int
                         cudaStream_t stream);
 
 const char *last_error_cstr();
-int build_device_tree(DeviceTree &t, const mnv_tree_desc &desc);
+int build_device_tree(DeviceTree &t, const mnv_tree_desc &desc, const mnv_vq_desc *vq = nullptr);
 int download_device_tree(const DeviceTree &t, int64_t first, int64_t count, uint16_t *data,
                          int32_t *child, int32_t *parent, int16_t *sample_counts);
 

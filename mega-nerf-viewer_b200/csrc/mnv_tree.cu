@@ -33,6 +33,28 @@ __global__ void build_cells_kernel(const int32_t *__restrict__ child_aos,
     }
 }
 
+// VQ decode (src/n3tree/n3tree.cpp:109-175 restated for the device): one thread per (slot, basis function) writes the
+// three channels of that basis function into the staged AoS record; the sigma column by the basis-0 thread.
+// map / retained / sigma are the chunk's slices: map[b][n_slots], retained[b][n_slots][3], sigma[n_slots].
+__global__ void vq_decode_kernel(const uint16_t *__restrict__ book, const uint16_t *__restrict__ map,
+                                 const uint16_t *__restrict__ retained, const uint16_t *__restrict__ sigma,
+                                 int64_t n_slots, int n_quant, int n_retain, int data_dim,
+                                 uint16_t *__restrict__ data_aos) {
+    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_basis = n_quant + n_retain;
+    if (i >= n_slots * n_basis) return;
+    const int64_t slot = i / n_basis;
+    const int b = (int) (i - slot * n_basis);
+    const uint16_t *c;
+    if (b < n_retain) c = retained + ((size_t) b * n_slots + slot) * 3;
+    else c = book + ((size_t) (b - n_retain) * 65536 + map[(size_t) (b - n_retain) * n_slots + slot]) * 3;
+    uint16_t *dst = data_aos + slot * data_dim + b;
+    dst[0] = c[0];
+    dst[n_basis] = c[1];
+    dst[2 * n_basis] = c[2];
+    if (b == 0) data_aos[slot * data_dim + data_dim - 1] = sigma[slot];
+}
+
 // One thread per 16-byte chunk of a payload record.
 __global__ void build_payload_kernel(const uint16_t *__restrict__ data_aos, int64_t first_slot,
                                      int64_t n_slots, int data_dim, int rec_u4,
@@ -92,7 +114,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
                                                                           : MNV_ERR_CUDA;
 }
 
-int build_device_tree(DeviceTree &t, const mnv_tree_desc &d) {
+int build_device_tree(DeviceTree &t, const mnv_tree_desc &d, const mnv_vq_desc *vq) {
     const int64_t cap = d.capacity;
     const int D = d.data_dim;
     t.rec_u4 = (D + 7) / 8;
@@ -113,18 +135,44 @@ int build_device_tree(DeviceTree &t, const mnv_tree_desc &d) {
     int32_t *s_child = nullptr;
     uint16_t *s_data = nullptr;
     int16_t *s_counts = nullptr;
+    uint16_t *s_book = nullptr, *s_map = nullptr, *s_ret = nullptr, *s_sig = nullptr;  // VQ staging
     MNV_CUDA(cudaMalloc(&s_child, chunk_nodes * 8 * sizeof(int32_t)));
     MNV_CUDA(cudaMalloc(&s_data, chunk_nodes * 8 * D * sizeof(uint16_t)));
     if (d.sample_counts) MNV_CUDA(cudaMalloc(&s_counts, chunk_nodes * 8 * sizeof(int16_t)));
+    if (vq) {
+        MNV_CUDA(cudaMalloc(&s_book, (size_t) vq->n_quant * 65536 * 3 * sizeof(uint16_t)));
+        MNV_CUDA(cudaMalloc(&s_map, (size_t) std::max(vq->n_quant, 1) * chunk_nodes * 8 * sizeof(uint16_t)));
+        MNV_CUDA(cudaMalloc(&s_ret, (size_t) std::max(vq->n_retain, 1) * chunk_nodes * 8 * 3 * sizeof(uint16_t)));
+        MNV_CUDA(cudaMalloc(&s_sig, (size_t) chunk_nodes * 8 * sizeof(uint16_t)));
+        MNV_CUDA(cudaMemcpyAsync(s_book, vq->quant_colors, (size_t) vq->n_quant * 65536 * 3 * sizeof(uint16_t),
+                                 cudaMemcpyHostToDevice, t.stream));
+    }
     int rc = MNV_OK;
     for (int64_t first = 0; first < cap && rc == MNV_OK; first += chunk_nodes) {
         const int64_t n = std::min(chunk_nodes, cap - first);
         const int64_t slots = n * 8;
         cudaError_t e = cudaMemcpyAsync(s_child, d.child + first * 8, slots * sizeof(int32_t),
                                         cudaMemcpyHostToDevice, t.stream);
-        if (e == cudaSuccess)
+        if (e == cudaSuccess && !vq)
             e = cudaMemcpyAsync(s_data, d.data + first * 8 * D, slots * D * sizeof(uint16_t),
                                 cudaMemcpyHostToDevice, t.stream);
+        if (vq) {
+            // the chunk's slices of the compressed arrays, then the decode fills the staged AoS records
+            for (int b = 0; b < vq->n_quant && e == cudaSuccess; ++b)
+                e = cudaMemcpyAsync(s_map + (size_t) b * slots, vq->quant_map + ((size_t) b * cap + first) * 8,
+                                    slots * sizeof(uint16_t), cudaMemcpyHostToDevice, t.stream);
+            for (int b = 0; b < vq->n_retain && e == cudaSuccess; ++b)
+                e = cudaMemcpyAsync(s_ret + (size_t) b * slots * 3, vq->data_retained + ((size_t) b * cap + first) * 8 * 3,
+                                    slots * 3 * sizeof(uint16_t), cudaMemcpyHostToDevice, t.stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(s_sig, vq->sigma + first * 8, slots * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                    t.stream);
+            if (e == cudaSuccess) {
+                const int64_t work = slots * (vq->n_quant + vq->n_retain);
+                vq_decode_kernel<<<(unsigned) ((work + 255) / 256), 256, 0, t.stream>>>(
+                        s_book, s_map, s_ret, s_sig, slots, vq->n_quant, vq->n_retain, D, s_data);
+            }
+        }
         if (e == cudaSuccess && s_counts)
             e = cudaMemcpyAsync(s_counts, d.sample_counts + first * 8, slots * sizeof(int16_t),
                                 cudaMemcpyHostToDevice, t.stream);
@@ -144,6 +192,10 @@ int build_device_tree(DeviceTree &t, const mnv_tree_desc &d) {
     cudaFree(s_child);
     cudaFree(s_data);
     if (s_counts) cudaFree(s_counts);
+    cudaFree(s_book);
+    cudaFree(s_map);
+    cudaFree(s_ret);
+    cudaFree(s_sig);
     return rc;
 }
 

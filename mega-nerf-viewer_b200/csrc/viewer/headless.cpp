@@ -132,6 +132,7 @@ int main(int argc, char **argv) {
             return 0;
         }
         if (st_load) {  // host-only: checksums of what N3Tree::open produced
+            tree.decode_vq_host();  // host consumers read `data` (the GPU decode is exercised by a render)
             std::printf("{\"N\": %d, \"data_dim\": %d, \"format\": \"%s\", \"basis_dim\": %d, \"capacity\": %d, "
                         "\"scale\": [%.9g, %.9g, %.9g], \"offset\": [%.9g, %.9g, %.9g], "
                         "\"child\": \"%016" PRIx64 "\", \"parent\": \"%016" PRIx64 "\", \"data\": \"%016" PRIx64

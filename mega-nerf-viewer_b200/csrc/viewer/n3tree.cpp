@@ -107,34 +107,22 @@ void N3Tree::open(const std::string &path) {
         if ((int64_t) qm.num_vals() != n_q * dcap * N3_) throw std::runtime_error("quant_map shape does not match the tree");
         if (data_dim != 3 * n_basis + 1) throw std::runtime_error("data_dim does not match the number of quantised basis functions");
         if (sg.word_size != 2 || (int64_t) sg.num_vals() != dcap * N3_) throw std::runtime_error("sigma must be half [cap, N, N, N]");
+        // The compressed arrays are kept; the decode happens on the GPU in move_to_device (mnv_tree_create_vq) and
+        // only on request on the host (decode_vq_host: save(), tools that read `data`).
         data.shape = {dcap, N3_, data_dim};
-        data.v.assign((size_t) dcap * N3_ * data_dim, 0);
-        const uint16_t *map = qm.data<uint16_t>(), *book = qc.data<uint16_t>(), *sig = sg.data<uint16_t>();
-        for (int64_t b = 0; b < n_q; ++b) {
-            const uint16_t *mb = map + b * dcap * N3_, *cb = book + b * 65536 * 3;
-            for (int64_t s = 0; s < dcap * N3_; ++s) {
-                const uint16_t *c = cb + (size_t) mb[s] * 3;
-                uint16_t *dst = data.v.data() + s * data_dim + (n_retain + b);
-                dst[0] = c[0];
-                dst[n_basis] = c[1];
-                dst[2 * n_basis] = c[2];
-            }
-        }
+        data.v.clear();
+        vq_n_quant = (int) n_q;
+        vq_n_retain = (int) n_retain;
+        vq_book.assign(qc.data<uint16_t>(), qc.data<uint16_t>() + qc.num_vals());
+        vq_map.assign(qm.data<uint16_t>(), qm.data<uint16_t>() + qm.num_vals());
+        vq_sigma.assign(sg.data<uint16_t>(), sg.data<uint16_t>() + sg.num_vals());
+        vq_retained.clear();
         if (n_retain) {
             const npz::Array &rt = need("data_retained");
             if (rt.word_size != 2 || (int64_t) rt.num_vals() != n_retain * dcap * N3_ * 3)
                 throw std::runtime_error("data_retained must be half [n_retain, cap, N, N, N, 3]");
-            const uint16_t *r = rt.data<uint16_t>();
-            for (int64_t b = 0; b < n_retain; ++b)
-                for (int64_t s = 0; s < dcap * N3_; ++s) {
-                    const uint16_t *c = r + ((size_t) b * dcap * N3_ + s) * 3;
-                    uint16_t *dst = data.v.data() + s * data_dim + b;
-                    dst[0] = c[0];
-                    dst[n_basis] = c[1];
-                    dst[2 * n_basis] = c[2];
-                }
+            vq_retained.assign(rt.data<uint16_t>(), rt.data<uint16_t>() + rt.num_vals());
         }
-        for (int64_t s = 0; s < dcap * N3_; ++s) data.v[(size_t) s * data_dim + data_dim - 1] = sig[s];
     } else {
         const npz::Array &dn = need("data");
         if (dn.word_size != 2 || dn.shape.empty()) throw std::runtime_error("data must be stored in half precision");
@@ -157,6 +145,34 @@ void N3Tree::open(const std::string &path) {
     std::printf("Data format %s, data size: %d\n", data_format.to_string().c_str(), capacity);
 }
 
+bool N3Tree::is_vq_compressed() const { return vq_n_quant + vq_n_retain > 0 && data.v.empty(); }
+
+// Host decode of a VQ-compressed tree (n3tree.cpp:137-175 with the destination index the format means).
+void N3Tree::decode_vq_host() {
+    if (!is_vq_compressed()) return;
+    const int64_t dcap = data.size(0), n_q = vq_n_quant, n_retain = vq_n_retain, n_basis = n_q + n_retain;
+    data.v.assign((size_t) dcap * N3_ * data_dim, 0);
+    for (int64_t b = 0; b < n_q; ++b) {
+        const uint16_t *mb = vq_map.data() + b * dcap * N3_, *cb = vq_book.data() + b * 65536 * 3;
+        for (int64_t s = 0; s < dcap * N3_; ++s) {
+            const uint16_t *c = cb + (size_t) mb[s] * 3;
+            uint16_t *dst = data.v.data() + s * data_dim + (n_retain + b);
+            dst[0] = c[0];
+            dst[n_basis] = c[1];
+            dst[2 * n_basis] = c[2];
+        }
+    }
+    for (int64_t b = 0; b < n_retain; ++b)
+        for (int64_t s = 0; s < dcap * N3_; ++s) {
+            const uint16_t *c = vq_retained.data() + ((size_t) b * dcap * N3_ + s) * 3;
+            uint16_t *dst = data.v.data() + s * data_dim + b;
+            dst[0] = c[0];
+            dst[n_basis] = c[1];
+            dst[2 * n_basis] = c[2];
+        }
+    for (int64_t s = 0; s < dcap * N3_; ++s) data.v[(size_t) s * data_dim + data_dim - 1] = vq_sigma[(size_t) s];
+}
+
 void N3Tree::move_to_device(long max_capacity, bool /*need_parent*/, bool /*need_sample_counts*/) {
     if (device_tree) {
         mnv_tree_destroy(device_tree);
@@ -170,7 +186,8 @@ void N3Tree::move_to_device(long max_capacity, bool /*need_parent*/, bool /*need
     d.format = data_format.format == DataFormat::SH ? MNV_FORMAT_SH : MNV_FORMAT_RGBA;
     d.basis_dim = data_format.basis_dim;
     d.capacity = cap;
-    d.data = data.data_ptr();
+    const bool vq = is_vq_compressed() && cap == data.size(0);
+    d.data = vq ? nullptr : data.data_ptr();
     d.child = child.data_ptr();
     d.parent = parent.numel() >= cap ? parent.data_ptr() : nullptr;
     d.sample_counts = sample_counts.numel() >= cap * 8 ? sample_counts.data_ptr() : nullptr;
@@ -178,8 +195,22 @@ void N3Tree::move_to_device(long max_capacity, bool /*need_parent*/, bool /*need
         d.scale[i] = scale.v[i];
         d.offset[i] = offset.v[i];
     }
-    if (mnv_tree_create(&device_tree, &d, max_capacity, 0) != MNV_OK)
-        throw std::runtime_error(std::string("move_to_device: ") + mnv_last_error());
+    int rc;
+    if (vq) {  // compressed arrays go up as they are and are decoded on the device
+        mnv_vq_desc q;
+        q.n_quant = vq_n_quant;
+        q.n_retain = vq_n_retain;
+        q.quant_colors = vq_book.data();
+        q.quant_map = vq_map.data();
+        q.data_retained = vq_retained.empty() ? nullptr : vq_retained.data();
+        q.sigma = vq_sigma.data();
+        rc = mnv_tree_create_vq(&device_tree, &d, &q, max_capacity, 0);
+    } else {
+        if (is_vq_compressed()) decode_vq_host();  // host arrays were edited (--bounds_only style): plain path
+        d.data = data.data_ptr();
+        rc = mnv_tree_create(&device_tree, &d, max_capacity, 0);
+    }
+    if (rc != MNV_OK) throw std::runtime_error(std::string("move_to_device: ") + mnv_last_error());
     capacity = (int) cap;
 }
 
@@ -205,9 +236,15 @@ void N3Tree::download() {
     if (mnv_tree_download(device_tree, 0, cap, data.data_ptr(), child.data_ptr(), parent.data_ptr(),
                           sample_counts.data_ptr()) != MNV_OK)
         throw std::runtime_error(std::string("download: ") + mnv_last_error());
+    vq_n_quant = vq_n_retain = 0;  // the host arrays now hold the decoded (and possibly refined) tree
+    vq_book.clear();
+    vq_map.clear();
+    vq_retained.clear();
+    vq_sigma.clear();
 }
 
 void N3Tree::save(const std::string &path) const {
+    if (is_vq_compressed()) const_cast<N3Tree *>(this)->decode_vq_host();  // the file holds plain `data`
     const int64_t cap = child.size(0);
     if (cap == 0 || data.size(0) != cap) throw std::runtime_error("save: empty or inconsistent tree");
     // parent_depth [cap, 2]: packed parent slot, depth of the node (root 0); children follow their parents

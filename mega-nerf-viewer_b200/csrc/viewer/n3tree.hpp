@@ -75,9 +75,16 @@ struct N3Tree {
     // Write the tree in the svox schema open() reads (after download(): the refined tree).  The reference has no
     // writer; `parent_depth` column 1 is recomputed from the links.
     void save(const std::string &path) const;
+    // VQ-compressed files (quant_colors / quant_map / data_retained / sigma, n3tree.cpp:109-175) stay compressed on
+    // the host: move_to_device uploads them as they are and the GPU decodes (mnv_tree_create_vq).  `data` is empty
+    // until decode_vq_host() (or download()) fills it for consumers that read leaf payloads on the host.
+    bool is_vq_compressed() const;
+    void decode_vq_host();
 
    private:
     int N2_ = 0, N3_ = 0;
+    int vq_n_quant = 0, vq_n_retain = 0;
+    std::vector<uint16_t> vq_book, vq_map, vq_retained, vq_sigma;
 };
 
 }  // namespace viewer

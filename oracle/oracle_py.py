@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 import subprocess
 
 import numpy as np
@@ -248,6 +249,44 @@ def composite_nerf(tree, cam: dict, opt: RenderOptions, values, z_vals, offsets,
 # ---------------------------------------------------------------------------
 def ref_available(instr: bool = False) -> bool:
     return os.path.exists(REF_INSTR_SO if instr else REF_SO)
+
+
+def ref_load_host(npz_path: str) -> dict:
+    """The reference's own loader (N3Tree::open + the vendored cnpy, src/n3tree/n3tree.cpp:16-205) on the host: no
+    GPU needed.  Returns the arrays it built, in its layout."""
+    import torch  # noqa: F401  (loads libtorch / libc10 before the driver .so)
+
+    L = C.CDLL(REF_SO)
+    L.ref_open_host.restype = C.c_void_p
+    L.ref_open_host.argtypes = [C.c_char_p]
+    for fn in (L.ref_close, L.ref_capacity, L.ref_data_dim):
+        fn.argtypes = [C.c_void_p]
+    L.ref_download.argtypes = [C.c_void_p] * 6
+    L.ref_sample_counts.argtypes = [C.c_void_p, C.c_void_p]
+    L.ref_format.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    sys.stdout.flush()
+    saved = os.dup(1)  # the reference's loader prints its header dump to stdout
+    os.dup2(2, 1)
+    try:
+        h = L.ref_open_host(npz_path.encode())
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    if not h:
+        raise RuntimeError(f"reference N3Tree::open failed for {npz_path}")
+    cap, D = L.ref_capacity(h), L.ref_data_dim(h)
+    out = dict(capacity=cap, data_dim=D, data=np.empty((cap, 8, D), np.uint16), child=np.empty((cap, 8), np.int32),
+               parent=np.empty(cap, np.int32), scale=np.empty(3, np.float32), offset=np.empty(3, np.float32),
+               sample_counts=np.empty((cap, 8), np.int16))
+    L.ref_download(h, out["data"].ctypes.data, out["child"].ctypes.data, out["parent"].ctypes.data,
+                   out["scale"].ctypes.data, out["offset"].ctypes.data)
+    L.ref_sample_counts(h, out["sample_counts"].ctypes.data)
+    buf = C.create_string_buffer(32)
+    out["basis_dim"] = L.ref_format(h, buf, 32)
+    out["format"] = buf.value.decode()
+    L.ref_close(h)
+    return out
 
 
 class RefRenderer:

@@ -89,6 +89,33 @@ void *ref_open(const char *npz_path, long max_capacity) {
     return c;
 }
 
+// The reference's loader alone (N3Tree::open -> cnpy::npz_load -> load_npz, src/n3tree/n3tree.cpp:16-205), host
+// tensors only: no CUDA call, so the loader cross-check runs on machines without a GPU.  ref_download /
+// ref_sample_counts / ref_capacity / ref_data_dim / ref_format work on such a context; nothing else does.
+void *ref_open_host(const char *npz_path) {
+    auto *c = new RefCtx();
+    c->tree.open(npz_path);
+    if (c->tree.N == 0) {
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+
+// "SH9" / "RGBA" ... as the reference parsed it (data_format.cpp:5-24) -> buf
+int ref_format(void *ctx, char *buf, int n) {
+    const std::string s = static_cast<RefCtx *>(ctx)->tree.data_format.to_string();
+    std::snprintf(buf, (size_t) n, "%s", s.c_str());
+    return static_cast<RefCtx *>(ctx)->tree.data_format.basis_dim;
+}
+
+int ref_sample_counts(void *ctx, int16_t *out) {
+    auto *c = static_cast<RefCtx *>(ctx);
+    auto t = c->tree.sample_counts.slice(0, 0, c->tree.capacity).cpu().contiguous();
+    std::memcpy(out, t.data_ptr(), t.numel() * 2);
+    return 0;
+}
+
 void ref_close(void *ctx) {
     auto *c = static_cast<RefCtx *>(ctx);
     if (!c) return;

@@ -110,6 +110,51 @@ def test_headless_saves_the_refined_tree(mnv, tmp_path):
     dt.close()
 
 
+@pytest.mark.parametrize("n_retain", [0, 2])
+def test_vq_tree_decoded_on_the_gpu(mnv, tmp_path, n_retain):
+    """quant_colors / quant_map / data_retained / sigma (n3tree.cpp:109-175) go to the device
+    compressed and are decoded there — through the C-ABI (mnv_tree_create_vq) and through viewer::N3Tree::open +
+    move_to_device — and equal the numpy decode bit for bit."""
+    tree = mnv.synth.make_tree(depth=5)
+    cap, nb = tree.capacity, 9
+    n_q = nb - n_retain
+    rng = np.random.default_rng(21 + n_retain)
+    book = rng.standard_normal((n_q, 65536, 3)).astype(np.float16)
+    qmap = rng.integers(0, 65536, (n_q, cap, 8), dtype=np.uint16)
+    retained = rng.standard_normal((n_retain, cap, 8, 3)).astype(np.float16)
+    sigma = np.ascontiguousarray(tree.data[..., -1])
+    want = np.zeros((cap, 8, 28), np.float16)
+    for b in range(n_q):
+        col = book[b][qmap[b]]
+        for ch in range(3):
+            want[:, :, ch * nb + n_retain + b] = col[..., ch]
+    for b in range(n_retain):
+        for ch in range(3):
+            want[:, :, ch * nb + b] = retained[b][..., ch]
+    want[:, :, 27] = sigma
+    # C-ABI
+    dt = mnv.DeviceTree(tree, vq=dict(quant_colors=book, quant_map=qmap, data_retained=retained, sigma=sigma))
+    data, child, parent, counts = dt.download()
+    assert np.array_equal(data.view(np.uint16), want.view(np.uint16))
+    assert np.array_equal(child, tree.child) and (counts == 8).all()
+    dt.close()
+    # C++ API: the file stays compressed on the host, the frame equals the one of the decoded tree
+    path, raw = tmp_path / "vq.npz", tmp_path / "f.rgba"
+    np.savez(path, data_dim=np.int64(28), data_format=np.array("SH9"), invradius3=tree.scale, offset=tree.offset,
+             child=tree.child.reshape(cap, 2, 2, 2), parent_depth=np.stack([tree.parent, tree.depth], 1).astype(np.int32),
+             quant_colors=book, quant_map=qmap.reshape(n_q, cap, 2, 2, 2), sigma=sigma.reshape(cap, 2, 2, 2),
+             **({"data_retained": retained.reshape(n_retain, cap, 2, 2, 2, 3)} if n_retain else {}))
+    j = run(mnv, path, "--width", 320, "--height", 180, "--frames", 1, "--poses", 1, "--raw", raw)
+    decoded = mnv.HostTree(N=2, data_dim=28, data_format="SH9", child=tree.child, parent=tree.parent, depth=tree.depth,
+                           data=want, scale=tree.scale, offset=tree.offset)
+    dt = mnv.DeviceTree(decoded)
+    opt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8])
+    img = dt.render(cam_from(j, 320, 180), opt).cpu().numpy()
+    assert np.array_equal(np.fromfile(raw, np.uint8).reshape(180, 320, 4), img)
+    assert img[..., :3].max() > 0
+    dt.close()
+
+
 def test_headless_prunes_when_full(mnv, tmp_path):
     """max_tree_capacity - capacity < split_batch_size triggers Impl::prune_tree
     (cuda_renderer.cpp:146-151).  Visit tracking only starts once capacity > 3/4 max or after a

@@ -65,6 +65,41 @@ def test_loader_invradius_scalar_and_extra_keys(built, tmp_path):
     assert j["capacity"] == cap
 
 
+@pytest.mark.parametrize("variant", ["stored", "deflated", "invradius_scalar", "rgba_deflated"])
+def test_loader_matches_reference_loader(built, oracle, tmp_path, variant):
+    """viewer::N3Tree::open (csrc/viewer/npz.cpp + n3tree.cpp) against the REFERENCE's own N3Tree::open + cnpy
+    (src/n3tree/n3tree.cpp:16-205, 3rdparty/cnpy/cnpy.cpp:303-369, compiled from its sources into oracle/_ref) on
+    the same file: every array the reference builds, byte for byte."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    mnv = built
+    fmt = "RGBA" if variant.startswith("rgba") else "SH9"
+    tree = mnv.synth.make_tree(depth=5, data_format=fmt)
+    cap = tree.capacity
+    path = tmp_path / f"{variant}.npz"
+    if variant == "invradius_scalar":
+        np.savez(path, data_dim=np.int64(tree.data_dim), data_format=np.array(fmt), invradius=np.float64(0.25),
+                 offset=np.array([0.5, 0.25, 0.125], np.float32), child=tree.child.reshape(cap, 2, 2, 2),
+                 parent_depth=np.stack([tree.parent, tree.depth], 1).astype(np.int32),
+                 data=tree.data.reshape(cap, 2, 2, 2, -1), n_internal=np.int64(cap), n_free=np.int64(0),
+                 depth_limit=np.int64(10), geom_resize_fact=np.float64(1.5), extra_data=np.zeros((0, 3), np.float32))
+    else:
+        tree.save_npz(str(path), compressed=variant.endswith("deflated"))
+    ref = oracle.ref_load_host(str(path))
+    r = run(mnv, path, "--selftest-load")
+    assert r.returncode == 0, r.stderr
+    j = last_json(r.stdout)
+    assert (j["data_dim"], j["capacity"], j["format"], j["basis_dim"]) == \
+        (ref["data_dim"], ref["capacity"], ref["format"], ref["basis_dim"])
+    assert j["scale"] == [float(v) for v in ref["scale"]] and j["offset"] == [float(v) for v in ref["offset"]]
+    assert j["child"] == mnv.bytes_checksum(ref["child"])
+    assert j["parent"] == mnv.bytes_checksum(ref["parent"])
+    assert j["data"] == mnv.bytes_checksum(ref["data"])
+    assert j["sample_counts_all_8"] is True and (ref["sample_counts"] == 8).all()
+    # and both equal what numpy wrote
+    assert np.array_equal(ref["child"], tree.child) and np.array_equal(ref["data"], tree.data.view(np.uint16))
+
+
 @pytest.mark.parametrize("n_retain", [0, 1, 3])
 def test_loader_vq_compressed_tree(built, tmp_path, n_retain):
     """quant_colors / quant_map / data_retained / sigma (n3tree.cpp:109-175): basis functions
