@@ -483,10 +483,12 @@ int mnv_group_synchronize(mnv_group *group);
 /* One frame with dynamic refinement ON across the group (Impl::render + expand_voxels, cuda_renderer.cpp:68-163,
  * :205-278): votes of each replica's bands reduced to records and exchanged with peer copies, identical selection
  * and linking everywhere, MLP rows sharded by child (models[i] lives on replica i's device), fp16 payload records
- * exchanged and committed everywhere.  All replicas hold the same tree afterwards.  rgba_host may be NULL. */
+ * exchanged and committed everywhere.  All replicas hold the same tree afterwards.  The frame (marched before the
+ * split, like the reference's) goes to any of the three targets that is not NULL. */
 int mnv_group_refine_frame(mnv_group *group, mnv_model *const *models, const mnv_camera *cam,
                            const mnv_render_options *opt, const int32_t grid_dim[2], const float min_position[3],
-                           const float range[3], uint64_t seed, uint8_t *rgba_host, int band_rows, int *nodes_added);
+                           const float range[3], uint64_t seed, uint8_t *image_linear_dev0, void *image_arr_dev0,
+                           uint8_t *rgba_host, int band_rows, int *nodes_added);
 
 #ifdef __cplusplus
 }

@@ -188,7 +188,7 @@ def lib() -> C.CDLL:
     L.mnv_group_render_frame_host.argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderOptions), vp, i32]
     L.mnv_group_synchronize.argtypes = [vp]
     L.mnv_group_refine_frame.argtypes = [vp, C.POINTER(vp), C.POINTER(Camera), C.POINTER(RenderOptions), vp, vp, vp,
-                                         C.c_uint64, vp, i32, C.POINTER(i32)]
+                                         C.c_uint64, vp, vp, vp, i32, C.POINTER(i32)]
     L.mnv_model_create.argtypes = [C.POINTER(vp), i32, C.POINTER(MlpDesc), vp, vp, vp, i32]
     L.mnv_model_destroy.argtypes = [vp]
     L.mnv_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_double)]
@@ -317,7 +317,7 @@ class DeviceTree:
 
     def close(self):
         h = getattr(self, "_h", None)
-        if h is not None and h.value and _lib is not None:
+        if h is not None and h.value and _lib is not None and getattr(self, "_owned", True):
             _lib.mnv_tree_destroy(h)
         self._h = None
 
@@ -652,7 +652,7 @@ class ReplicaGroup:
         h = C.c_void_p()
         _check(lib().mnv_group_tree(self._h, i, C.byref(h)))
         t._h, t.device, t.data_dim, t._keep = h, self.devices[i], self.data_dim, None
-        t.close = lambda: None  # owned by the group
+        t._owned = False  # the group destroys its replicas
         return t
 
     def render_frame_host(self, cam, opt, band_rows: int = 8) -> np.ndarray:
@@ -677,7 +677,7 @@ class ReplicaGroup:
         keep, g = DeviceTree._grid_args(grid_dim, min_position, rng)
         mh = (C.c_void_p * len(models))(*[m._h for m in models])
         k = C.c_int(0)
-        _check(lib().mnv_group_refine_frame(self._h, mh, C.byref(cam), C.byref(opt), g[0], g[1], g[2], seed,
+        _check(lib().mnv_group_refine_frame(self._h, mh, C.byref(cam), C.byref(opt), g[0], g[1], g[2], seed, None, None,
                                             None if out is None else out.ctypes.data, band_rows, C.byref(k)))
         return out, k.value
 

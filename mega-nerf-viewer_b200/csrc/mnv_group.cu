@@ -56,11 +56,6 @@ using namespace mnv;
 
 namespace {
 
-int for_device(int dev) {
-    MNV_CUDA(cudaSetDevice(dev));
-    return MNV_OK;
-}
-
 cudaStream_t stream_of(mnv_group::Replica &rp) { return device_tree_of(rp.tree).stream; }
 
 // bands b % mod == rem of a [H][row_bytes] image: one strided copy for the complete bands, one for a ragged tail
@@ -274,7 +269,8 @@ int mnv_group_synchronize(mnv_group *g) {
 // split or the tree is full).  Every replica ends the call with the same tree, bit for bit.
 int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_camera *cam, const mnv_render_options *opt,
                            const int32_t grid_dim[2], const float min_position[3], const float range[3], uint64_t seed,
-                           uint8_t *rgba_host, int band_rows, int *nodes_added) {
+                           uint8_t *image_linear_dev0, void *image_arr_dev0, uint8_t *rgba_host, int band_rows,
+                           int *nodes_added) {
     if (!g || !models || !cam || !opt || !grid_dim || !min_position || !range) return MNV_ERR_INVALID;
     if (nodes_added) *nodes_added = 0;
     const int n = (int) g->r.size();
@@ -344,8 +340,8 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
     if (kk > 0) {
         DeviceTree &t0 = device_tree_of(g->r[0].tree);
         if (t0.capacity + kk > t0.max_capacity) {
-            if (rgba_host) return group_deliver(g, cam, nullptr, nullptr, rgba_host);
-            return MNV_OK;  // "Full", cuda_renderer.cpp:228-231
+            rc = group_deliver(g, cam, image_linear_dev0, image_arr_dev0, rgba_host);  // "Full", cuda_renderer.cpp:228-231
+            return rc == MNV_OK ? mnv_group_synchronize(g) : rc;
         }
         const int c = opt->samples_per_corner;
         const int rd = 3 + (opt->need_viewdir ? 3 : 0) + (opt->appearance_embedding != -1 ? 1 : 0);
@@ -420,7 +416,7 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
         }
         if (nodes_added) *nodes_added = kk;
     }
-    if (rgba_host) rc = group_deliver(g, cam, nullptr, nullptr, rgba_host);
+    rc = group_deliver(g, cam, image_linear_dev0, image_arr_dev0, rgba_host);
     // the exchange buffers are read by the peers: nobody may start the next frame's reduction before all copies landed
     if (rc == MNV_OK) rc = mnv_group_synchronize(g);
     return rc;

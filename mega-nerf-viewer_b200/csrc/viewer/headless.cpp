@@ -65,7 +65,7 @@ void print_camera(const Camera &c) {
 
 int main(int argc, char **argv) {
     std::string tree_path, model_path, out_ppm, out_raw, save_path, resave_path;
-    int width = 1920, height = 1080, frames = 16, poses = 16, wire_depth = -1;
+    int width = 1920, height = 1080, frames = 16, poses = 16, wire_depth = -1, gpus = 1, replicas = 0;
     long max_cap = 0;
     bool splitting = false, guided = false, verbose = false, st_load = false, st_camera = false, interop = false;
     float bg = 0.f;
@@ -94,6 +94,8 @@ int main(int argc, char **argv) {
         else if (a == "--selftest-resave") resave_path = val(); // host only: load, write back
         else if (a == "--seed") seed = std::strtoull(val(), nullptr, 0);
         else if (a == "--verbose") verbose = true;
+        else if (a == "--gpus") gpus = std::atoi(val());  // image tiles over this many devices (replica group)
+        else if (a == "--replicas") replicas = std::atoi(val());  // dev/tests: group members, devices wrap around
         else if (a == "--interop") interop = true;  // present through cudaArray surfaces, like the GL viewer does
         else if (a == "--selftest-load") st_load = true;
         else if (a == "--selftest-camera") st_camera = true;
@@ -164,6 +166,14 @@ int main(int argc, char **argv) {
         rend.options.use_splitting = splitting;
         rend.options.use_guided_sampling = guided;
         if (max_cap <= 0) max_cap = (long) tree.capacity + (splitting ? 4 * 4192L * (frames + 4) : 8192);
+        if (gpus > 1 || replicas > 1) {
+            int have = 0;
+            mnv_device_count(&have);
+            if (gpus > have) throw std::runtime_error("--gpus exceeds the visible devices");
+            std::vector<int> devs;
+            for (int i = 0; i < std::max(gpus, replicas); ++i) devs.push_back(i % std::max(gpus, 1));
+            rend.set_devices(devs);
+        }
         rend.set(tree, max_cap);
         if (!model_path.empty()) rend.load_model(model_path);
         // the reference constructs a 256x256 camera and resizes it to the window (main.cpp:593);
@@ -213,6 +223,7 @@ int main(int argc, char **argv) {
             }
         }
         if (!save_path.empty()) {
+            if (gpus > 1 || replicas > 1) throw std::runtime_error("--save is not available with a replica group");
             tree.download();
             tree.save(save_path);
         }

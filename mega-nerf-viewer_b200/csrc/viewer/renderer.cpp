@@ -11,6 +11,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "../../../include/mnv_b200.h"
 #include "model.hpp"
@@ -79,6 +80,8 @@ struct VolumeRenderer::Impl {
             b->release();
         if (frame_pinned) mnv_free_host(frame_pinned);
         if (stream) mnv_stream_destroy(stream);
+        group_models.clear();
+        if (group) mnv_group_destroy(group);
     }
 
     void start() {
@@ -115,7 +118,12 @@ struct VolumeRenderer::Impl {
         start();
         camera._update();
         self.last_frame = FrameInfo();
-        if (tree == nullptr || tree->device_tree == nullptr) return;
+        if (tree == nullptr) return;
+        if (group) {
+            render_group();
+            return;
+        }
+        if (tree->device_tree == nullptr) return;
         mnv_tree *dt = tree->device_tree;
         mnv_camera cam;
         camera.fill(cam);
@@ -177,6 +185,44 @@ struct VolumeRenderer::Impl {
         frame_host_valid = false;
         if (interop) {
             ck(mnv_stream_synchronize(stream), "sync");
+            buf_index ^= 1;
+        }
+    }
+
+    // Multi-GPU frame: interleaved bands on every replica, NVLink gather into devices[0], refinement across the group.
+    void render_group() {
+        mnv_camera cam;
+        camera.fill(cam);
+        init_trackers_if_resized();
+        if (options.use_guided_sampling && !camera.is_dragging())
+            throw std::runtime_error("guided sampling is a single-GPU feature: do not call set_devices()");
+        camera.has_changed();
+        void *image_arr = interop ? ca[buf_index * 2] : nullptr;
+        uint8_t *linear = frame.as<uint8_t>();
+        if (options.use_splitting && !camera.is_dragging()) {
+            if (group_models.empty()) throw std::runtime_error("use_splitting needs load_model()");
+            std::vector<mnv_model *> mh;
+            for (auto &m : group_models) mh.push_back(m->device_model);
+            int added = 0;
+            ck(mnv_group_refine_frame(group, mh.data(), &cam, opt(), group_models[0]->grid_dim,
+                                      group_models[0]->min_position, group_models[0]->range, self.rng_seed, linear,
+                                      image_arr, nullptr, 8, &added),
+               "group refine");
+            frame_host_valid = false;
+            self.last_frame.added = added;
+            self.last_frame.split_candidates = added > 0 ? added : 0;
+        } else {
+            ck(mnv_group_render_frame(group, &cam, opt(), linear, image_arr, 8), "group frame");
+            frame_host_valid = false;
+        }
+        mnv_tree *t0 = nullptr;
+        ck(mnv_group_tree(group, 0, &t0), "group tree");
+        int64_t c = 0, m = 0;
+        mnv_tree_capacity(t0, &c, &m);
+        tree->capacity = (int) c;
+        self.last_frame.capacity = c;
+        if (interop) {
+            ck(mnv_group_synchronize(group), "sync");
             buf_index ^= 1;
         }
     }
@@ -328,6 +374,10 @@ struct VolumeRenderer::Impl {
     // Impl::set, cuda_renderer.cpp:498-516
     void set(N3Tree &t, long max_capacity) {
         start();
+        if (devices.size() > 1) {
+            set_group(t, max_capacity);
+            return;
+        }
         t.move_to_device(max_capacity, true, true);
         tree = &t;
         int64_t c = 0, m = 0;
@@ -342,8 +392,56 @@ struct VolumeRenderer::Impl {
         prune_happened = false;
     }
 
+    // replicas on every device of the group, built from the host arrays (VQ files are decoded on the host here)
+    void set_group(N3Tree &t, long max_capacity) {
+        if (group) {
+            mnv_group_destroy(group);
+            group = nullptr;
+        }
+        t.decode_vq_host();
+        const int64_t cap = t.child.size(0);
+        mnv_tree_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.N = t.N;
+        d.data_dim = t.data_dim;
+        d.format = t.data_format.format == DataFormat::SH ? MNV_FORMAT_SH : MNV_FORMAT_RGBA;
+        d.basis_dim = t.data_format.basis_dim;
+        d.capacity = cap;
+        d.data = t.data.data_ptr();
+        d.child = t.child.data_ptr();
+        d.parent = t.parent.numel() >= cap ? t.parent.data_ptr() : nullptr;
+        d.sample_counts = t.sample_counts.numel() >= cap * 8 ? t.sample_counts.data_ptr() : nullptr;
+        for (int i = 0; i < 3; ++i) {
+            d.scale[i] = t.scale.v[i];
+            d.offset[i] = t.offset.v[i];
+        }
+        ck(mnv_group_create(&group, &d, max_capacity, devices.data(), (int) devices.size()), "group create");
+        tree = &t;
+        mnv_tree *t0 = nullptr;
+        ck(mnv_group_tree(group, 0, &t0), "group tree");
+        int64_t c = 0, m = 0;
+        mnv_tree_capacity(t0, &c, &m);
+        max_tree_capacity = m;
+        t.capacity = (int) c;
+        options.basis_minmax[0] = 0;
+        options.basis_minmax[1] = std::max(t.data_format.basis_dim - 1, 0);
+        can_reuse_results = false;
+        prune_happened = false;
+    }
+
     void load_model(const std::filesystem::path &path) {
         if (self.verbose) std::printf("Loading model from: %s\n", path.c_str());
+        if (devices.size() > 1) {  // one copy of the sub-modules per device of the group (1.2 MB of bf16 each)
+            group_models.clear();
+            for (int dev : devices) {
+                group_models.push_back(std::make_unique<ModelContainer>());
+                group_models.back()->load(path.string(), dev);
+            }
+            options.need_viewdir = group_models[0]->need_viewdir;
+            if (options.appearance_embedding == -1 && group_models[0]->need_appearance_embedding)
+                options.appearance_embedding = 0;
+            return;
+        }
         model.load(path.string(), 0);
         options.need_viewdir = model.need_viewdir;
         if (options.appearance_embedding == -1 && model.need_appearance_embedding) options.appearance_embedding = 0;
@@ -356,6 +454,9 @@ struct VolumeRenderer::Impl {
     RenderOptions &options;
     N3Tree *tree = nullptr;
     ModelContainer model;
+    std::vector<int> devices;  // set_devices(): more than one -> replica group
+    mnv_group *group = nullptr;
+    std::vector<std::unique_ptr<ModelContainer>> group_models;
     void *stream = nullptr;
     bool started = false;
     bool initial_resize = true;
@@ -392,6 +493,8 @@ void VolumeRenderer::set_interop_surfaces(void *const cuda_arrays[4]) {
     for (int i = 0; i < 4; ++i) impl_->ca[i] = cuda_arrays ? cuda_arrays[i] : nullptr;
     impl_->buf_index = 0;
 }
+
+void VolumeRenderer::set_devices(const std::vector<int> &devices) { impl_->devices = devices; }
 
 const uint8_t *VolumeRenderer::frame_device() const { return impl_->frame.as<uint8_t>(); }
 

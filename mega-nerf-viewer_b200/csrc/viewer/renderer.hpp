@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <filesystem>
 #include <memory>
+#include <vector>
 
 #include "camera.hpp"
 #include "n3tree.hpp"
@@ -51,6 +52,13 @@ struct VolumeRenderer {
     // fake-depth (R32F) renderbuffers, in the order of Impl::ca (cuda_renderer.cpp:447-455).
     // With surfaces set, render() writes there with offscreen=false compositing.
     void set_interop_surfaces(void *const cuda_arrays[4]);
+    // Multi-GPU (image tiles with the tree replicated): call before set().  The tree is replicated
+    // on every listed device (mnv_group); render() marches interleaved 8-row bands on all of them and gathers the
+    // bands over NVLink peer copies into devices[0] — the headless frame or the GL-interop colour surface — and, with
+    // options.use_splitting, runs the refinement step across the group (votes and fp16 payloads exchanged by peer
+    // copies, MLP rows sharded; load_model() places a copy of the sub-modules on every device).  Guided sampling
+    // and pruning stay single-GPU features: with a group they are not available (render() throws / never prunes).
+    void set_devices(const std::vector<int> &devices);
     // Headless: the frame render() produced, read back to host memory ([height][width][4]).
     const uint8_t *frame_host();
     // Device pointer of that frame (RGBA8 linear), valid until the next resize.

@@ -155,6 +155,28 @@ def test_vq_tree_decoded_on_the_gpu(mnv, tmp_path, n_retain):
     dt.close()
 
 
+def test_headless_replica_group_frames_and_refinement(mnv, tmp_path):
+    """viewer::VolumeRenderer::set_devices (C++ multi-GPU host path, csrc/mnv_group.cu): the gathered frame equals the
+    one-GPU frame bit for bit — headless and through the interop surface — and refinement across three replicas
+    reproduces itself (same seed, same frame hash and capacity)."""
+    tree = mnv.synth.make_tree(depth=6)
+    path, mpath = tmp_path / "t.npz", tmp_path / "m.npz"
+    tree.save_npz(str(path))
+    make_model(mnv, mpath)
+    one = run(mnv, path, "--width", 400, "--height", 232, "--frames", 2, "--poses", 1)
+    grp = run(mnv, path, "--width", 400, "--height", 232, "--frames", 2, "--poses", 1, "--replicas", 3)
+    assert grp["frame_hash"] == one["frame_hash"]
+    grp_i = run(mnv, path, "--width", 400, "--height", 232, "--frames", 2, "--poses", 1, "--replicas", 3, "--interop")
+    one_i = run(mnv, path, "--width", 400, "--height", 232, "--frames", 2, "--poses", 1, "--interop")
+    assert grp_i["frame_hash"] == one_i["frame_hash"] == one["frame_hash"]
+    args = ("--model", mpath, "--width", 400, "--height", 232, "--frames", 4, "--poses", 1, "--use_splitting",
+            "--max_tree_capacity", tree.capacity + 40000, "--replicas", 3)
+    a, b = run(mnv, path, *args), run(mnv, path, *args)
+    # (the two warm-up frames refine too: capacity grows by more than the timed frames' count)
+    assert a["nodes_added"] > 0 and tree.capacity + a["nodes_added"] <= a["capacity"] <= tree.capacity + 40000
+    assert a["frame_hash"] == b["frame_hash"] and a["capacity"] == b["capacity"]
+
+
 def test_headless_prunes_when_full(mnv, tmp_path):
     """max_tree_capacity - capacity < split_batch_size triggers Impl::prune_tree
     (cuda_renderer.cpp:146-151).  Visit tracking only starts once capacity > 3/4 max or after a
