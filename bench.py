@@ -445,8 +445,9 @@ def target_sections(args, mnv, torch, dist, rank, world, local_rank):
                          "timing": "host clock around the frame (march with vote tracking -> vote exchange -> selection -> "
                                    "4096 splits x 8 children x 8 samples -> 8 sub-MLPs -> commit), max over ranks, median",
                          "parallelism": "one GPU" if world == 1 else
-                         f"row blocks over {world} GPUs, tree + sub-MLPs replicated; vote records and fp16 payloads "
-                         "all-gathered (NCCL), MLP rows sharded by child",
+                         f"interleaved {BAND_ROWS}-row bands over {world} GPUs, tree + sub-MLPs replicated; vote records "
+                         "and fp16 payloads all-gathered (NCCL), MLP rows sharded by child",
+                         "stage_ms_per_frame": ({k: v / (n_ref + 3) for k, v in pipe.stages.items()} if pipe.stages else None),
                          "exchange_bytes_per_frame": None if world == 1 else
                          {"vote_records_all_gather": getattr(pipe, "vote_bytes", None),
                           "payload_records_all_gather": getattr(pipe, "payload_bytes", None)},
@@ -460,7 +461,7 @@ def target_sections(args, mnv, torch, dist, rank, world, local_rank):
     while True:  # sample-row capacity: the densest pose of the orbit decides
         try:
             for i in range(n_g):
-                pipe.guided_block(cams[i], gopt, capacity_rows=cap)
+                pipe.guided_blocks(cams[i], gopt, capacity_rows=cap)
             break
         except mnv.MnvError as e:
             if e.code != 7 or cap > n * W * 40:
@@ -474,7 +475,7 @@ def target_sections(args, mnv, torch, dist, rank, world, local_rank):
         flush.fill_(i & 0xff)
         sync()
         t1 = time.perf_counter()
-        _, r = pipe.guided_block(cams[i % N_POSES], gopt, capacity_rows=cap)
+        _, r = pipe.guided_blocks(cams[i % N_POSES], gopt, capacity_rows=cap)
         torch.cuda.synchronize()
         ms.append((time.perf_counter() - t1) * 1e3)
         rows += r
@@ -491,7 +492,7 @@ def target_sections(args, mnv, torch, dist, rank, world, local_rank):
                               "timing": "host clock around the frame (emission -> per-sample MLP over 8 sub-modules -> "
                                         "per-ray compositing) incl. the row-count sync, max over ranks, median",
                               "parallelism": "one GPU" if world == 1 else
-                              f"row blocks over {world} GPUs, tree + sub-MLPs replicated, no exchange",
+                              f"{4 * world} row blocks dealt round-robin over {world} GPUs, tree + sub-MLPs replicated, no exchange",
                               "clocks": clocks}
     pipe.close()
     return out

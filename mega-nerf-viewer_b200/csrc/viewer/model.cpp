@@ -16,11 +16,11 @@ long scalar_int(const npz::Array &a) {
         case '?': return a.bytes[0] != 0;
         case 'i':
         case 'u':
-            if (a.word_size == 8) return (long) *a.data<int64_t>();
-            if (a.word_size == 4) return *a.data<int32_t>();
-            if (a.word_size == 2) return *a.data<int16_t>();
-            return *a.data<int8_t>();
-        case 'f': return a.word_size == 8 ? (long) *a.data<double>() : (long) *a.data<float>();
+            if (a.word_size == 8) return (long) *a.checked<int64_t>(1, "scalar");
+            if (a.word_size == 4) return *a.checked<int32_t>(1, "scalar");
+            if (a.word_size == 2) return *a.checked<int16_t>(1, "scalar");
+            return *a.checked<int8_t>(1, "scalar");
+        case 'f': return a.word_size == 8 ? (long) *a.checked<double>(1, "scalar") : (long) *a.checked<float>(1, "scalar");
     }
     throw std::runtime_error("model container: unsupported scalar type");
 }
@@ -37,7 +37,7 @@ const float *f32(const npz::Archive &z, const std::string &key, size_t n_expecte
     if (n_expected && a.num_vals() != n_expected)
         throw std::runtime_error("model container: " + key + " has " + std::to_string(a.num_vals()) +
                                  " values, expected " + std::to_string(n_expected));
-    return a.data<float>();
+    return a.checked<float>(a.num_vals(), key.c_str());
 }
 
 }  // namespace
@@ -56,8 +56,9 @@ void ModelContainer::load(const std::string &path, int device) {
     {
         const npz::Array &g = need(z, "grid_dim");
         if (g.num_vals() != 2) throw std::runtime_error("model container: grid_dim must have 2 entries");
+        if (g.kind != 'i' && g.kind != 'u') throw std::runtime_error("model container: grid_dim must be an integer array");
         for (int i = 0; i < 2; ++i)
-            grid_dim[i] = g.word_size == 8 ? (int32_t) g.data<int64_t>()[i] : g.data<int32_t>()[i];
+            grid_dim[i] = g.word_size == 8 ? (int32_t) g.checked<int64_t>(2, "grid_dim")[i] : g.checked<int32_t>(2, "grid_dim")[i];
     }
     std::memcpy(min_position, f32(z, "min_position", 3), 12);
     std::memcpy(max_position, f32(z, "max_position", 3), 12);
@@ -78,7 +79,7 @@ void ModelContainer::load(const std::string &path, int device) {
         std::memset(&d, 0, sizeof(d));
         const npz::Array &cfg = need(z, p + "config");
         if (cfg.num_vals() < 5 || cfg.word_size != 4) throw std::runtime_error("model container: bad " + p + "config");
-        const int32_t *c = cfg.data<int32_t>();
+        const int32_t *c = cfg.checked<int32_t>(5, "config");
         d.n_trunk_layers = c[0];
         d.skip_layer = c[1];
         d.pe_xyz_freqs = c[2];

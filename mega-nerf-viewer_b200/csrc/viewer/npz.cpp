@@ -163,7 +163,7 @@ Archive load(const std::string &path) {
     uint64_t n_entries = rd16(&buf[eocd + 10]), cd_off = rd32(&buf[eocd + 16]);
     if (eocd >= 20 && rd32(&buf[eocd - 20]) == 0x07064b50) {  // ZIP64 locator
         const uint64_t z64 = rd64(&buf[eocd - 20 + 8]);
-        if (z64 + 56 > size || rd32(&buf[z64]) != 0x06064b50) fail("bad ZIP64 end record");
+        if (z64 > size || size - z64 < 56 || rd32(&buf[z64]) != 0x06064b50) fail("bad ZIP64 end record");
         n_entries = rd64(&buf[z64 + 32]);
         cd_off = rd64(&buf[z64 + 48]);
     }
@@ -203,6 +203,9 @@ Archive load(const std::string &path) {
         if (data > size || csize > size - data) fail("member " + name + " runs past the end of the file");
         if (method == 0 && usize != csize) fail("stored member " + name + " with different sizes");
         if (usize > (uint64_t(1) << 40)) fail("member " + name + " is implausibly large");
+        // raw deflate expands by at most ~1032x: a larger claim is a corrupt (or hostile) header, refused before
+        // the output buffer is allocated
+        if (method != 0 && usize / 1040 > csize + 64) fail("member " + name + " declares an impossible inflated size");
         if (name.size() > 4 && name.compare(name.size() - 4, 4, ".npy") == 0) name.resize(name.size() - 4);
         if (method == 0) {
             check_crc(&buf[data], (size_t) usize, want_crc, name);

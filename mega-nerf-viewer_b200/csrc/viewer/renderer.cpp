@@ -215,16 +215,16 @@ struct VolumeRenderer::Impl {
             ck(mnv_group_render_frame(group, &cam, opt(), linear, image_arr, 8), "group frame");
             frame_host_valid = false;
         }
+        // the gathered frame was produced on the replicas' streams: frame_host() / the GL blit read it from another
+        // stream, so the frame is completed here (one host synchronisation per frame)
+        ck(mnv_group_synchronize(group), "group sync");
         mnv_tree *t0 = nullptr;
         ck(mnv_group_tree(group, 0, &t0), "group tree");
         int64_t c = 0, m = 0;
         mnv_tree_capacity(t0, &c, &m);
         tree->capacity = (int) c;
         self.last_frame.capacity = c;
-        if (interop) {
-            ck(mnv_group_synchronize(group), "sync");
-            buf_index ^= 1;
-        }
+        if (interop) buf_index ^= 1;
     }
 
     void init_trackers_if_resized() {

@@ -202,6 +202,17 @@ def row_block(height: int, world: int, rank: int):
     return first, max(0, min(per, height - first))
 
 
+def row_blocks(height: int, world: int, rank: int, parts: int = 4):
+    """[(first, n)]: the frame cut into parts * world row blocks (multiples of 8 rows), dealt round-robin."""
+    m = parts * world
+    per = ((height + m - 1) // m + 7) // 8 * 8
+    out = []
+    for b in range(rank, m, world):
+        first = min(b * per, height)
+        out.append((first, max(0, min(per, height - first))))
+    return out
+
+
 def window_camera(cam: dict, first_row: int, n_rows: int) -> dict:
     """The camera of rows [first_row, first_row + n_rows): identical rays, bit for bit, when cy is a multiple of 0.5."""
     return dict(cam, height=int(n_rows), cy=float(cam["cy"]) - float(first_row))
@@ -221,12 +232,19 @@ class ReplicatedPipeline:
         self.range = [float(b) - float(a) for a, b in zip(min_position, max_position)]
         self.data_dim = tree.data_dim
         self.steps = 0
+        import os
+        self.stage_timing = os.environ.get("MNV_STAGE_TIMING") == "1"
+        self.stages = {}
 
     def guided_block(self, cam: dict, opt, capacity_rows=None):
-        """RGBA8 [rows of this rank, W, 4] of the guided-sampling frame."""
+        """RGBA8 [rows of this rank, W, 4] of the guided-sampling frame (one contiguous row block per rank)."""
+        first, n = row_block(cam["height"], self.world, self.rank)
+        out, total = self._guided_rows(cam, opt, first, n, capacity_rows)
+        return out, total
+
+    def _guided_rows(self, cam, opt, first, n, capacity_rows):
         import torch
 
-        first, n = row_block(cam["height"], self.world, self.rank)
         wc = window_camera(cam, first, n)
         cap = capacity_rows or max(1 << 16, n * cam["width"] * 24)
         g = self.dt.guided_samples(wc, opt, self.grid_dim, self.min_position, self.range, capacity_rows=cap)
@@ -235,28 +253,64 @@ class ReplicatedPipeline:
             self.model.query_submodules(g["cluster"], g["rows"], vals)
         return self.dt.render_nerf_results(wc, opt, vals, g["z_vals"], g["offsets"], sigma_col=self.data_dim - 1), g["total"]
 
-    def refine_frame(self, cam: dict, opt):
-        """One frame with refinement on.  Returns (RGBA8 block of this rank, nodes added).
+    def guided_blocks(self, cam: dict, opt, capacity_rows=None, parts: int = 4):
+        """This rank's share of the guided-sampling frame: list of (first_row, RGBA8 [rows, W, 4]) sub-blocks and the
+        MLP rows evaluated.  The frame is cut into parts * world row blocks dealt round-robin (sky and ground rows
+        cost very different amounts: contiguous halves left one GPU with most of the samples); each sub-block is
+        emitted, evaluated and composited on its own through a windowed camera — no exchange."""
+        out, total = [], 0
+        for first, n in row_blocks(cam["height"], self.world, self.rank, parts if self.world > 1 else 1):
+            if n == 0:
+                continue
+            img, rows = self._guided_rows(cam, opt, first, n, capacity_rows)
+            out.append((first, img))
+            total += rows
+        return out, total
 
-        Per rank: own rows rendered with vote tracking -> the votes reduced to (leaf, priority, count) records
-        (mnv_vote_reduce; a fraction of the rays) -> ONE all-gather of the records (NCCL) -> the identical selection
-        on every replica -> children linked on every replica -> the n*8*c MLP rows SHARDED by child across the
-        ranks -> each rank reduces its children to fp16 payload records -> ONE all-gather of the records (64 B per
-        child) -> committed on every replica.  Replicas stay bit-identical to each other and to the one-GPU
-        sequence (per-row MLP results do not depend on the batch they are evaluated in)."""
+    def _stage(self, name, t0=None):
+        """MNV_STAGE_TIMING=1: synchronising per-stage clock (dev; the timed numbers of bench.py run without it)."""
+        import time
+        import torch
+
+        if not self.stage_timing:
+            return None
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if t0 is not None:
+            self.stages[name] = self.stages.get(name, 0.0) + (now - t0) * 1e3
+        return now
+
+    def refine_frame(self, cam: dict, opt, band_rows: int = 8):
+        """One frame with refinement on.  Returns (RGBA8 [H, W, 4] with this rank's bands filled, nodes added).
+
+        Per rank: its interleaved bands (b % world == rank, like the image-tile mode: balanced whatever the scene)
+        marched with vote tracking -> the votes reduced to (leaf, priority, count) records (mnv_vote_reduce; a
+        fraction of the rays) -> ONE all-gather of the records (NCCL) -> the identical selection on every replica ->
+        children linked on every replica -> the n*8*c MLP rows SHARDED by child across the ranks -> each rank reduces
+        its children to fp16 payload records -> ONE all-gather of the records (64 B per child) -> committed on every
+        replica.  Replicas stay bit-identical to each other and to the one-GPU sequence (per-row MLP results do not
+        depend on the batch they are evaluated in)."""
         import torch
 
         from . import select_candidates, select_from_votes, vote_reduce
 
         dev = f"cuda:{self.device}"
         W, H = cam["width"], cam["height"]
-        first, n = row_block(H, self.world, self.rank)
-        wc = window_camera(cam, first, n)
-        ts = torch.full((max(n * W, 1), 3), -1.0, device=dev)
-        tp = torch.full((max(n * W, 1), 3), -1.0, device=dev)
-        img = self.dt.render(wc, opt, to_split=ts[: n * W], to_sample=tp[: n * W]) if n else None
+        P = W * H
+        if getattr(self, "_ts", None) is None or self._ts.shape[0] != P:
+            self._ts = torch.empty((P, 3), device=dev)
+            self._tp = torch.empty((P, 3), device=dev)
+            self._img = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+        ts, tp, img = self._ts, self._tp, self._img
+        t = self._stage("begin")
         if self.world > 1:
-            rec = vote_reduce(ts)  # [r, 3] i32, r known on the host
+            ts.fill_(-1.0)  # rows of the other ranks' bands: no candidate
+            tp.fill_(-1.0)
+            self.dt.render_tiles(cam, opt, img, ((W + 15) // 16) * 16, band_rows, self.world, self.rank, to_split=ts,
+                                 to_sample=tp)
+            t = self._stage("march (own bands, vote tracking)", t)
+            rec = vote_reduce(ts, cap_records=P // self.world + W * band_rows + 1024)  # [r, 3] i32, r known on the host
+            t = self._stage("vote reduce", t)
             cnt = torch.tensor([rec.shape[0]], device=dev, dtype=torch.int64)
             self.dist.all_reduce(cnt, op=self.dist.ReduceOp.MAX)
             rmax = max(int(cnt.item()), 1)
@@ -265,9 +319,13 @@ class ReplicatedPipeline:
             allrec = torch.empty((self.world * rmax, 3), dtype=torch.int32, device=dev)
             self.dist.all_gather_into_tensor(allrec, send)
             self.vote_bytes = int(allrec.numel() * 4)
+            t = self._stage("vote records all-gather", t)
             nodes, _ = select_from_votes(allrec, opt.split_batch_size, "split")
         else:
+            self.dt.render(cam, opt, out=img, to_split=ts, to_sample=tp)
+            t = self._stage("march (own bands, vote tracking)", t)
             nodes, _ = select_candidates(ts, opt.split_batch_size, "split")
+        t = self._stage("selection", t)
         k = nodes.shape[0]
         self.steps += 1
         if k == 0 or self.dt.capacity + k > self.dt.max_capacity:
@@ -278,10 +336,13 @@ class ReplicatedPipeline:
         samples = torch.rand((k * 8, c, rd), device=dev, generator=g)
         cluster = torch.zeros((k * 8, c), dtype=torch.int16, device=dev)
         self.dt.add_children(opt, nodes, samples, cluster, self.grid_dim, self.min_position, self.range)
+        t = self._stage("rand + add children", t)
         if self.world == 1:
             results = torch.empty((k * 8 * c, self.data_dim + 1), device=dev)
             self.model.query_submodules(cluster.view(-1), samples.view(-1, rd), results)
+            t = self._stage("query_submodules", t)
             self.dt.commit_children(opt, k, results.view(k * 8, c, -1))
+            self._stage("commit", t)
             return img, k
         per = (k * 8 + self.world - 1) // self.world  # children per rank
         lo, hi = min(self.rank * per, k * 8), min((self.rank + 1) * per, k * 8)
@@ -291,10 +352,12 @@ class ReplicatedPipeline:
             results = torch.empty(((hi - lo) * c, self.data_dim + 1), device=dev)
             self.model.query_submodules(cluster[lo:hi].reshape(-1), samples[lo:hi].reshape(-1, rd), results)
             mine[: hi - lo] = self.dt.reduce_children(opt, results.view(hi - lo, c, -1))
+        t = self._stage("query_submodules", t)
         allp = torch.empty((self.world * per, rb), dtype=torch.uint8, device=dev)
         self.dist.all_gather_into_tensor(allp, mine)
         self.payload_bytes = int(allp.numel())
         self.dt.commit_children_records(opt, k, allp)
+        self._stage("payload all-gather + commit", t)
         return img, k
 
     def tree_checksum(self) -> int:

@@ -32,18 +32,20 @@ def main():
     cap = tree.capacity + 4000
     pipe = MG.ReplicatedPipeline(tree, subs, grid, mn, mx, rank=rank, world=world, device=local, dist=dist, max_capacity=cap)
     solo = MG.ReplicatedPipeline(tree, subs, grid, mn, mx, device=local, max_capacity=cap) if rank == 0 else None
-    per = MG.row_block(h, world, 0)[1]
-
-    def gather_frame(block):
-        padded = torch.zeros((per, w, 4), dtype=torch.uint8, device=f"cuda:{local}")
-        if block is not None:
-            padded[: block.shape[0]] = block
-        parts = [torch.empty_like(padded) for _ in range(world)] if rank == 0 else None
-        dist.gather(padded, parts, dst=0)
-        return torch.cat(parts)[:h].cpu().numpy() if rank == 0 else None
+    def gather_frame(pieces):
+        """pieces: [(first_row, rows tensor)] or a full-size frame with only this rank's bands filled (the rest zero):
+        the partitions are disjoint, so the sum over ranks is the frame."""
+        full = torch.zeros((h, w, 4), dtype=torch.uint8, device=f"cuda:{local}")
+        if isinstance(pieces, list):
+            for first, img in pieces:
+                full[first:first + img.shape[0]] = img
+        else:
+            full.copy_(pieces)
+        dist.all_reduce(full)
+        return full.cpu().numpy() if rank == 0 else None
 
     ok = {}
-    blk, rows = pipe.guided_block(cam, gopt)
+    blk, rows = pipe.guided_blocks(cam, gopt)
     frame = gather_frame(blk)
     if rank == 0:
         want, _ = solo.guided_block(cam, gopt)

@@ -323,3 +323,11 @@ def test_camera_matches_reference_golden(built):
     for s, ref in zip(steps, g["steps"]):
         got = np.asarray(s["transform"] + s["K"] + s["w2c"] + [s["fx"], s["fy"], s["cx"], s["cy"]], np.float32)
         assert np.allclose(got, np.asarray(ref, np.float32), rtol=2e-6, atol=2e-6), np.abs(got - ref).max()
+
+
+def test_gl_presentation_shim_type_checks(built):
+    """viewer::GlPresenter (csrc/viewer/gl_interop.cpp; reference cuda_renderer.cpp:43-66,70-95,156-162,383-458) is
+    built only with -DMNV_WITH_GL; without GL development packages it is compiled against declarations-only headers."""
+    csrc = os.path.join(os.path.dirname(built.LIB_PATH), "csrc")
+    r = subprocess.run(["make", "-C", csrc, "gl-check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
