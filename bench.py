@@ -190,6 +190,31 @@ def mlp_section(mnv, torch, dev, iters=20):
                         "frac_of_sustained_peak": tf / sustained, "peak_source": src + " cuBLAS bf16, burst (kernel timed alone)",
                         "kernel": "mnv::mlp_forward_kernel", "traffic": ncu_traffic("mlp_ncu_summary.json")}}
     model.close()
+    # the reference's evaluation mode for the same contraction: the TorchScript module under fp16 autocast through LibTorch
+    # (cuda_renderer.cpp:188-193) — here the PyTorch statement of the named shapes (tests/mlp_reference.py, test infrastructure),
+    # eager, same rows; reported beside the fused kernel, never on the product path
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from mlp_reference import MegaNerfMLP
+        torch.manual_seed(3)
+        ref = MegaNerfMLP().to(dev).eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            for _ in range(3):
+                ref(x)
+            torch.cuda.synchronize()
+            tms = []
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ref(x)
+                e1.record()
+                torch.cuda.synchronize()
+                tms.append(e0.elapsed_time(e1))
+        sec["vs_torch_autocast"] = {"torch_fp16_autocast_ms": float(np.mean(tms)), "speedup": float(np.mean(tms)) / t,
+                                    "what": "torch eager fp16 autocast of the same module (the reference's evaluation mode, "
+                                            "cuda_renderer.cpp:188-193), same rows"}
+    except Exception as e:  # the comparison is informational
+        sec["vs_torch_autocast"] = {"error": str(e)[:200]}
     return sec
 
 

@@ -149,23 +149,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "r"(parity)
             : "memory");
 }
-// The same copy delivered to the same CTA-relative offset (and mbarrier) of every CTA in cta_mask: each CTA of a
-// pair fetches HALF of a weight chunk from L2 and both halves land in both CTAs' rings.
-__device__ __forceinline__ void tma_bulk_g2s_multicast(void *dst, const void *src, uint32_t bytes, uint64_t *bar,
-                                                       uint16_t cta_mask) {
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                             uint64_t *bar) {
     asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                     "r"(smem_u32(dst)),
-            "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+            "l"(src), "r"(bytes), "r"(smem_u32(bar))
             : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -179,13 +169,6 @@ __device__ __forceinline__ void fence_async_smem() {
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                          smem_u32(bar))
-                 : "memory");
-}
-// completion of every MMA issued so far, signalled on the mbarrier at this CTA-relative offset in BOTH CTAs of the pair
-__device__ __forceinline__ void tc_commit_multicast(uint64_t *bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                         smem_u32(bar)),
-                 "h"(cta_mask)
                  : "memory");
 }
 // UMMA shared-memory descriptors (K-major, SWIZZLE_NONE, cute::UMMA::SmemDescriptor layout) are assembled from
@@ -282,14 +265,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         p.row_index += p.dyn[0];
         p.rows = p.dyn[1];
         p.n_groups = (int) ((p.rows + kTiles * kTileM - 1) / (kTiles * kTileM));
-        // uniform per CTA PAIR (both CTAs of a cluster leave together), before any barrier / TMEM allocation
-        if ((int) (blockIdx.x >> 1) >= (p.n_groups + 1) / 2) return;
+        if ((int) blockIdx.x >= p.n_groups) return;  // uniform per CTA, before any barrier / TMEM allocation
     }
-    // CTA pairs (cluster of 2): both CTAs run the same number of groups — pair q takes group pairs q, q + n_pairs, ...
-    // and CTA r of the pair rows group 2 * gp + r (past the end: every row invalid, the pipeline still runs, because
-    // the two weight rings advance together)
-    const uint32_t cta_rank = cluster_ctarank();
-    const int pair = (int) (blockIdx.x >> 1), n_pairs = (int) (gridDim.x >> 1), n_gp = (p.n_groups + 1) / 2;
     const int kStages = p.n_stages;
     uint8_t *s_act = smem;                           // [kTiles][kActBytes]
     uint8_t *s_pe = s_act + kTiles * kActBytes;      // [kTiles][kPeBytes]
@@ -314,7 +291,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_full + s, 1);
-            mbar_init(bar_empty + s, 2);  // released by the MMA commits of BOTH CTAs of the pair
+            mbar_init(bar_empty + s, 1);
         }
         for (int t = 0; t < kTiles; ++t) {
             mbar_init(bar_acc + t, 1);
@@ -345,7 +322,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into its shared memory
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
@@ -354,7 +330,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         // every layer's chunks are streamed twice in a row (tile 0, then tile 1): the second pass hits L2
         if (lane == 0) {
             uint32_t s = 0, ph = 1;
-            for (int gp = pair; gp < n_gp; gp += n_pairs) {
+            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
                 const uint8_t *layer_src = p.weights;  // chunks are contiguous in schedule order
                 for (int l = 0; l < n_layers; ++l) {
                     const uint32_t w0 = s_layer[l * kLayerWords];
@@ -362,14 +338,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                     for (int t = 0; t < kTiles; ++t) {
                         const uint8_t *src = layer_src;
                         for (uint32_t c = 0; c < n_chunks; ++c) {
-                            // this CTA fetches its half of the chunk from L2 and multicasts it into both rings; the
-                            // other half arrives from the peer (same stage, same barrier offset).  Bytes in flight
-                            // towards L2 per SM halve: the ring was latency-bound (7 x 8 KiB / ~1.2 us per SM)
                             mbar_wait(bar_empty + s, ph);
                             mbar_expect_tx(bar_full + s, bytes);
-                            const uint32_t half = bytes >> 1;
-                            tma_bulk_g2s_multicast(s_stage + s * kStageBytes + cta_rank * half, src + cta_rank * half, half,
-                                                   bar_full + s, (uint16_t) 3);
+                            tma_bulk_g2s(s_stage + s * kStageBytes, src, bytes, bar_full + s);
                             src += bytes;
                             if (++s == (uint32_t) kStages) {
                                 s = 0;
@@ -391,7 +362,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         const bool issue = elect_one();
         uint32_t s = 0, ph = 0, act_ph = 0;
         MLP_T(long long w_act = 0, w_full = 0, w_act_l[kMaxLayers] = {0}; const long long t_begin = p.dbg ? clock64() : 0;)
-        for (int gp = pair; gp < n_gp; gp += n_pairs) {
+        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
             for (int l = 0; l < n_layers; ++l) {
                 const uint32_t *w = s_layer + l * kLayerWords;
                 const uint32_t n_segs = w[0] & 0xffu, idesc = w[1];
@@ -412,7 +383,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                             if (issue) {
                                 umma_bf16(tmem_base + t * kMaxN, ((uint64_t) a_hi << 32) | a_lo,
                                           ((uint64_t) b_hi << 32) | (b_lo0 + s * (kStageBytes >> 4)), idesc, acc);
-                                tc_commit_multicast(bar_empty + s, (uint16_t) 3);  // frees the weight stage in both CTAs
+                                tc_commit(bar_empty + s);  // frees the weight stage
                             }
                             acc = 1;
                             a_lo += (kChunkK / 8 * 128u) >> 4;  // next 16 K columns of the K-major A operand
@@ -444,8 +415,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         const int row = q * 32 + lane;  // 0..127, TMEM lane
         const uint32_t tlane = tmem_base + ((uint32_t) (q * 32) << 16);
         uint32_t acc_ph = 0;
-        for (int gp = pair; gp < n_gp; gp += n_pairs) {
-            const int64_t grp = 2 * (int64_t) gp + cta_rank;
+        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
             int64_t grow[kTiles];
             bool valid[kTiles];
             int ai[kTiles];
@@ -614,7 +584,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();  // the peer may still multicast into this CTA's ring / arrive on its barriers until it is done too
     if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -909,8 +878,7 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
     p.ones_col = m->ones_col;
     p.sigma_activation = m->cfg.sigma_activation;
     p.out_real = m->cfg.out_rgb_dim;
-    // CTA pairs: an even grid, at most one CTA per SM
-    const int grid = std::min(2 * ((p.n_groups + 1) / 2), m->num_sms & ~1);
+    const int grid = std::min(p.n_groups, m->num_sms);
     p.dbg = nullptr;
 #ifdef MNV_MLP_TIMING
     static const bool debug = std::getenv("MNV_MLP_DEBUG") != nullptr;  // dev: where does the issuer wait?
@@ -922,21 +890,7 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
         MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 32 * sizeof(long long), stream));
     }
     p.n_stages = mlp_stages(p.need_viewdir != 0);
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned) grid);
-        cfg.blockDim = dim3(kMlpThreads);
-        cfg.dynamicSmemBytes = mlp_smem_bytes(p.need_viewdir != 0);
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        MNV_CUDA(cudaLaunchKernelEx(&cfg, mlp_forward_kernel, p));
-    }
+    mlp_forward_kernel<<<grid, kMlpThreads, mlp_smem_bytes(p.need_viewdir != 0), stream>>>(p);
     MNV_CUDA(cudaGetLastError());
     if (debug) {
         std::vector<long long> h((size_t) grid * 32);
