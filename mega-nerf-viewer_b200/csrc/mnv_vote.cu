@@ -14,7 +14,7 @@
 //   2. vote_collect  a coalesced sweep over the table, each block over its own share: count, reserve the output
 //                    range with ONE global atomic, then write — live slots with enough votes become 64-bit rank
 //                    keys — and the table is left clean for the next frame;
-//   3. radix select  six 11-bit MSB-first passes (histogram + one-block scan) find the max_n-th smallest rank —
+//   3. radix select  six 11-bit MSB-first passes (one launch each: histogram, the last block scans) find the max_n-th smallest rank —
 //                    keys are unique, so exactly min(max_n, candidates) keys are <= that threshold;
 //   4. gather + one-block bitonic sort of those <= max_n keys -> (chunk, child) rows in the reference's order.
 //
@@ -39,7 +39,7 @@ constexpr int kMaxSortN = 16384;  // keys the one-block bitonic sort holds in sh
 
 struct Ctl {
     unsigned long long prefix, prefix_mask, threshold;
-    uint32_t n_uniq, n_cand, n_sel, n_pairs, k_rem, take_all, overflow, pad;
+    uint32_t n_uniq, n_cand, n_sel, n_pairs, k_rem, take_all, overflow, pad;  // pad: ticket counter of select_pass_kernel
     uint32_t hist[kBins];
 };
 
@@ -247,8 +247,13 @@ __global__ void select_begin_kernel(Ctl *ctl, uint32_t k) {
     ctl->n_sel = 0;
 }
 
-__global__ void __launch_bounds__(256) select_hist_kernel(const unsigned long long *__restrict__ cand, Ctl *ctl, int shift) {
+// One radix-select pass in one launch: every block histograms its share of the live keys' current digit; the block
+// that finishes LAST (ticket counter) scans the 2048 bins, fixes the digit whose bucket holds the k_rem-th key and
+// clears the histogram for the next pass — no separate one-block "pick" launch between passes.
+__global__ void __launch_bounds__(256) select_pass_kernel(const unsigned long long *__restrict__ cand, Ctl *ctl, int shift,
+                                                          int last) {
     __shared__ uint32_t h[kBins];
+    __shared__ uint32_t s_warp[8], s_last;
     if (ctl->take_all) return;
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
     __syncthreads();
@@ -267,43 +272,53 @@ __global__ void __launch_bounds__(256) select_hist_kernel(const unsigned long lo
     __syncthreads();
     for (int i = threadIdx.x; i < kBins; i += blockDim.x)
         if (h[i]) atomicAdd(&ctl->hist[i], h[i]);
-}
-
-// one block of 1024 threads: the digit whose bucket holds the k_rem-th key; histogram cleared for the next pass
-__global__ void __launch_bounds__(1024) select_pick_kernel(Ctl *ctl, int shift, int last) {
-    __shared__ uint32_t s_scan[1024];
-    if (ctl->take_all) return;
-    const int t = threadIdx.x;
-    const uint32_t a = ctl->hist[2 * t], b = ctl->hist[2 * t + 1];
-    ctl->hist[2 * t] = 0;
-    ctl->hist[2 * t + 1] = 0;
-    s_scan[t] = a + b;
+    // ---- last block: pick the digit ----
+    __threadfence();
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // inclusive scan
-        const uint32_t v = t >= off ? s_scan[t - off] : 0;
-        __syncthreads();
-        s_scan[t] += v;
-        __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&ctl->pad, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int t = threadIdx.x;  // 8 consecutive bins per thread
+    uint32_t c[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        c[j] = __ldcg(&ctl->hist[8 * t + j]);
+        ctl->hist[8 * t + j] = 0;
+        sum += c[j];
     }
+    // exclusive prefix of the per-thread sums over the block
+    const int lane = t & 31, warp = t >> 5;
+    uint32_t incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = incl - sum;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
     const uint32_t k = ctl->k_rem;
-    const uint32_t before = s_scan[t] - (a + b);  // keys in bins < 2t
     __syncthreads();
-    int bin = -1;
-    uint32_t below = 0;
-    if (before < k && k <= before + a) {
-        bin = 2 * t;
-        below = before;
-    } else if (before + a < k && k <= before + a + b) {
-        bin = 2 * t + 1;
-        below = before + a;
-    }
-    if (bin >= 0) {
+    if (before < k && k <= before + sum) {  // exactly one thread: the k-th key is in one of its bins
+        uint32_t below = before;
+        int bin = 8 * t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (k <= below + c[j]) {
+                bin = 8 * t + j;
+                break;
+            }
+            below += c[j];
+        }
         const unsigned long long digit_mask = (unsigned long long) (kBins - 1) << shift;
         ctl->prefix |= ((unsigned long long) bin << shift) & digit_mask;
         ctl->prefix_mask |= digit_mask;
         ctl->k_rem = k - below;
-        if (last) ctl->threshold = ctl->prefix | (((unsigned long long) bin << shift) & digit_mask);
+        if (last) ctl->threshold = ctl->prefix;
     }
+    if (t == 0) ctl->pad = 0;  // ticket counter ready for the next pass
 }
 
 __global__ void __launch_bounds__(256) select_gather_kernel(const unsigned long long *__restrict__ cand, Ctl *ctl,
@@ -371,8 +386,7 @@ int run_select(Scratch &s, int kind, int max_n, int32_t *nodes_dev, int *n_selec
     select_begin_kernel<<<1, 1, 0, stream>>>(s.ctl, (uint32_t) max_n);
     for (int p = 0; p < kPasses; ++p) {
         const int shift = std::max(64 - kDigitBits * (p + 1), 0);  // 53, 42, 31, 20, 9, 0 (the last digit overlaps: harmless)
-        select_hist_kernel<<<148 * 2, 256, 0, stream>>>(s.cand, s.ctl, shift);
-        select_pick_kernel<<<1, 1024, 0, stream>>>(s.ctl, shift, p == kPasses - 1);
+        select_pass_kernel<<<148 * 2, 256, 0, stream>>>(s.cand, s.ctl, shift, p == kPasses - 1);
     }
     select_gather_kernel<<<148 * 2, 256, 0, stream>>>(s.cand, s.ctl, s.sel, (uint32_t) max_n);
     uint32_t m = 1;

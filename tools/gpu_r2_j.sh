@@ -24,3 +24,5 @@ for rows in (4096, 32768, 262144, 2097152):
     t = float(np.mean(ms)); print(rows, "rows", round(t, 4), "ms", round(rows * model.flops_per_row / t / 1e9, 1), "TFLOP/s")
 PY
 timeout 600 python -m pytest tests/test_pipeline_gpu.py tests/test_viewer_gpu.py tests/test_group_gpu.py -x -q 2>&1 | tail -5 | tee gpurun_out/r2j_pytest2.log | cut -c1-200
+timeout 300 python tools/profile_select.py --width 1920 --height 1080 2>&1 | tail -4 | tee gpurun_out/r2j_select_1080p.log
+timeout 300 python tools/profile_select.py 2>&1 | tail -4 | tee gpurun_out/r2j_select_4k.log

@@ -7,7 +7,12 @@ sys.path.insert(0, ROOT)
 import torch
 import mega_nerf_viewer_b200 as mnv
 
-W, H = 3840, 2160
+import argparse
+ap = argparse.ArgumentParser()
+ap.add_argument("--width", type=int, default=3840)
+ap.add_argument("--height", type=int, default=2160)
+a = ap.parse_args()
+W, H = a.width, a.height
 tree = mnv.synth.make_tree(depth=10)
 dt = mnv.DeviceTree(tree)
 opt = mnv.default_options(background_brightness=0.0, basis_minmax=[0, 8])
