@@ -18,6 +18,8 @@
 // exchanged and committed everywhere — the C++ form of multigpu.ReplicatedPipeline.refine_frame, with peer copies
 // in place of NCCL.
 #include <algorithm>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "mnv_internal.cuh"
@@ -291,13 +293,31 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
             rp.rec_cap = cap_local;
         }
     }
-    for (int i = 0; i < n; ++i) {
-        mnv_group::Replica &rp = g->r[(size_t) i];
-        MNV_CUDA(cudaSetDevice(rp.device));
-        // own records go to slot i of the replica's own gather buffer
-        rc = vote_reduce(rp.split, rays, rp.records + (size_t) i * rp.rec_cap * 3, rp.rec_cap, &n_rec[(size_t) i],
-                         stream_of(rp));
+    // launch on every device before waiting for any (replicas that share a device — tests — go one wave at a time:
+    // the selection scratch is per device)
+    for (int w0 = 0; w0 < n;) {
+        int w1 = w0;
+        while (w1 < n) {
+            bool clash = false;
+            for (int j = w0; j < w1; ++j) clash |= g->r[(size_t) j].device == g->r[(size_t) w1].device;
+            if (clash) break;
+            ++w1;
+        }
+        for (int i = w0; i < w1; ++i) {
+            mnv_group::Replica &rp = g->r[(size_t) i];
+            MNV_CUDA(cudaSetDevice(rp.device));
+            // own records go to slot i of the replica's own gather buffer
+            rc = vote_reduce_launch(rp.split, rays, rp.records + (size_t) i * rp.rec_cap * 3, rp.rec_cap, stream_of(rp));
+            if (rc != MNV_OK) return rc;
+        }
+        for (int i = w0; i < w1; ++i) {
+            mnv_group::Replica &rp = g->r[(size_t) i];
+            MNV_CUDA(cudaSetDevice(rp.device));
+            const int rc_i = vote_reduce_finish(rp.rec_cap, &n_rec[(size_t) i], stream_of(rp));
+            if (rc_i != MNV_OK) rc = rc_i;
+        }
         if (rc != MNV_OK) return rc;
+        w0 = w1;
     }
     // 2. exchange: replica i pulls replica j's records (peer copy); record layout [j][rec_cap][3], unused rows are
     //    skipped by passing each block separately to the selection
@@ -321,14 +341,33 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
     // 3. identical selection + linking on every replica
     const int max_n = opt->split_batch_size;
     std::vector<int> k((size_t) n, 0);
-    for (int i = 0; i < n; ++i) {
-        mnv_group::Replica &rp = g->r[(size_t) i];
+    for (auto &rp : g->r) {
         MNV_CUDA(cudaSetDevice(rp.device));
         if (!rp.nodes) MNV_CUDA(cudaMalloc(&rp.nodes, (size_t) 16384 * 2 * sizeof(int32_t)));
-        int cand = 0;
-        rc = select_candidates(0, nullptr, 0, rp.records, (int64_t) n * rp.rec_cap, max_n, rp.nodes, &k[(size_t) i], &cand,
-                               stream_of(rp));
+    }
+    for (int w0 = 0; w0 < n;) {
+        int w1 = w0;
+        while (w1 < n) {
+            bool clash = false;
+            for (int j = w0; j < w1; ++j) clash |= g->r[(size_t) j].device == g->r[(size_t) w1].device;
+            if (clash) break;
+            ++w1;
+        }
+        for (int i = w0; i < w1; ++i) {
+            mnv_group::Replica &rp = g->r[(size_t) i];
+            MNV_CUDA(cudaSetDevice(rp.device));
+            rc = select_candidates_launch(0, nullptr, 0, rp.records, (int64_t) n * rp.rec_cap, max_n, rp.nodes, stream_of(rp));
+            if (rc != MNV_OK) return rc;
+        }
+        for (int i = w0; i < w1; ++i) {
+            mnv_group::Replica &rp = g->r[(size_t) i];
+            MNV_CUDA(cudaSetDevice(rp.device));
+            int cand = 0;
+            const int rc_i = select_candidates_finish(&k[(size_t) i], &cand, stream_of(rp));
+            if (rc_i != MNV_OK) rc = rc_i;
+        }
         if (rc != MNV_OK) return rc;
+        w0 = w1;
     }
     for (int i = 1; i < n; ++i)
         if (k[(size_t) i] != k[0]) {
@@ -350,7 +389,10 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
         int rec_bytes = 0;
         mnv_tree_record_bytes(g->r[0].tree, &rec_bytes);
         const int out_stride = t0.data_dim + 1;
-        for (int i = 0; i < n; ++i) {
+        // One host thread per replica for this stage: mnv_query_submodules ends with a synchronisation (it validates the
+        // cluster ids and recycles its index scratch), so issued from one thread the replicas' MLP shares would run one
+        // after the other.  (Replicas that share a device — tests — serialise on that device's scratch mutex.)
+        auto replica_stage = [&](int i) -> int {
             mnv_group::Replica &rp = g->r[(size_t) i];
             MNV_CUDA(cudaSetDevice(rp.device));
             cudaStream_t s = stream_of(rp);
@@ -381,23 +423,41 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
                 rp.payload_cap = need_p;
             }
             // the same counter-based random numbers on every replica (torch::rand in the reference, :250)
-            rc = fill_uniform(rp.samples, (int64_t) need_s, seed + g->step, s);
-            if (rc == MNV_OK)
-                rc = mnv_add_children_and_generate_samples(rp.tree, opt, rp.nodes, kk, rp.samples, rp.cluster, nullptr,
-                                                           grid_dim, min_position, range, s);
-            if (rc != MNV_OK) return rc;
+            int r = fill_uniform(rp.samples, (int64_t) need_s, seed + g->step, s);
+            if (r == MNV_OK)
+                r = mnv_add_children_and_generate_samples(rp.tree, opt, rp.nodes, kk, rp.samples, rp.cluster, nullptr,
+                                                          grid_dim, min_position, range, s);
+            if (r != MNV_OK) return r;
             // 4. this replica's share of the MLP rows -> payload records, into slot i of its own gather buffer
             const int lo = std::min(i * per, children), hi = std::min((i + 1) * per, children);
             MNV_CUDA(cudaMemsetAsync(rp.payload + (size_t) i * per * rec_bytes, 0, (size_t) per * rec_bytes, s));
             if (hi > lo) {
-                rc = mnv_query_submodules(models[i], rp.cluster + (size_t) lo * c, rp.samples + (size_t) lo * c * rd, rd,
-                                          (int64_t) (hi - lo) * c, rp.results, out_stride, s);
-                if (rc == MNV_OK)
-                    rc = mnv_tree_reduce_children(rp.tree, opt, hi - lo, rp.results, out_stride,
-                                                  rp.payload + (size_t) i * per * rec_bytes, s);
-                if (rc != MNV_OK) return rc;
+                r = mnv_query_submodules(models[i], rp.cluster + (size_t) lo * c, rp.samples + (size_t) lo * c * rd, rd,
+                                         (int64_t) (hi - lo) * c, rp.results, out_stride, s);
+                if (r == MNV_OK)
+                    r = mnv_tree_reduce_children(rp.tree, opt, hi - lo, rp.results, out_stride,
+                                                 rp.payload + (size_t) i * per * rec_bytes, s);
+                if (r != MNV_OK) return r;
             }
             MNV_CUDA(cudaEventRecord(rp.done, s));
+            return MNV_OK;
+        };
+        {
+            std::vector<int> rcs((size_t) n, MNV_OK);
+            std::vector<std::string> msgs((size_t) n);
+            std::vector<std::thread> workers;
+            for (int i = 1; i < n; ++i)
+                workers.emplace_back([&, i] {
+                    rcs[(size_t) i] = replica_stage(i);
+                    if (rcs[(size_t) i] != MNV_OK) msgs[(size_t) i] = mnv_last_error();  // the message is thread-local
+                });
+            rcs[0] = replica_stage(0);
+            for (auto &w : workers) w.join();
+            for (int i = 0; i < n; ++i)
+                if (rcs[(size_t) i] != MNV_OK) {
+                    if (i > 0) set_error("%s", msgs[(size_t) i].c_str());
+                    return rcs[(size_t) i];
+                }
         }
         // 5. payload exchange (64 B per child) and commit everywhere
         for (int i = 0; i < n; ++i) {

@@ -294,6 +294,12 @@ int select_candidates(int kind, const float *rows_dev, int64_t P, const uint32_t
                       int32_t *nodes_dev, int *n_selected, int *n_candidates, cudaStream_t stream);
 int vote_reduce(const float *rows_dev, int64_t P, uint32_t *pairs_out_dev, int64_t cap, int64_t *n_out,
                 cudaStream_t stream);
+// launch / finish halves (one operation in flight per device; see mnv_vote.cu)
+int select_candidates_launch(int kind, const float *rows_dev, int64_t P, const uint32_t *pairs_dev, int64_t n_pairs, int max_n,
+                             int32_t *nodes_dev, cudaStream_t stream);
+int select_candidates_finish(int *n_selected, int *n_candidates, cudaStream_t stream);
+int vote_reduce_launch(const float *rows_dev, int64_t P, uint32_t *pairs_out_dev, int64_t cap, cudaStream_t stream);
+int vote_reduce_finish(int64_t cap, int64_t *n_out, cudaStream_t stream);
 int query_submodules(MlpModel *const *subs, int n_subs, const int16_t *cluster_dev, const float *rows_dev,
                      int in_dim, int64_t V, float *out_dev, int out_stride, cudaStream_t stream);
 

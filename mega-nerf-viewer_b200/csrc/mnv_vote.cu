@@ -378,8 +378,7 @@ __global__ void report_kernel(const Ctl *ctl, uint32_t *host_out) {
     host_out[4] = ctl->overflow;
 }
 
-int run_select(Scratch &s, int kind, int max_n, int32_t *nodes_dev, int *n_selected, int *n_candidates,
-               cudaStream_t stream) {
+int run_select(Scratch &s, int kind, int max_n, int32_t *nodes_dev, cudaStream_t stream) {
     const uint32_t grid = 148 * 8;
     if (kind == 0) vote_collect_kernel<0><<<std::min(grid, s.T / 256), 256, 0, stream>>>(s.keys, s.counts, s.T, s.cand, nullptr, 0, s.ctl);
     else vote_collect_kernel<1><<<std::min(grid, s.T / 256), 256, 0, stream>>>(s.keys, s.counts, s.T, s.cand, nullptr, 0, s.ctl);
@@ -402,6 +401,10 @@ int run_select(Scratch &s, int kind, int max_n, int32_t *nodes_dev, int *n_selec
     }
     select_sort_kernel<<<1, 1024, smem, stream>>>(s.sel, s.ctl, (uint32_t) max_n, kind == 0 ? 31 : 32, nodes_dev, s.host_out);
     MNV_CUDA(cudaGetLastError());
+    return MNV_OK;
+}
+
+int finish_select(Scratch &s, int *n_selected, int *n_candidates, cudaStream_t stream) {
     MNV_CUDA(cudaStreamSynchronize(stream));  // the one synchronisation: n sizes the caller's next launches
     if (n_selected) *n_selected = (int) s.host_out[0];
     if (n_candidates) *n_candidates = (int) s.host_out[1];
@@ -419,23 +422,42 @@ int begin(Scratch &s, int64_t voters, cudaStream_t stream) {
 
 // kind 0: split candidates (cuda_renderer.cpp:205-226); kind 1: re-sample candidates (:281-293).
 // rows (tracker, may be null) and pairs (vote records of other ranks, may be null) are merged.
-int select_candidates(int kind, const float *rows_dev, int64_t P, const uint32_t *pairs_dev, int64_t n_pairs, int max_n,
-                      int32_t *nodes_dev, int *n_selected, int *n_candidates, cudaStream_t stream) {
+// The *_launch / *_finish pairs split every call into "enqueue on this device's stream" and "synchronise + read the counts":
+// a host thread that drives several GPUs (mnv_group.cu) launches on all of them before it waits for any.  One operation
+// may be in flight per device (its scratch and result words); launch locks the device's scratch, finish unlocks it.
+int select_candidates_launch(int kind, const float *rows_dev, int64_t P, const uint32_t *pairs_dev, int64_t n_pairs, int max_n,
+                             int32_t *nodes_dev, cudaStream_t stream) {
     if (max_n > kMaxSortN) {
         set_error("select_candidates: max_n %d exceeds %d", max_n, kMaxSortN);
         return MNV_ERR_INVALID;
     }
     Scratch &s = scratch_for_current_device();
-    std::lock_guard<std::mutex> lock(s.mu);
+    s.mu.lock();
     const int64_t voters = std::max<int64_t>((rows_dev ? P : 0) + (pairs_dev ? n_pairs : 0), 1);
     int rc = begin(s, voters, stream);
-    if (rc != MNV_OK) return rc;
-    const int shift = 32 - __builtin_ctz(s.T);
-    if (rows_dev && P > 0)
-        vote_insert_rows_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, stream>>>(rows_dev, P, s.keys, s.counts, s.T - 1, shift);
-    if (pairs_dev && n_pairs > 0)
-        vote_insert_pairs_kernel<<<(unsigned) ((n_pairs + 255) / 256), 256, 0, stream>>>(pairs_dev, n_pairs, s.keys, s.counts, s.T - 1, shift);
-    return run_select(s, kind, max_n, nodes_dev, n_selected, n_candidates, stream);
+    if (rc == MNV_OK) {
+        const int shift = 32 - __builtin_ctz(s.T);
+        if (rows_dev && P > 0)
+            vote_insert_rows_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, stream>>>(rows_dev, P, s.keys, s.counts, s.T - 1, shift);
+        if (pairs_dev && n_pairs > 0)
+            vote_insert_pairs_kernel<<<(unsigned) ((n_pairs + 255) / 256), 256, 0, stream>>>(pairs_dev, n_pairs, s.keys, s.counts, s.T - 1, shift);
+        rc = run_select(s, kind, max_n, nodes_dev, stream);
+    }
+    if (rc != MNV_OK) s.mu.unlock();
+    return rc;
+}
+
+int select_candidates_finish(int *n_selected, int *n_candidates, cudaStream_t stream) {
+    Scratch &s = scratch_for_current_device();
+    const int rc = finish_select(s, n_selected, n_candidates, stream);
+    s.mu.unlock();
+    return rc;
+}
+
+int select_candidates(int kind, const float *rows_dev, int64_t P, const uint32_t *pairs_dev, int64_t n_pairs, int max_n,
+                      int32_t *nodes_dev, int *n_selected, int *n_candidates, cudaStream_t stream) {
+    const int rc = select_candidates_launch(kind, rows_dev, P, pairs_dev, n_pairs, max_n, nodes_dev, stream);
+    return rc != MNV_OK ? rc : select_candidates_finish(n_selected, n_candidates, stream);
 }
 
 int select_split_candidates(const float *to_split_dev, int64_t P, int max_n, int32_t *nodes_dev,
@@ -450,26 +472,42 @@ int select_sample_candidates(const float *to_sample_dev, int64_t P, int max_n, i
 
 // One rank's tracker rows -> vote records (id, priority, count), unordered.  *n_out = records the rows reduce to;
 // MNV_ERR_FULL when that exceeds `cap` (the caller falls back to exchanging raw rows).
-int vote_reduce(const float *rows_dev, int64_t P, uint32_t *pairs_out_dev, int64_t cap, int64_t *n_out, cudaStream_t stream) {
+int vote_reduce_launch(const float *rows_dev, int64_t P, uint32_t *pairs_out_dev, int64_t cap, cudaStream_t stream) {
     Scratch &s = scratch_for_current_device();
-    std::lock_guard<std::mutex> lock(s.mu);
+    s.mu.lock();
     int rc = begin(s, std::max<int64_t>(P, 1), stream);
-    if (rc != MNV_OK) return rc;
-    const int shift = 32 - __builtin_ctz(s.T);
-    if (P > 0)
-        vote_insert_rows_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, stream>>>(rows_dev, P, s.keys, s.counts, s.T - 1, shift);
-    vote_collect_kernel<2><<<std::min(148u * 8u, s.T / 256), 256, 0, stream>>>(
-            s.keys, s.counts, s.T, nullptr, reinterpret_cast<U32x3 *>(pairs_out_dev),
-            (uint32_t) std::min<int64_t>(cap, 0xffffffffll), s.ctl);
-    report_kernel<<<1, 1, 0, stream>>>(s.ctl, s.host_out);
-    MNV_CUDA(cudaGetLastError());
-    MNV_CUDA(cudaStreamSynchronize(stream));
-    if (n_out) *n_out = (int64_t) s.host_out[3];
-    if (s.host_out[4]) {
-        set_error("vote_reduce: %u records do not fit %lld", s.host_out[3], (long long) cap);
-        return MNV_ERR_FULL;
+    if (rc == MNV_OK) {
+        const int shift = 32 - __builtin_ctz(s.T);
+        if (P > 0)
+            vote_insert_rows_kernel<<<(unsigned) ((P + 255) / 256), 256, 0, stream>>>(rows_dev, P, s.keys, s.counts, s.T - 1, shift);
+        vote_collect_kernel<2><<<std::min(148u * 8u, s.T / 256), 256, 0, stream>>>(
+                s.keys, s.counts, s.T, nullptr, reinterpret_cast<U32x3 *>(pairs_out_dev),
+                (uint32_t) std::min<int64_t>(cap, 0xffffffffll), s.ctl);
+        report_kernel<<<1, 1, 0, stream>>>(s.ctl, s.host_out);
+        if (cudaGetLastError() != cudaSuccess) rc = MNV_ERR_CUDA;
     }
-    return MNV_OK;
+    if (rc != MNV_OK) s.mu.unlock();
+    return rc;
+}
+
+int vote_reduce_finish(int64_t cap, int64_t *n_out, cudaStream_t stream) {
+    Scratch &s = scratch_for_current_device();
+    int rc = MNV_OK;
+    if (cudaStreamSynchronize(stream) != cudaSuccess) rc = MNV_ERR_CUDA;
+    if (rc == MNV_OK) {
+        if (n_out) *n_out = (int64_t) s.host_out[3];
+        if (s.host_out[4]) {
+            set_error("vote_reduce: %u records do not fit %lld", s.host_out[3], (long long) cap);
+            rc = MNV_ERR_FULL;
+        }
+    }
+    s.mu.unlock();
+    return rc;
+}
+
+int vote_reduce(const float *rows_dev, int64_t P, uint32_t *pairs_out_dev, int64_t cap, int64_t *n_out, cudaStream_t stream) {
+    const int rc = vote_reduce_launch(rows_dev, P, pairs_out_dev, cap, stream);
+    return rc != MNV_OK ? rc : vote_reduce_finish(cap, n_out, stream);
 }
 
 }  // namespace mnv
