@@ -48,6 +48,13 @@
 #else
 #define MLP_T(...)
 #endif
+// Dev-only diagnostic builds (results are WRONG, timing only): bit 0 = the epilogue computes but does not store the next
+// A operand, bit 1 = the producer signals a stage without copying weights into it, bit 2 = the epilogue does not read the
+// accumulators out of TMEM (its registers hold a stand-in value).  They separate shared-memory
+// bandwidth contention from the issuing lane's own instruction latency (profiles/r2_mlp_smem_diag.md).
+#ifndef MNV_MLP_DIAG
+#define MNV_MLP_DIAG 0
+#endif
 
 namespace mnv {
 namespace {
@@ -56,7 +63,7 @@ constexpr int kMlpThreads = 320;
 constexpr int kEpiThreads = 256;
 constexpr int kTileM = 128;
 constexpr int kTiles = 2;  // row tiles per CTA
-constexpr int kMaxStages = 7;  // 7 without view directions, 5 with (the dir-PE buffers take 16 KiB)
+constexpr int kMaxStages = 13;  // ring stages: whatever shared memory is left holds (mlp_stages)
 constexpr int kChunkK = 16;
 constexpr int kMaxN = 256;
 constexpr int kStageBytes = kMaxN * kChunkK * 2;  // 8 KiB
@@ -149,6 +156,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "r"(parity)
             : "memory");
 }
+// one poll; may suspend the thread for a hardware-defined time if the phase has not completed yet.  The same form serves
+// barriers that take arrivals from the peer CTA: cluster-scope acquire / release qualifiers on the poll and on the remote
+// arrive cost a full fence each (measured: 570 clk per ring stage on the issuing lane) and buy nothing here — what is
+// handed over sits in shared memory, written through the async proxy or fenced with fence.proxy.async by its writer.
+template <bool CLUSTER>
+__device__ __forceinline__ bool mbar_try(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of a shared::cta address as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {  // every thread of both CTAs
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
                                              uint64_t *bar) {
     asm volatile(
@@ -166,10 +209,16 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(bar))
-                 : "memory");
+// PAIR: the arrival is delivered to the barrier at this offset in BOTH CTAs of the pair
+template <bool PAIR>
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar_addr) {
+    if constexpr (PAIR)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
+                     "h"((uint16_t) 3)
+                     : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr)
+                     : "memory");
 }
 // UMMA shared-memory descriptors (K-major, SWIZZLE_NONE, cute::UMMA::SmemDescriptor layout) are assembled from
 // two 32-bit halves in the issue loop: low = start>>4 [0,14) | LBO>>4 [16,30); high = SBO>>4 [0,14) | version 1 [14,16).
@@ -179,16 +228,27 @@ __device__ __forceinline__ uint32_t umma_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (n >> 3) << 17) |
            ((uint32_t) (m >> 4) << 24);
 }
+template <bool PAIR>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-            "}" ::"r"(tmem_d),
-            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-            : "memory");
+    if constexpr (PAIR)
+        asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                "}" ::"r"(tmem_d),
+                "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                : "memory");
+    else
+        asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                "}" ::"r"(tmem_d),
+                "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                : "memory");
 }
 __device__ __forceinline__ bool elect_one() {  // one lane of the (converged) warp
     uint32_t pred;
@@ -197,6 +257,11 @@ __device__ __forceinline__ bool elect_one() {  // one lane of the (converged) wa
 }
 // asynchronous: the registers are valid after tmem_wait()
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+#if MNV_MLP_DIAG & 4
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = taddr + j;
+    return;
+#endif
     asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -259,25 +324,100 @@ __device__ __forceinline__ void write_pe_octaves(uint8_t *buf, int row, int sbo,
     }
 }
 
+// Epilogue of one (layer, tile) for the layers that produce the next A operand, straight-line for a compile-time kind
+// and column count: accumulators out of TMEM 32 columns at a time (the next load is in flight while this one is used),
+// + fp32 bias row (shared memory, or the per-appearance-index row in global memory), [sigma-head partial dot product],
+// ReLU fused into the bf16 conversion, four 16-byte stores into the K-major core-matrix layout.  The generic loop this
+// replaces spent 3.5 instructions per useful one (register copies of every accumulator, per-block branches on the layer
+// kind: profiles/r2_mlp_smem_diag.md) and its 2500 clk per unit, not the tensor pipe's 2048, paced the kernel.
+//   taddr: TMEM address of this thread's first column; dst: &A[row][first column]; bias: &row[first column]
+template <int KIND, int N_MINE>
+__device__ __forceinline__ void epilogue_unit(const uint32_t taddr, uint8_t *__restrict__ dst, const float *__restrict__ bias,
+                                              const float *__restrict__ sigma_w, float &sigma) {
+    constexpr int kBlocks = N_MINE / 32;
+    uint32_t r[2][32];
+    tmem_ld32(taddr, r[0]);
+#pragma unroll
+    for (int blk = 0; blk < kBlocks; ++blk) {
+        float4 b[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float4 *b4 = reinterpret_cast<const float4 *>(bias + 32 * blk) + g;
+            b[g] = KIND == kEpiReluActApp ? __ldg(b4) : *b4;
+        }
+        float4 sw[8];
+        if constexpr (KIND == kEpiReluActSigma) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) sw[g] = __ldg(reinterpret_cast<const float4 *>(sigma_w + 32 * blk) + g);
+        }
+        tmem_wait();
+        if (blk + 1 < kBlocks) tmem_ld32(taddr + 32 * (blk + 1), r[(blk + 1) & 1]);  // overlaps the math below
+        const uint32_t(&rr)[32] = r[blk & 1];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v[j] = __uint_as_float(rr[8 * g + j]) + (&b[2 * g].x)[j];
+                v[4 + j] = __uint_as_float(rr[8 * g + 4 + j]) + (&b[2 * g + 1].x)[j];
+            }
+            if constexpr (KIND == kEpiReluActSigma) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sigma = fmaf(fmaxf(v[j], 0.f), (&sw[2 * g].x)[j], sigma);
+                    sigma = fmaf(fmaxf(v[4 + j], 0.f), (&sw[2 * g + 1].x)[j], sigma);
+                }
+            }
+            uint4 o;
+            if constexpr (KIND == kEpiLinearAct) {
+                o.x = pack_bf16(v[0], v[1]);
+                o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]);
+                o.w = pack_bf16(v[6], v[7]);
+            } else {
+                o.x = pack_bf16_relu(v[0], v[1]);
+                o.y = pack_bf16_relu(v[2], v[3]);
+                o.z = pack_bf16_relu(v[4], v[5]);
+                o.w = pack_bf16_relu(v[6], v[7]);
+            }
+#if MNV_MLP_DIAG & 1
+            if (sigma_w == nullptr)  // never true: keeps the arithmetic, drops the store traffic
+#endif
+            *reinterpret_cast<uint4 *>(dst + (4 * blk + g) * 128) = o;  // 8 columns = one 16-byte row of a core matrix
+        }
+    }
+}
+
+// PAIR: two CTAs of a cluster (one TPC) run tcgen05.mma.cta_group::2 — one lane of the leader CTA issues M = 256 MMAs
+// that span both SMs; each CTA keeps its own 2 x 128 rows (A operand, accumulators) and HALF of every weight chunk
+// (its N/2 rows of B), so the same ring holds twice as many MMAs of look-ahead and each SM reads half the weight bytes.
+// PER: weight chunks (MMAs) per ring stage — one "weights landed" poll and one stage-release commit per PER MMAs.
+template <bool PAIR, int PER>
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t kSlot = PAIR ? kStageBytes / 2 : kStageBytes;  // one chunk (or this CTA's half of it)
+    constexpr uint32_t kStageB = PER * kSlot;
+    const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    // the pair walks the 256-row groups together: CTA rank r of the pair at even block b takes group b + r, b + r + grid, ...
+    const int g_first = PAIR ? (int) (blockIdx.x & ~1u) : (int) blockIdx.x;
     if (p.dyn) {  // bucket of a sub-module dispatch: size and position were computed by the previous kernels
         p.row_index += p.dyn[0];
         p.rows = p.dyn[1];
         p.n_groups = (int) ((p.rows + kTiles * kTileM - 1) / (kTiles * kTileM));
-        if ((int) blockIdx.x >= p.n_groups) return;  // uniform per CTA, before any barrier / TMEM allocation
+        if (g_first >= p.n_groups) return;  // uniform per CTA pair, before any barrier / TMEM allocation
     }
     const int kStages = p.n_stages;
     uint8_t *s_act = smem;                           // [kTiles][kActBytes]
     uint8_t *s_pe = s_act + kTiles * kActBytes;      // [kTiles][kPeBytes]
     uint8_t *s_dir = s_pe + kTiles * kPeBytes;       // [kTiles][kDirBytes], only with view directions
-    uint8_t *s_stage = s_dir + (p.need_viewdir ? kTiles * kDirBytes : 0);  // [kStages][kStageBytes]
-    float *s_bias = reinterpret_cast<float *>(s_stage + kStages * kStageBytes);  // [2][kMaxN] this / next layer's bias row
+    uint8_t *s_stage = s_dir + (p.need_viewdir ? kTiles * kDirBytes : 0);  // [kStages][kStageB]
+    float *s_bias = reinterpret_cast<float *>(s_stage + kStages * kStageB);  // [2][kMaxN] this / next layer's bias row
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_bias + 2 * kMaxN);
-    uint64_t *bar_full = bars;                       // [kMaxStages] weights landed
+    uint64_t *bar_full = bars;                       // [kMaxStages] weights landed (PAIR: in both CTAs, leader's barrier)
     uint64_t *bar_empty = bars + kMaxStages;         // [kMaxStages] weights consumed
     uint64_t *bar_acc = bars + 2 * kMaxStages;       // [kTiles] accumulator of the current layer complete
-    uint64_t *bar_act = bars + 2 * kMaxStages + kTiles; // [kTiles] A operand of the next layer written (256 arrivals)
+    uint64_t *bar_act = bars + 2 * kMaxStages + kTiles; // [kTiles] A operand of the next layer written
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * kMaxStages + 2 * kTiles);
     // issuer-side schedule, per layer 2 + 3 * 3 words: n_segs | n_chunks << 8 | weight bytes per chunk << 16;
     // instruction descriptor; then per segment: low word of tile 0's A descriptor, high word,
@@ -290,26 +430,33 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(bar_full + s, 1);
+            // PAIR: the leader's barrier also takes one arrival from the peer CTA (its half has landed)
+            mbar_init(bar_full + s, (PAIR && leader) ? 2 : 1);
             mbar_init(bar_empty + s, 1);
         }
         for (int t = 0; t < kTiles; ++t) {
             mbar_init(bar_acc + t, 1);
-            mbar_init(bar_act + t, kEpiThreads);
+            // PAIR: one arrival per epilogue warp of both CTAs (the warp's lanes meet in __syncwarp first)
+            mbar_init(bar_act + t, PAIR ? 2 * (kEpiThreads / 32) : kEpiThreads);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                             smem_u32(s_tmem)),
-                     "r"(kTmemCols));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                         "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                         "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     if (threadIdx.x < n_layers) {
         const LayerDesc ld = S.layers[threadIdx.x];
         uint32_t *w = s_layer + threadIdx.x * kLayerWords;
         w[0] = (uint32_t) ld.n_segs | ((uint32_t) (ld.chunk_end - ld.chunk_begin) << 8) | ((uint32_t) ld.n * kChunkK * 2u) << 16;
-        w[1] = umma_idesc(kTileM, ld.n);
+        w[1] = umma_idesc(PAIR ? 2 * kTileM : kTileM, ld.n);
         for (int i = 0; i < ld.n_segs; ++i) {
             const SegDesc sg = ld.segs[i];
             const uint8_t *abuf = sg.a_src == kSrcAct ? s_act : (sg.a_src == kSrcPE ? s_pe : s_dir);
@@ -321,30 +468,42 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // barriers initialised and TMEM allocated in both CTAs
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 8) {
         // ===================== TMA producer =====================
-        // every layer's chunks are streamed twice in a row (tile 0, then tile 1): the second pass hits L2
+        // every layer's chunks are streamed twice in a row (tile 0, then tile 1): the second pass hits L2.
+        // PAIR: this CTA copies its half of every chunk (rows n of B in [rank * N/2, (rank + 1) * N/2)).
         if (lane == 0) {
             uint32_t s = 0, ph = 1;
-            for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+            for (int gb = g_first; gb < p.n_groups; gb += gridDim.x) {
                 const uint8_t *layer_src = p.weights;  // chunks are contiguous in schedule order
                 for (int l = 0; l < n_layers; ++l) {
-                    const uint32_t w0 = s_layer[l * kLayerWords];
-                    const uint32_t n_chunks = (w0 >> 8) & 0xffu, bytes = w0 >> 16;
+                    const uint32_t *w = s_layer + l * kLayerWords;
+                    const uint32_t w0 = w[0];
+                    const uint32_t n_segs = w0 & 0xffu, n_chunks = (w0 >> 8) & 0xffu, bytes = w0 >> 16;
+                    const uint32_t part = PAIR ? bytes >> 1 : bytes;
                     for (int t = 0; t < kTiles; ++t) {
-                        const uint8_t *src = layer_src;
-                        for (uint32_t c = 0; c < n_chunks; ++c) {
-                            mbar_wait(bar_empty + s, ph);
-                            mbar_expect_tx(bar_full + s, bytes);
-                            tma_bulk_g2s(s_stage + s * kStageBytes, src, bytes, bar_full + s);
-                            src += bytes;
-                            if (++s == (uint32_t) kStages) {
-                                s = 0;
-                                ph ^= 1;
+                        const uint8_t *src = layer_src + cta_rank * part;
+                        for (uint32_t i = 0; i < n_segs; ++i) {
+                            for (uint32_t left = w[4 + 3 * i] & 0xffffu; left > 0;) {
+                                const uint32_t k = left < (uint32_t) PER ? left : (uint32_t) PER;
+                                mbar_wait(bar_empty + s, ph);
+#if MNV_MLP_DIAG & 2
+                                mbar_arrive(bar_full + s);
+#else
+                                mbar_expect_tx(bar_full + s, k * part);
+                                for (uint32_t j = 0; j < k; ++j)
+                                    tma_bulk_g2s(s_stage + s * kStageB + j * kSlot, src + j * bytes, part, bar_full + s);
+#endif
+                                src += k * bytes;
+                                left -= k;
+                                if (++s == (uint32_t) kStages) {
+                                    s = 0;
+                                    ph ^= 1;
+                                }
                             }
                         }
                     }
@@ -352,48 +511,87 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                 }
             }
         }
+    } else if (warp == 9 && PAIR && !leader) {
+        // ===================== peer CTA: forward "my half has landed" to the leader's barrier =====================
+        if (lane == 0) {
+            const uint32_t full_leader = mapa_u32(smem_u32(bar_full), 0);
+            uint32_t s = 0, ph = 0;
+            for (int gb = g_first; gb < p.n_groups; gb += gridDim.x)
+                for (int l = 0; l < n_layers; ++l) {
+                    const uint32_t *w = s_layer + l * kLayerWords;
+                    const uint32_t n_segs = w[0] & 0xffu;
+                    for (int t = 0; t < kTiles; ++t)
+                        for (uint32_t i = 0; i < n_segs; ++i)
+                            for (uint32_t left = w[4 + 3 * i] & 0xffffu; left > 0; left -= (left < (uint32_t) PER ? left : (uint32_t) PER)) {
+                                mbar_wait(bar_full + s, ph);
+                                mbar_arrive_cluster(full_leader + 8 * s);
+                                if (++s == (uint32_t) kStages) {
+                                    s = 0;
+                                    ph ^= 1;
+                                }
+                            }
+                }
+        }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        // The whole warp runs the (warp-uniform) loop and one elected lane issues: per chunk the work is a
-        // barrier poll, two integer adds for the descriptors, the MMA and the commit that frees the weight
-        // stage — it must stay under the 128 clk an M=128 x N=256 x K=16 MMA takes (measured).
+        // The whole warp runs the (warp-uniform) loop and one elected lane issues.  What the lane pays between two MMAs
+        // is what bounds the kernel (a poll of the weights barrier ~70 clk and a commit cost more than the MMA itself:
+        // tools/micro/umma_bench.cu, profiles/r2_mlp_smem_diag.md), so the ring position is carried as addresses,
+        // one poll / one stage-release commit serve PER MMAs, and the poll of the NEXT stage is issued right behind the
+        // commit so that its latency overlaps the loop control.
         const uint32_t b_lo0 = ((smem_u32(s_stage) >> 4) & 0x3fffu) | ((128u >> 4) << 16);
         const uint32_t b_hi = ((kChunkK / 8 * 128u) >> 4) | (1u << 14);
         const bool issue = elect_one();
+        const uint32_t full0 = smem_u32(bar_full), empty0 = smem_u32(bar_empty);
         uint32_t s = 0, ph = 0, act_ph = 0;
+        uint32_t full_a = full0, empty_a = empty0, b_lo = b_lo0;
         MLP_T(long long w_act = 0, w_full = 0, w_act_l[kMaxLayers] = {0}; const long long t_begin = p.dbg ? clock64() : 0;)
-        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        bool ready = mbar_try<PAIR>(full_a, ph);
+        for (int gb = g_first; gb < p.n_groups; gb += gridDim.x) {
             for (int l = 0; l < n_layers; ++l) {
                 const uint32_t *w = s_layer + l * kLayerWords;
                 const uint32_t n_segs = w[0] & 0xffu, idesc = w[1];
                 for (int t = 0; t < kTiles; ++t) {
                     MLP_T(const long long t0 = p.dbg ? clock64() : 0;)
-                    mbar_wait(bar_act + t, act_ph);  // A operand of tile t ready, its accumulator drained
+                    while (!mbar_try<PAIR>(smem_u32(bar_act + t), act_ph)) {}  // A operand of tile t ready, accumulator drained
                     MLP_T(if (p.dbg) { const long long d = clock64() - t0; w_act += d; w_act_l[l] += d; })
                     uint32_t acc = 0;
                     for (uint32_t i = 0; i < n_segs; ++i) {
                         const uint32_t w2 = w[4 + 3 * i];
                         uint32_t a_lo = w[2 + 3 * i] + t * (w2 >> 16);
                         const uint32_t a_hi = w[3 + 3 * i];
-                        for (uint32_t c = w2 & 0xffffu; c > 0; --c) {
+                        for (uint32_t left = w2 & 0xffffu; left > 0;) {
+                            const uint32_t k = left < (uint32_t) PER ? left : (uint32_t) PER;
                             MLP_T(const long long t1 = p.dbg ? clock64() : 0;)
-                            mbar_wait(bar_full + s, ph);
+                            while (!ready) ready = mbar_try<PAIR>(full_a, ph);
                             MLP_T(if (p.dbg) w_full += clock64() - t1;)
                             tc_fence_after();
                             if (issue) {
-                                umma_bf16(tmem_base + t * kMaxN, ((uint64_t) a_hi << 32) | a_lo,
-                                          ((uint64_t) b_hi << 32) | (b_lo0 + s * (kStageBytes >> 4)), idesc, acc);
-                                tc_commit(bar_empty + s);  // frees the weight stage
+#pragma unroll
+                                for (uint32_t j = 0; j < (uint32_t) PER; ++j)
+                                    if (j < k) {
+                                        umma_bf16<PAIR>(tmem_base + t * kMaxN, ((uint64_t) a_hi << 32) | (a_lo + j * ((kChunkK / 8 * 128u) >> 4)),
+                                                        ((uint64_t) b_hi << 32) | (b_lo + j * (kSlot >> 4)), idesc, j == 0 ? acc : 1u);
+                                    }
+                                tc_commit_addr<PAIR>(empty_a);  // frees the weight stage (in both CTAs)
                             }
                             acc = 1;
-                            a_lo += (kChunkK / 8 * 128u) >> 4;  // next 16 K columns of the K-major A operand
+                            a_lo += k * ((kChunkK / 8 * 128u) >> 4);  // next K columns of the K-major A operand
+                            left -= k;
+                            full_a += 8;
+                            empty_a += 8;
+                            b_lo += kStageB >> 4;
                             if (++s == (uint32_t) kStages) {
                                 s = 0;
                                 ph ^= 1;
+                                full_a = full0;
+                                empty_a = empty0;
+                                b_lo = b_lo0;
                             }
+                            ready = mbar_try<PAIR>(full_a, ph);
                         }
                     }
-                    if (issue) tc_commit(bar_acc + t);  // accumulator complete -> epilogue of tile t
+                    if (issue) tc_commit_addr<PAIR>(smem_u32(bar_acc + t));  // accumulator complete -> epilogue of tile t
                     __syncwarp();
                 }
                 act_ph ^= 1;
@@ -415,7 +613,20 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
         const int row = q * 32 + lane;  // 0..127, TMEM lane
         const uint32_t tlane = tmem_base + ((uint32_t) (q * 32) << 16);
         uint32_t acc_ph = 0;
-        for (int grp = blockIdx.x; grp < p.n_groups; grp += gridDim.x) {
+        MLP_T(long long e_wait = 0, e_busy = 0, e_busy_l2 = 0, e_bar = 0; const long long e_begin = p.dbg ? clock64() : 0;)
+        const uint32_t act_leader = PAIR ? mapa_u32(smem_u32(bar_act), 0) : 0u;
+        // "A operand of tile t written / accumulator drained": every thread has fenced its own writes; PAIR: the warp's
+        // lanes meet and one of them arrives on the LEADER's barrier (a remote arrival for the peer CTA)
+        auto act_arrive = [&](int t) {
+            if constexpr (PAIR) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(act_leader + 8 * t);
+            } else {
+                mbar_arrive(bar_act + t);
+            }
+        };
+        for (int gb = g_first; gb < p.n_groups; gb += gridDim.x) {
+            const int grp = gb + (int) cta_rank;  // may lie past the last group in the peer CTA: its rows are invalid
             int64_t grow[kTiles];
             bool valid[kTiles];
             int ai[kTiles];
@@ -451,7 +662,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                 }
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(bar_act + t);
+                act_arrive(t);
             }
 
             float sigma[kTiles] = {0.f, 0.f};
@@ -466,7 +677,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                 const LayerDesc ld = S.layers[l];
                 const bool last_layer = ld.epilogue == kEpiOut;
                 // all 256 threads are done with layer l-1 (and its bias row); layer l's row is complete
+                MLP_T(const long long b0 = p.dbg ? clock64() : 0;)
                 asm volatile("bar.sync 1, 256;" ::: "memory");
+                MLP_T(if (p.dbg) e_bar += clock64() - b0;)
                 if (l + 1 < n_layers) {
                     const LayerDesc nx = S.layers[l + 1];
                     s_bias[((l + 1) & 1) * kMaxN + threadIdx.x] =
@@ -479,13 +692,31 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
 #pragma unroll
                 for (int t = 0; t < kTiles; ++t) {
                     uint8_t *act = s_act + t * kActBytes;
+                    MLP_T(const long long e0 = p.dbg ? clock64() : 0;)
                     mbar_wait(bar_acc + t, acc_ph);
+                    MLP_T(const long long e1 = p.dbg ? clock64() : 0; e_wait += e1 - e0;)
                     tc_fence_after();
                     const uint32_t taddr = tlane + t * kMaxN + col0;
+                    // the common shapes (256- and 128-wide layers that write the next A operand) run straight-line code
+                    bool lean = !last_layer && (ld.n == 256 || ld.n == 128);
+                    if (lean) {
+                        uint8_t *dst = act + a_off(row, col0, kActSBO);
+                        const float *sw = p.sigma_w + col0;
+                        switch (ld.epilogue | (ld.n == 256 ? 0x100u : 0u)) {
+                            case kEpiReluAct | 0x100u: epilogue_unit<kEpiReluAct, 128>(taddr, dst, lbias + col0, sw, sigma[t]); break;
+                            case kEpiReluActSigma | 0x100u: epilogue_unit<kEpiReluActSigma, 128>(taddr, dst, lbias + col0, sw, sigma[t]); break;
+                            case kEpiLinearAct | 0x100u: epilogue_unit<kEpiLinearAct, 128>(taddr, dst, lbias + col0, sw, sigma[t]); break;
+                            case kEpiReluAct: epilogue_unit<kEpiReluAct, 64>(taddr, dst, lbias + col0, sw, sigma[t]); break;
+                            case kEpiReluActApp:
+                                epilogue_unit<kEpiReluActApp, 64>(taddr, dst, p.app_bias + (size_t) ai[t] * p.head_n + col0, sw, sigma[t]);
+                                break;
+                            default: lean = false; break;
+                        }
+                    }
                     uint32_t r[2][32];
-                    if (n_mine > 0) tmem_ld32(taddr, r[0]);
+                    if (!lean && n_mine > 0) tmem_ld32(taddr, r[0]);
 #pragma unroll 1
-                    for (int c0 = 0; c0 < n_mine; c0 += 64) {
+                    for (int c0 = 0; c0 < (lean ? 0 : n_mine); c0 += 64) {
 #pragma unroll
                         for (int half = 0; half < 2; ++half) {
                             const int cc = c0 + half * 32;
@@ -552,6 +783,9 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                                     o.z = pack_bf16_relu(v[8 * g + 4], v[8 * g + 5]);
                                     o.w = pack_bf16_relu(v[8 * g + 6], v[8 * g + 7]);
                                 }
+#if MNV_MLP_DIAG & 1
+                                if (p.rows < 0)  // never true: keeps the arithmetic, drops the store traffic
+#endif
                                 *reinterpret_cast<uint4 *>(act + a_off(row, col + 8 * g, kActSBO)) = o;
                             }
                         }
@@ -575,29 +809,70 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_forward_kernel(MlpParams p
                         if (ld.epilogue == kEpiReluActSigma) __threadfence_block();
                         fence_async_smem();  // generic-proxy smem writes -> visible to the UMMA proxy
                         tc_fence_before();
-                        mbar_arrive(bar_act + t);
+                        act_arrive(t);
                     }
+                    MLP_T(if (p.dbg) { e_busy += clock64() - e1; if (l == 2) e_busy_l2 += clock64() - e1; })
                 }
                 acc_ph ^= 1;
             }
         }
+#ifdef MNV_MLP_TIMING
+        if (p.dbg && threadIdx.x == 0) {  // epilogue warp 0: waiting for accumulators / working / waiting for the other warps
+            long long *o = p.dbg + (size_t) blockIdx.x * 32;
+            o[3] = clock64() - e_begin;
+            o[4] = e_wait;
+            o[5] = e_busy;
+            o[6] = e_bar;
+            o[7] = e_busy_l2;
+        }
+#endif
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (PAIR) cluster_sync_all(); else __syncthreads();  // PAIR: neither CTA leaves while the other may still signal it
     if (warp == 9) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"(kTmemCols));
+        if constexpr (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
     }
 }
 
-constexpr int mlp_stages(bool viewdir) { return viewdir ? 5 : 7; }  // everything that is left
-constexpr size_t mlp_smem_bytes(bool viewdir) {
-    return kTiles * (kActBytes + kPeBytes + (viewdir ? kDirBytes : 0)) + mlp_stages(viewdir) * kStageBytes +
-           2 * kMaxN * 4 + (2 * kMaxStages + 2 * kTiles) * 8 + 16 + kMaxLayers * kLayerWords * 4;
+constexpr size_t kSmemLimit = 232448;  // opt-in dynamic shared memory of one sm_100 CTA
+constexpr size_t mlp_smem_fixed(bool viewdir) {
+    return kTiles * (kActBytes + kPeBytes + (viewdir ? kDirBytes : 0)) + 2 * kMaxN * 4 + (2 * kMaxStages + 2 * kTiles) * 8 + 16 +
+           kMaxLayers * kLayerWords * 4;
 }
-static_assert(mlp_smem_bytes(false) <= 232448 && mlp_smem_bytes(true) <= 232448 && mlp_stages(false) <= kMaxStages,
+// ring depth: everything that is left (7 x 8 KiB without view directions, 5 with; 13 / 10 stages of 4 KiB)
+constexpr int mlp_stages(bool viewdir, size_t stage_bytes) {
+    return (int) std::min<size_t>(kMaxStages, (kSmemLimit - mlp_smem_fixed(viewdir)) / stage_bytes);
+}
+constexpr size_t mlp_smem_bytes(bool viewdir, size_t stage_bytes) {
+    return mlp_smem_fixed(viewdir) + mlp_stages(viewdir, stage_bytes) * stage_bytes;
+}
+static_assert(mlp_stages(false, kStageBytes) == 7 && mlp_stages(true, kStageBytes) == 5 && mlp_stages(true, 2 * kStageBytes) >= 2,
               "shared memory budget of one sm_100 CTA");
+
+// launch shape: MNV_MLP_PAIR=0/1 (CTA pairs with cta_group::2 MMAs), MNV_MLP_PER=1/2/4 (MMAs per ring stage)
+struct MlpMode {
+    bool pair;
+    int per;
+};
+const MlpMode &mlp_mode() {
+    static const MlpMode m = [] {
+        MlpMode r{true, 2};
+        if (const char *e = std::getenv("MNV_MLP_PAIR")) r.pair = std::atoi(e) != 0;
+        if (const char *e = std::getenv("MNV_MLP_PER")) r.per = std::atoi(e);
+        if (r.per != 1 && r.per != 2 && r.per != 4) r.per = 2;
+        return r;
+    }();
+    return m;
+}
+using MlpKernel = void (*)(MlpParams);
+MlpKernel mlp_kernel(bool pair, int per) {
+    if (pair) return per == 1 ? mlp_forward_kernel<true, 1> : (per == 2 ? mlp_forward_kernel<true, 2> : mlp_forward_kernel<true, 4>);
+    return per == 1 ? mlp_forward_kernel<false, 1> : (per == 2 ? mlp_forward_kernel<false, 2> : mlp_forward_kernel<false, 4>);
+}
 
 // ------------------------------------------------------------------ host packing
 uint16_t f2bf(float f) {
@@ -805,8 +1080,8 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
     if (e == cudaSuccess) e = cudaMemcpy(m->sched_dev, &S, sizeof(S), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) std::max(mlp_smem_bytes(false), mlp_smem_bytes(true)));
+        e = cudaFuncSetAttribute(mlp_kernel(mlp_mode().pair, mlp_mode().per), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kSmemLimit);
     if (e != cudaSuccess) {
         *rc_out = cuda_fail(e, "mlp_create", __FILE__, __LINE__);
         mlp_destroy(m);
@@ -878,7 +1153,9 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
     p.ones_col = m->ones_col;
     p.sigma_activation = m->cfg.sigma_activation;
     p.out_real = m->cfg.out_rgb_dim;
-    const int grid = std::min(p.n_groups, m->num_sms);
+    const MlpMode &mode = mlp_mode();
+    // pairs: an even number of CTAs, one pair per TPC
+    const int grid = mode.pair ? std::min((p.n_groups + 1) & ~1, m->num_sms & ~1) : std::min(p.n_groups, m->num_sms);
     p.dbg = nullptr;
 #ifdef MNV_MLP_TIMING
     static const bool debug = std::getenv("MNV_MLP_DEBUG") != nullptr;  // dev: where does the issuer wait?
@@ -889,8 +1166,25 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
         MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 32 * sizeof(long long)));
         MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 32 * sizeof(long long), stream));
     }
-    p.n_stages = mlp_stages(p.need_viewdir != 0);
-    mlp_forward_kernel<<<grid, kMlpThreads, mlp_smem_bytes(p.need_viewdir != 0), stream>>>(p);
+    const size_t stage_bytes = (size_t) mode.per * (mode.pair ? kStageBytes / 2 : kStageBytes);
+    p.n_stages = mlp_stages(p.need_viewdir != 0, stage_bytes);
+    if (p.n_stages < 2) {
+        set_error("mlp_forward: MNV_MLP_PER=%d leaves %d ring stages", mode.per, p.n_stages);
+        return MNV_ERR_INVALID;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned) grid);
+    cfg.blockDim = dim3(kMlpThreads);
+    cfg.dynamicSmemBytes = mlp_smem_bytes(p.need_viewdir != 0, stage_bytes);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = mode.pair ? 1 : 0;
+    MNV_CUDA(cudaLaunchKernelEx(&cfg, mlp_kernel(mode.pair, mode.per), p));
     MNV_CUDA(cudaGetLastError());
     if (debug) {
         std::vector<long long> h((size_t) grid * 32);
@@ -900,7 +1194,8 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
         std::fprintf(stderr, "[mlp dbg] CTA0 issuer: total %lld clk = wait_act %lld + wait_full %lld + issue %lld; wait_act per layer:",
                      h[0], h[1], h[2], h[0] - h[1] - h[2]);
         for (int l = 0; l < m->sched.n_layers; ++l) std::fprintf(stderr, " %lld", h[8 + l]);
-        std::fprintf(stderr, "\n");
+        std::fprintf(stderr, "\n[mlp dbg] CTA0 epilogue warp 0: total %lld clk = wait_acc %lld + busy %lld (layer 2: %lld) + layer barrier %lld + rest\n",
+                     h[3], h[4], h[5], h[7], h[6]);
     }
     return MNV_OK;
 }

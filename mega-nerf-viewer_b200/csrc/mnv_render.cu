@@ -53,16 +53,32 @@ namespace {
 #ifndef MNV_SMEM_STATE
 #define MNV_SMEM_STATE 1  // park SH basis + shaded-only ray state in shared memory
 #endif
-constexpr int kThreads = 16 * MNV_TILE_H;  // each warp owns an 8x4-pixel tile
+#ifndef MNV_CTA_WARPS
+// warps per CTA.  Every warp owns an 8x4-pixel tile and never talks to the others (no barrier in the kernel), so a CTA
+// is only a scheduling unit: its warp slots, registers and shared memory stay allocated until its LAST warp's longest
+// ray ends.  Fewer warps per CTA free those slots earlier and let the tail of the frame spread over more SMs.
+#define MNV_CTA_WARPS (16 * MNV_TILE_H / 32)
+#endif
+#ifndef MNV_PACK_PRIO
+// candidate priorities are not carried through the march: the split priority (a depth) rides in bits 8..15 of `flags`,
+// the re-sample priority (the leaf's sample count) is re-read from the cell word once per ray
+#define MNV_PACK_PRIO 0
+#endif
+#ifndef MNV_DDA_SIGN
+#define MNV_DDA_SIGN 1  // exit distance of the unit cube by per-ray sign selection instead of three max()
+#endif
+constexpr int kWarps = MNV_CTA_WARPS;
+constexpr int kThreads = 32 * kWarps;  // each warp owns an 8x4-pixel tile
 #ifndef MNV_MIN_BLOCKS
-#define MNV_MIN_BLOCKS (1024 / (16 * MNV_TILE_H))  // resident CTAs per SM the register allocation targets
+#define MNV_MIN_BLOCKS (1024 / (32 * MNV_CTA_WARPS))  // resident CTAs per SM the register allocation targets
 #endif
 #ifndef MNV_MIN_BLOCKS_PLAIN
 // without candidate tracking the anchored march fits 56 registers: 9 CTAs per SM (measured 0.940 -> 0.906 ms;
 // the tracking variant spills at that budget and is slower, 1.004 -> 1.036 ms)
-#define MNV_MIN_BLOCKS_PLAIN (MNV_TILE_H == 8 ? 9 : MNV_MIN_BLOCKS)
+#define MNV_MIN_BLOCKS_PLAIN (MNV_CTA_WARPS == 4 ? 9 : (MNV_CTA_WARPS == 2 ? 18 : MNV_MIN_BLOCKS))
 #endif
-constexpr int kTileW = 16, kTileH = MNV_TILE_H;  // CTA tile; the multi-GPU partition is a multiple of 16x8
+constexpr int kTileW = 16, kTileH = MNV_TILE_H;  // launch-order tile; the multi-GPU partition is a multiple of 16x8
+constexpr int kWarpsPerTile = kTileW * kTileH / 32;
 constexpr int kMaxLevel = 22;    // q carries 23 bits per axis: leaf depth <= 23
 
 // words of per-ray state parked in shared memory (render_pixel)
@@ -76,7 +92,8 @@ struct RenderParams {
     mnv_render_options opt;
     RenderTargets tg;
     int mtiles_x;   // partition tiles per row (multi-GPU partition)
-    int tiles_x;    // 16x8-pixel CTA tiles per row
+    int tiles_x;    // 16x8-pixel tiles per row
+    int n_tiles;    // tiles of the frame
     int max_level;  // deepest level a descent may reach (tree max leaf depth - 1, <= 22)
     int path_levels;  // rows of the shared-memory node path (= max_level + 1; 0 with the anchor grid)
     int split_limit;  // min(opt.max_depth, 23): leaves at depth 23 cannot be split (23-bit cell coordinates)
@@ -280,6 +297,9 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
         int pdepth = 1;  // previous leaf depth: path valid for levels < pdepth
         const float clamp_hi = f_from_bits(0x3F7FFFEFu);  // 1.f - 1e-6f
         const uint32_t *__restrict__ cells = p.tree.cell;
+#if MNV_DDA_SIGN
+        const float ip0 = fmaxf(i0, 0.f), ip1 = fmaxf(i1, 0.f), ip2 = fmaxf(i2, 0.f);
+#endif
 
         // two steps per loop trip (the previous-cell registers rotate instead of being copied); the tracking
         // variants are register-bound and keep one
@@ -385,10 +405,19 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             // _dda_unit, rt_core.cuh:88-100: FMUL then FADD (not fused in the reference build)
             float tm;
             {
+#if MNV_DDA_SIGN
+                // max(a1, a1 + i) is a1 + i for i > 0 and a1 for i < 0 (rounding is monotonic; i is finite and
+                // non-zero by construction: 1 / (dir + 1e-9) in double); a1 >= +0 when i < 0, so adding +0 is exact
+                const float a2 = __fadd_rn(__fmul_rn(-fx, i0), ip0);
+                const float b2 = __fadd_rn(__fmul_rn(-fy, i1), ip1);
+                const float e2 = __fadd_rn(__fmul_rn(-fz, i2), ip2);
+                tm = fminf(fminf(fminf(a2, 1e4f), b2), e2);
+#else
                 const float a1 = __fmul_rn(-fx, i0), a2 = __fadd_rn(a1, i0);
                 const float b1 = __fmul_rn(-fy, i1), b2 = __fadd_rn(b1, i1);
                 const float e1 = __fmul_rn(-fz, i2), e2 = __fadd_rn(e1, i2);
                 tm = fminf(fminf(fminf(fmaxf(a1, a2), 1e4f), fmaxf(b1, b2)), fmaxf(e1, e2));
+#endif
             }
             // / cube_size (exact power of two), + step_size
             const float delta_t = __fadd_rn(__fmul_rn(tm, icube), opt.step_size);
@@ -403,13 +432,19 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 if (TRACK) {
                     if (weight > TS(kRsMaxW) && depth < p.split_limit) {
                         TSI(kRsSplitId) = (int32_t) slot;
-                        TSI(kRsSplitPrio) = depth;
                         TS(kRsMaxW) = weight;
+#if MNV_PACK_PRIO
+                        flags = (flags & 0xffff00ffu) | ((uint32_t) depth << 8) | 1u;
+#else
+                        TSI(kRsSplitPrio) = depth;
                         flags |= 1u;
+#endif
                     }
                     if (weight > TS(kRsMaxSW) && scount < opt.max_sample_count) {
                         TSI(kRsSampId) = (int32_t) slot;
+#if !MNV_PACK_PRIO
                         TSI(kRsSampPrio) = scount;
+#endif
                         TS(kRsMaxSW) = weight;
                         flags |= 2u;
                     }
@@ -479,6 +514,12 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             }
             t = __fadd_rn(t, delta_t);
         }
+#if MNV_PACK_PRIO
+        if (TRACK) {
+            if (flags & 1u) TSI(kRsSplitPrio) = (int) ((flags >> 8) & 0xffu);
+            if (flags & 2u) TSI(kRsSampPrio) = (int) ((__ldg(cells + TSI(kRsSampId)) >> 16) & 0x7fffu);
+        }
+#endif
 #if MNV_LAZY_EMPTY
         if (TRACK) {
             if (!(flags & 1u) && e_split != 0xffffffffu) {
@@ -578,15 +619,20 @@ __global__ void __launch_bounds__(kThreads, (ANCHOR && !TRACK && !LOGV && !VISIT
 render_voxels_kernel(const RenderParams p) {
     // [path_levels][kThreads] node path | [TERMS][kThreads] SH basis | [words][kThreads] ray state
     extern __shared__ int32_t s_dyn[];
-    const int bt = p.tg.tile_order ? p.tg.tile_order[blockIdx.x] : (int) blockIdx.x;
+    // warp v of the frame = sub-tile (v % 4) of 16x8-pixel tile (v / 4): the same pixel -> warp map for every kWarps
+    const int lane = threadIdx.x & 31;
+    const int vwarp = (int) blockIdx.x * kWarps + (int) (threadIdx.x >> 5);
+    const int sub = vwarp % kWarpsPerTile;
+    const int bt_raw = vwarp / kWarpsPerTile;
+    if (bt_raw >= p.n_tiles) return;
+    const int bt = p.tg.tile_order ? p.tg.tile_order[bt_raw] : bt_raw;
     const int bty = bt / p.tiles_x, btx = bt - bty * p.tiles_x;
     if (p.tg.tile_mod > 1) {
         const int mt = ((bty * kTileH) / p.tg.tile_h) * p.mtiles_x + (btx * kTileW) / p.tg.tile_w;
         if (mt % p.tg.tile_mod != p.tg.tile_rem) return;
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int x = btx * kTileW + (warp & 1) * 8 + (lane & 7);
-    const int y = bty * kTileH + (warp >> 1) * 4 + (lane >> 3);
+    const int x = btx * kTileW + (sub & 1) * 8 + (lane & 7);
+    const int y = bty * kTileH + (sub >> 1) * 4 + (lane >> 3);
     if (x >= p.cam.width || y >= p.cam.height) return;
     render_pixel<TERMS, TRACK, LOGV, VISIT, ANCHOR>(
             p, x, y, s_dyn + threadIdx.x,
@@ -712,7 +758,8 @@ int launch_render_voxels(DeviceTree &tree, const mnv_camera &cam,
     if (!p.tg.tile_order && tree.tile_order_dev && tree.tile_order_n == p.tiles_x * tiles_y)
         p.tg.tile_order = tree.tile_order_dev;
     const int terms = tree.format == MNV_FORMAT_SH ? tree.basis_dim : 0;
-    const dim3 grid((unsigned) (p.tiles_x * tiles_y));
+    p.n_tiles = p.tiles_x * tiles_y;
+    const dim3 grid((unsigned) ((p.n_tiles * kWarpsPerTile + kWarps - 1) / kWarps));
     const size_t smem = (size_t) (p.path_levels +
                                   (MNV_SMEM_STATE ? terms + (track ? kRsWordsTrack : kRsWordsBase) : 0)) *
                         kThreads * sizeof(int32_t);
