@@ -853,21 +853,24 @@ constexpr size_t mlp_smem_bytes(bool viewdir, size_t stage_bytes) {
 static_assert(mlp_stages(false, kStageBytes) == 7 && mlp_stages(true, kStageBytes) == 5 && mlp_stages(true, 2 * kStageBytes) >= 2,
               "shared memory budget of one sm_100 CTA");
 
-// launch shape: MNV_MLP_PAIR=0/1 (CTA pairs with cta_group::2 MMAs), MNV_MLP_PER=1/2/4 (MMAs per ring stage)
+// launch shape (dev overrides): MNV_MLP_PAIR=0/1 (CTA pairs with cta_group::2 MMAs), MNV_MLP_PER=1/2/4 (MMAs per ring stage;
+// 0 = by model: 4 — three 16 KiB stages per CTA — without view directions, 2 — five 8 KiB stages — with them).
+// Measured at 262 144 rows (profiles/r2_mlp_modes.log): pair/4 0.346 ms, pair/1 0.376, pair/2 0.404, single/1 0.382, single/2 0.408.
 struct MlpMode {
     bool pair;
     int per;
 };
 const MlpMode &mlp_mode() {
     static const MlpMode m = [] {
-        MlpMode r{true, 2};
+        MlpMode r{true, 0};
         if (const char *e = std::getenv("MNV_MLP_PAIR")) r.pair = std::atoi(e) != 0;
         if (const char *e = std::getenv("MNV_MLP_PER")) r.per = std::atoi(e);
-        if (r.per != 1 && r.per != 2 && r.per != 4) r.per = 2;
+        if (r.per != 1 && r.per != 2 && r.per != 4) r.per = 0;
         return r;
     }();
     return m;
 }
+int mlp_per(const MlpMode &mode, bool viewdir) { return mode.per ? mode.per : (viewdir ? 2 : 4); }
 using MlpKernel = void (*)(MlpParams);
 MlpKernel mlp_kernel(bool pair, int per) {
     if (pair) return per == 1 ? mlp_forward_kernel<true, 1> : (per == 2 ? mlp_forward_kernel<true, 2> : mlp_forward_kernel<true, 4>);
@@ -1080,8 +1083,8 @@ MlpModel *mlp_create(const mnv_mlp_desc &d, int device, int *rc_out) {
     if (e == cudaSuccess) e = cudaMemcpy(m->sched_dev, &S, sizeof(S), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(mlp_kernel(mlp_mode().pair, mlp_mode().per), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int) kSmemLimit);
+        e = cudaFuncSetAttribute(mlp_kernel(mlp_mode().pair, mlp_per(mlp_mode(), d.need_viewdir != 0)),
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemLimit);
     if (e != cudaSuccess) {
         *rc_out = cuda_fail(e, "mlp_create", __FILE__, __LINE__);
         mlp_destroy(m);
@@ -1166,10 +1169,11 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
         MNV_CUDA(cudaMalloc(&p.dbg, (size_t) grid * 32 * sizeof(long long)));
         MNV_CUDA(cudaMemsetAsync(p.dbg, 0, (size_t) grid * 32 * sizeof(long long), stream));
     }
-    const size_t stage_bytes = (size_t) mode.per * (mode.pair ? kStageBytes / 2 : kStageBytes);
+    const int per = mlp_per(mode, p.need_viewdir != 0);
+    const size_t stage_bytes = (size_t) per * (mode.pair ? kStageBytes / 2 : kStageBytes);
     p.n_stages = mlp_stages(p.need_viewdir != 0, stage_bytes);
     if (p.n_stages < 2) {
-        set_error("mlp_forward: MNV_MLP_PER=%d leaves %d ring stages", mode.per, p.n_stages);
+        set_error("mlp_forward: MNV_MLP_PER=%d leaves %d ring stages", per, p.n_stages);
         return MNV_ERR_INVALID;
     }
     cudaLaunchConfig_t cfg = {};
@@ -1184,7 +1188,7 @@ static int mlp_launch(const MlpModel *m, const float *x_dev, const int32_t *row_
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = mode.pair ? 1 : 0;
-    MNV_CUDA(cudaLaunchKernelEx(&cfg, mlp_kernel(mode.pair, mode.per), p));
+    MNV_CUDA(cudaLaunchKernelEx(&cfg, mlp_kernel(mode.pair, per), p));
     MNV_CUDA(cudaGetLastError());
     if (debug) {
         std::vector<long long> h((size_t) grid * 32);
