@@ -62,7 +62,7 @@ namespace {
 #ifndef MNV_PACK_PRIO
 // candidate priorities are not carried through the march: the split priority (a depth) rides in bits 8..15 of `flags`,
 // the re-sample priority (the leaf's sample count) is re-read from the cell word once per ray
-#define MNV_PACK_PRIO 0
+#define MNV_PACK_PRIO 1
 #endif
 #ifndef MNV_DDA_SIGN
 #define MNV_DDA_SIGN 1  // exit distance of the unit cube by per-ray sign selection instead of three max()
@@ -96,6 +96,7 @@ struct RenderParams {
     int n_tiles;    // tiles of the frame
     int max_level;  // deepest level a descent may reach (tree max leaf depth - 1, <= 22)
     int path_levels;  // rows of the shared-memory node path (= max_level + 1; 0 with the anchor grid)
+    uint32_t samp_limit;  // max_sample_count << 16, saturated: (cell word & 0x7fffffff) < samp_limit <=> count < max_sample_count
     int split_limit;  // min(opt.max_depth, 23): leaves at depth 23 cannot be split (23-bit cell coordinates)
     // anchor grid (mnv_internal.cuh): entry index = ((ax * dim + ay) * dim + az) - bias with a? the raw bits of
     // fma_rd(p?, 2^A, 2^23) — the 0x4B000000 exponents of the three terms fold into one constant
@@ -422,6 +423,8 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
             // / cube_size (exact power of two), + step_size
             const float delta_t = __fadd_rn(__fmul_rn(tm, icube), opt.step_size);
             const int scount = (int) ((cw >> 16) & 0x7fffu);
+            // scount < max_sample_count on the raw word (count in bits 16..30 above the sigma bits): one compare
+            const bool samp_ok = (cw & 0x7fffffffu) < p.samp_limit;
 
             if (shaded) {
                 if (LOGV) ++nshaded;
@@ -440,7 +443,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                         flags |= 1u;
 #endif
                     }
-                    if (weight > TS(kRsMaxSW) && scount < opt.max_sample_count) {
+                    if (weight > TS(kRsMaxSW) && samp_ok) {
                         TSI(kRsSampId) = (int32_t) slot;
 #if !MNV_PACK_PRIO
                         TSI(kRsSampPrio) = scount;
@@ -500,13 +503,13 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                     e_split = slot;
                     e_depth = depth;
                 }
-                if (scount < opt.max_sample_count) e_samp = slot;
+                if (samp_ok) e_samp = slot;
 #else
                 if (!(flags & 1u) && depth < p.split_limit) {
                     TSI(kRsSplitId) = (int32_t) slot;
                     TSI(kRsSplitPrio) = depth;
                 }
-                if (!(flags & 2u) && scount < opt.max_sample_count) {
+                if (!(flags & 2u) && samp_ok) {
                     TSI(kRsSampId) = (int32_t) slot;
                     TSI(kRsSampPrio) = scount;
                 }
@@ -731,6 +734,7 @@ int launch_render_voxels(DeviceTree &tree, const mnv_camera &cam,
     const bool anchored = tree.anchor_level > 0 && tree.anchor != nullptr;
     p.path_levels = anchored ? 0 : p.max_level + 1;
     p.split_limit = std::min(opt.max_depth, 23);
+    p.samp_limit = opt.max_sample_count <= 0 ? 0u : (opt.max_sample_count >= 32768 ? 0x80000000u : (uint32_t) opt.max_sample_count << 16);
     p.anchor = tree.anchor;
     p.anchor_level = tree.anchor_level;
     p.anchor_dim = 1u << tree.anchor_level;

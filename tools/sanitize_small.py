@@ -1,5 +1,5 @@
 """Dev: one small pass over every kernel family, meant to run under `compute-sanitizer --tool memcheck`
-(tools/gpu_sanitize.sh).  Sizes are tiny: the sanitizer slows kernels down 10-100x."""
+(tools/sessions/gpu_sanitize.sh).  Sizes are tiny: the sanitizer slows kernels down 10-100x."""
 import os
 import sys
 
