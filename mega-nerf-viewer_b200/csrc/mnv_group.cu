@@ -18,6 +18,9 @@
 // exchanged and committed everywhere — the C++ form of multigpu.ReplicatedPipeline.refine_frame, with peer copies
 // in place of NCCL.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -279,123 +282,103 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
     int rc = group_march(g, cam, opt, band_rows, true);
     if (rc != MNV_OK) return rc;
     const int64_t rays = (int64_t) cam->width * cam->height;
-    // 1. votes of every replica's own bands -> records (sync per replica: the record count sizes the exchange)
-    std::vector<int64_t> n_rec((size_t) n, 0);
     const int64_t cap_local = rays / n + (int64_t) cam->width * band_rows + 1024;
-    for (int i = 0; i < n; ++i) {
+    const int max_n = opt->split_batch_size;
+    const int c = opt->samples_per_corner;
+    const int rd = 3 + (opt->need_viewdir ? 3 : 0) + (opt->appearance_embedding != -1 ? 1 : 0);
+    std::vector<int64_t> n_rec((size_t) n, 0);
+    std::vector<int> k((size_t) n, 0);
+    ++g->step;
+    // One host thread per replica for the whole exchange: issued from one thread, the ~30 runtime calls a replica needs per
+    // frame (reduction, 7 record pulls + paddings, selection, sampling, MLP share, 7 payload pulls, commit) queue up behind
+    // those of the other replicas — 4.0 ms per 4K frame on 8 GPUs against 3.4 ms on 4 (profiles/r2_headless_group_n8b.log).
+    // The threads meet at three points: record counts known, selection sizes known, payload shares written.
+    // (Replicas that share a device — tests — serialise on that device's scratch mutex inside launch / finish pairs.)
+    struct Meet {
+        std::mutex mu;
+        std::condition_variable cv;
+        int waiting = 0, generation = 0;
+        void arrive_and_wait(int parties) {
+            std::unique_lock<std::mutex> lk(mu);
+            const int gen = generation;
+            if (++waiting == parties) {
+                waiting = 0;
+                ++generation;
+                cv.notify_all();
+            } else {
+                cv.wait(lk, [&] { return generation != gen; });
+            }
+        }
+    } meet;
+    std::atomic<int> failed{MNV_OK};
+    std::atomic<int> full{0};
+    std::vector<std::string> msgs((size_t) n);
+    auto worker = [&](int i) {
         mnv_group::Replica &rp = g->r[(size_t) i];
-        MNV_CUDA(cudaSetDevice(rp.device));
+        auto fail = [&](int code) {
+            int expect = MNV_OK;
+            if (failed.compare_exchange_strong(expect, code)) msgs[(size_t) i] = mnv_last_error();  // the message is thread-local
+        };
+#define GRP_CUDA(x)                                                   \
+    do {                                                              \
+        if (failed.load() == MNV_OK) {                                \
+            const cudaError_t e_ = (x);                               \
+            if (e_ != cudaSuccess) fail(cuda_fail(e_, #x, __FILE__, __LINE__)); \
+        }                                                             \
+    } while (0)
+        cudaSetDevice(rp.device);
+        cudaStream_t s = stream_of(rp);
+        // 1. votes of this replica's own bands -> records, into slot i of its own gather buffer (the finish call
+        //    synchronises the stream: the record count sizes the exchange)
         if (rp.rec_cap < cap_local) {
             cudaFree(rp.records);
             rp.records = nullptr;
             rp.rec_cap = 0;
-            MNV_CUDA(cudaMalloc(&rp.records, (size_t) n * cap_local * 3 * sizeof(uint32_t)));
-            rp.rec_cap = cap_local;
+            GRP_CUDA(cudaMalloc(&rp.records, (size_t) n * cap_local * 3 * sizeof(uint32_t)));
+            if (rp.records) rp.rec_cap = cap_local;
         }
-    }
-    // launch on every device before waiting for any (replicas that share a device — tests — go one wave at a time:
-    // the selection scratch is per device)
-    for (int w0 = 0; w0 < n;) {
-        int w1 = w0;
-        while (w1 < n) {
-            bool clash = false;
-            for (int j = w0; j < w1; ++j) clash |= g->r[(size_t) j].device == g->r[(size_t) w1].device;
-            if (clash) break;
-            ++w1;
+        if (!rp.nodes) GRP_CUDA(cudaMalloc(&rp.nodes, (size_t) 16384 * 2 * sizeof(int32_t)));
+        if (failed.load() == MNV_OK) {
+            int r = vote_reduce_launch(rp.split, rays, rp.records + (size_t) i * rp.rec_cap * 3, rp.rec_cap, s);
+            if (r == MNV_OK) r = vote_reduce_finish(rp.rec_cap, &n_rec[(size_t) i], s);
+            if (r != MNV_OK) fail(r);
         }
-        for (int i = w0; i < w1; ++i) {
-            mnv_group::Replica &rp = g->r[(size_t) i];
-            MNV_CUDA(cudaSetDevice(rp.device));
-            // own records go to slot i of the replica's own gather buffer
-            rc = vote_reduce_launch(rp.split, rays, rp.records + (size_t) i * rp.rec_cap * 3, rp.rec_cap, stream_of(rp));
-            if (rc != MNV_OK) return rc;
-        }
-        for (int i = w0; i < w1; ++i) {
-            mnv_group::Replica &rp = g->r[(size_t) i];
-            MNV_CUDA(cudaSetDevice(rp.device));
-            const int rc_i = vote_reduce_finish(rp.rec_cap, &n_rec[(size_t) i], stream_of(rp));
-            if (rc_i != MNV_OK) rc = rc_i;
-        }
-        if (rc != MNV_OK) return rc;
-        w0 = w1;
-    }
-    // 2. exchange: replica i pulls replica j's records (peer copy); record layout [j][rec_cap][3], unused rows are
-    //    skipped by passing each block separately to the selection
-    for (int i = 0; i < n; ++i) {
-        mnv_group::Replica &rp = g->r[(size_t) i];
-        MNV_CUDA(cudaSetDevice(rp.device));
-        for (int j = 0; j < n; ++j) {
-            if (j == i || n_rec[(size_t) j] == 0) continue;
-            MNV_CUDA(cudaMemcpyAsync(rp.records + (size_t) j * rp.rec_cap * 3,
-                                     g->r[(size_t) j].records + (size_t) j * g->r[(size_t) j].rec_cap * 3,
-                                     (size_t) n_rec[(size_t) j] * 3 * sizeof(uint32_t), cudaMemcpyDefault, stream_of(rp)));
-        }
-        // zero-vote padding between the blocks so that one contiguous range can be handed to the selection
-        for (int j = 0; j < n; ++j) {
+        meet.arrive_and_wait(n);
+        // 2. exchange: pull the peers' records (peer copies); layout [j][rec_cap][3] with zero-vote padding between the
+        //    blocks so that one contiguous range can be handed to the selection
+        for (int j = 0; j < n && failed.load() == MNV_OK; ++j) {
+            if (j != i && n_rec[(size_t) j] > 0)
+                GRP_CUDA(cudaMemcpyAsync(rp.records + (size_t) j * rp.rec_cap * 3,
+                                         g->r[(size_t) j].records + (size_t) j * g->r[(size_t) j].rec_cap * 3,
+                                         (size_t) n_rec[(size_t) j] * 3 * sizeof(uint32_t), cudaMemcpyDefault, s));
             const int64_t pad = rp.rec_cap - n_rec[(size_t) j];
             if (pad > 0)
-                MNV_CUDA(cudaMemsetAsync(rp.records + ((size_t) j * rp.rec_cap + (size_t) n_rec[(size_t) j]) * 3, 0,
-                                         (size_t) pad * 3 * sizeof(uint32_t), stream_of(rp)));
+                GRP_CUDA(cudaMemsetAsync(rp.records + ((size_t) j * rp.rec_cap + (size_t) n_rec[(size_t) j]) * 3, 0,
+                                         (size_t) pad * 3 * sizeof(uint32_t), s));
         }
-    }
-    // 3. identical selection + linking on every replica
-    const int max_n = opt->split_batch_size;
-    std::vector<int> k((size_t) n, 0);
-    for (auto &rp : g->r) {
-        MNV_CUDA(cudaSetDevice(rp.device));
-        if (!rp.nodes) MNV_CUDA(cudaMalloc(&rp.nodes, (size_t) 16384 * 2 * sizeof(int32_t)));
-    }
-    for (int w0 = 0; w0 < n;) {
-        int w1 = w0;
-        while (w1 < n) {
-            bool clash = false;
-            for (int j = w0; j < w1; ++j) clash |= g->r[(size_t) j].device == g->r[(size_t) w1].device;
-            if (clash) break;
-            ++w1;
-        }
-        for (int i = w0; i < w1; ++i) {
-            mnv_group::Replica &rp = g->r[(size_t) i];
-            MNV_CUDA(cudaSetDevice(rp.device));
-            rc = select_candidates_launch(0, nullptr, 0, rp.records, (int64_t) n * rp.rec_cap, max_n, rp.nodes, stream_of(rp));
-            if (rc != MNV_OK) return rc;
-        }
-        for (int i = w0; i < w1; ++i) {
-            mnv_group::Replica &rp = g->r[(size_t) i];
-            MNV_CUDA(cudaSetDevice(rp.device));
+        // 3. identical selection on every replica
+        if (failed.load() == MNV_OK) {
             int cand = 0;
-            const int rc_i = select_candidates_finish(&k[(size_t) i], &cand, stream_of(rp));
-            if (rc_i != MNV_OK) rc = rc_i;
+            int r = select_candidates_launch(0, nullptr, 0, rp.records, (int64_t) n * rp.rec_cap, max_n, rp.nodes, s);
+            if (r == MNV_OK) r = select_candidates_finish(&k[(size_t) i], &cand, s);
+            if (r != MNV_OK) fail(r);
         }
-        if (rc != MNV_OK) return rc;
-        w0 = w1;
-    }
-    for (int i = 1; i < n; ++i)
-        if (k[(size_t) i] != k[0]) {
+        meet.arrive_and_wait(n);
+        if (failed.load() == MNV_OK && k[(size_t) i] != k[0]) {
             set_error("group refine: replicas selected %d vs %d leaves", k[(size_t) i], k[0]);
-            return MNV_ERR_INVALID;
+            fail(MNV_ERR_INVALID);
         }
-    const int kk = k[0];
-    ++g->step;
-    if (kk > 0) {
-        DeviceTree &t0 = device_tree_of(g->r[0].tree);
-        if (t0.capacity + kk > t0.max_capacity) {
-            rc = group_deliver(g, cam, image_linear_dev0, image_arr_dev0, rgba_host);  // "Full", cuda_renderer.cpp:228-231
-            return rc == MNV_OK ? mnv_group_synchronize(g) : rc;
-        }
-        const int c = opt->samples_per_corner;
-        const int rd = 3 + (opt->need_viewdir ? 3 : 0) + (opt->appearance_embedding != -1 ? 1 : 0);
+        const int kk = k[0];
+        const DeviceTree &t = device_tree_of(rp.tree);
+        const bool is_full = kk > 0 && t.capacity + kk > t.max_capacity;  // "Full", cuda_renderer.cpp:228-231
+        if (is_full) full.store(1);
         const int children = kk * 8;
         const int per = (children + n - 1) / n;
         int rec_bytes = 0;
-        mnv_tree_record_bytes(g->r[0].tree, &rec_bytes);
-        const int out_stride = t0.data_dim + 1;
-        // One host thread per replica for this stage: mnv_query_submodules ends with a synchronisation (it validates the
-        // cluster ids and recycles its index scratch), so issued from one thread the replicas' MLP shares would run one
-        // after the other.  (Replicas that share a device — tests — serialise on that device's scratch mutex.)
-        auto replica_stage = [&](int i) -> int {
-            mnv_group::Replica &rp = g->r[(size_t) i];
-            MNV_CUDA(cudaSetDevice(rp.device));
-            cudaStream_t s = stream_of(rp);
+        mnv_tree_record_bytes(rp.tree, &rec_bytes);
+        const int out_stride = t.data_dim + 1;
+        const bool go = kk > 0 && !is_full;
+        if (go && failed.load() == MNV_OK) {
             const size_t need_s = (size_t) children * c * rd, need_r = (size_t) per * c * out_stride,
                          need_p = (size_t) n * per * rec_bytes;
             if (rp.samples_cap < need_s) {
@@ -404,78 +387,73 @@ int mnv_group_refine_frame(mnv_group *g, mnv_model *const *models, const mnv_cam
                 rp.samples = nullptr;
                 rp.cluster = nullptr;
                 rp.samples_cap = 0;
-                MNV_CUDA(cudaMalloc(&rp.samples, need_s * sizeof(float)));
-                MNV_CUDA(cudaMalloc(&rp.cluster, (size_t) children * c * sizeof(int16_t)));
-                rp.samples_cap = need_s;
+                GRP_CUDA(cudaMalloc(&rp.samples, need_s * sizeof(float)));
+                GRP_CUDA(cudaMalloc(&rp.cluster, (size_t) children * c * sizeof(int16_t)));
+                if (rp.samples && rp.cluster) rp.samples_cap = need_s;
             }
             if (rp.results_cap < need_r) {
                 cudaFree(rp.results);
                 rp.results = nullptr;
                 rp.results_cap = 0;
-                MNV_CUDA(cudaMalloc(&rp.results, need_r * sizeof(float)));
-                rp.results_cap = need_r;
+                GRP_CUDA(cudaMalloc(&rp.results, need_r * sizeof(float)));
+                if (rp.results) rp.results_cap = need_r;
             }
             if (rp.payload_cap < need_p) {
                 cudaFree(rp.payload);
                 rp.payload = nullptr;
                 rp.payload_cap = 0;
-                MNV_CUDA(cudaMalloc(&rp.payload, need_p));
-                rp.payload_cap = need_p;
+                GRP_CUDA(cudaMalloc(&rp.payload, need_p));
+                if (rp.payload) rp.payload_cap = need_p;
             }
-            // the same counter-based random numbers on every replica (torch::rand in the reference, :250)
-            int r = fill_uniform(rp.samples, (int64_t) need_s, seed + g->step, s);
-            if (r == MNV_OK)
-                r = mnv_add_children_and_generate_samples(rp.tree, opt, rp.nodes, kk, rp.samples, rp.cluster, nullptr,
-                                                          grid_dim, min_position, range, s);
-            if (r != MNV_OK) return r;
-            // 4. this replica's share of the MLP rows -> payload records, into slot i of its own gather buffer
-            const int lo = std::min(i * per, children), hi = std::min((i + 1) * per, children);
-            MNV_CUDA(cudaMemsetAsync(rp.payload + (size_t) i * per * rec_bytes, 0, (size_t) per * rec_bytes, s));
-            if (hi > lo) {
-                r = mnv_query_submodules(models[i], rp.cluster + (size_t) lo * c, rp.samples + (size_t) lo * c * rd, rd,
-                                         (int64_t) (hi - lo) * c, rp.results, out_stride, s);
+            if (failed.load() == MNV_OK) {
+                // the same counter-based random numbers on every replica (torch::rand in the reference, :250)
+                int r = fill_uniform(rp.samples, (int64_t) need_s, seed + g->step, s);
                 if (r == MNV_OK)
-                    r = mnv_tree_reduce_children(rp.tree, opt, hi - lo, rp.results, out_stride,
-                                                 rp.payload + (size_t) i * per * rec_bytes, s);
-                if (r != MNV_OK) return r;
-            }
-            MNV_CUDA(cudaEventRecord(rp.done, s));
-            return MNV_OK;
-        };
-        {
-            std::vector<int> rcs((size_t) n, MNV_OK);
-            std::vector<std::string> msgs((size_t) n);
-            std::vector<std::thread> workers;
-            for (int i = 1; i < n; ++i)
-                workers.emplace_back([&, i] {
-                    rcs[(size_t) i] = replica_stage(i);
-                    if (rcs[(size_t) i] != MNV_OK) msgs[(size_t) i] = mnv_last_error();  // the message is thread-local
-                });
-            rcs[0] = replica_stage(0);
-            for (auto &w : workers) w.join();
-            for (int i = 0; i < n; ++i)
-                if (rcs[(size_t) i] != MNV_OK) {
-                    if (i > 0) set_error("%s", msgs[(size_t) i].c_str());
-                    return rcs[(size_t) i];
+                    r = mnv_add_children_and_generate_samples(rp.tree, opt, rp.nodes, kk, rp.samples, rp.cluster, nullptr,
+                                                              grid_dim, min_position, range, s);
+                // 4. this replica's share of the MLP rows -> payload records, into slot i of its own gather buffer
+                const int lo = std::min(i * per, children), hi = std::min((i + 1) * per, children);
+                if (r == MNV_OK) GRP_CUDA(cudaMemsetAsync(rp.payload + (size_t) i * per * rec_bytes, 0, (size_t) per * rec_bytes, s));
+                if (r == MNV_OK && hi > lo) {
+                    r = mnv_query_submodules(models[i], rp.cluster + (size_t) lo * c, rp.samples + (size_t) lo * c * rd, rd,
+                                             (int64_t) (hi - lo) * c, rp.results, out_stride, s);
+                    if (r == MNV_OK)
+                        r = mnv_tree_reduce_children(rp.tree, opt, hi - lo, rp.results, out_stride,
+                                                     rp.payload + (size_t) i * per * rec_bytes, s);
                 }
+                if (r != MNV_OK) fail(r);
+                GRP_CUDA(cudaEventRecord(rp.done, s));
+            }
         }
-        // 5. payload exchange (64 B per child) and commit everywhere
-        for (int i = 0; i < n; ++i) {
-            mnv_group::Replica &rp = g->r[(size_t) i];
-            MNV_CUDA(cudaSetDevice(rp.device));
-            cudaStream_t s = stream_of(rp);
+        meet.arrive_and_wait(n);
+        // 5. payload exchange (64 B per child) and commit
+        if (go && failed.load() == MNV_OK) {
             for (int j = 0; j < n; ++j) {
                 if (j == i) continue;
-                MNV_CUDA(cudaStreamWaitEvent(s, g->r[(size_t) j].done, 0));
-                MNV_CUDA(cudaMemcpyAsync(rp.payload + (size_t) j * per * rec_bytes,
+                GRP_CUDA(cudaStreamWaitEvent(s, g->r[(size_t) j].done, 0));
+                GRP_CUDA(cudaMemcpyAsync(rp.payload + (size_t) j * per * rec_bytes,
                                          g->r[(size_t) j].payload + (size_t) j * per * rec_bytes, (size_t) per * rec_bytes,
                                          cudaMemcpyDefault, s));
             }
-            rc = mnv_tree_commit_children_records(rp.tree, opt, kk, rp.payload, s);
-            if (rc != MNV_OK) return rc;
+            if (failed.load() == MNV_OK) {
+                const int r = mnv_tree_commit_children_records(rp.tree, opt, kk, rp.payload, s);
+                if (r != MNV_OK) fail(r);
+            }
         }
-        if (nodes_added) *nodes_added = kk;
+#undef GRP_CUDA
+    };
+    {
+        std::vector<std::thread> workers;
+        for (int i = 1; i < n; ++i) workers.emplace_back(worker, i);
+        worker(0);
+        for (auto &w : workers) w.join();
     }
+    if (failed.load() != MNV_OK) {
+        for (int i = 0; i < n; ++i)
+            if (!msgs[(size_t) i].empty()) set_error("%s", msgs[(size_t) i].c_str());
+        return failed.load();
+    }
+    if (nodes_added && !full.load()) *nodes_added = k[0];
     rc = group_deliver(g, cam, image_linear_dev0, image_arr_dev0, rgba_host);
     // the exchange buffers are read by the peers: nobody may start the next frame's reduction before all copies landed
     if (rc == MNV_OK) rc = mnv_group_synchronize(g);
