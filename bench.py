@@ -334,6 +334,35 @@ def frame_parity(got: np.ndarray, want: np.ndarray) -> dict:
             "psnr": 99.0 if mse == 0 else float(10 * np.log10(255.0 ** 2 / mse))}
 
 
+def gather_frame(torch, dist, dev, blk, first: int, n_pixels: int, world: int):
+    """Every rank contributes the RGBA8 pixels [first, first + len(blk)) it owns; returns the whole frame [n_pixels, 4]
+    as numpy (meaningful on every rank; parity checks use rank 0's)."""
+    blk = blk.reshape(-1, 4)
+    meta = torch.tensor([first, blk.shape[0]], device=dev, dtype=torch.int64)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    metas = [m.cpu().tolist() for m in metas]
+    cap = max(m[1] for m in metas)
+    buf = torch.zeros((max(cap, 1), 4), dtype=torch.uint8, device=dev)
+    buf[: blk.shape[0]] = blk
+    bufs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    frame = np.zeros((n_pixels, 4), np.uint8)
+    for (f, n), b in zip(metas, bufs):
+        frame[f:f + n] = b[:n].cpu().numpy()
+    return frame
+
+
+def worst_parity(pars):
+    """The worst of several frame_parity records."""
+    w = None
+    for pr in pars:
+        if w is None or pr["max_abs"] > w["max_abs"] or pr["psnr"] < w["psnr"]:
+            w = dict(pr, frac_within_1=min(pr["frac_within_1"], (w or pr)["frac_within_1"]), psnr=min(pr["psnr"], (w or pr)["psnr"]),
+                     max_abs=max(pr["max_abs"], (w or pr)["max_abs"]), bit_exact=pr["bit_exact"] and (w or pr)["bit_exact"])
+    return w
+
+
 def cpu_baseline(tree, cams, O, opt_kw, seconds_budget=20.0):
     """CPU oracle (port) on all host cores; bounded sample: whole frames of the
     orbit until ~seconds_budget elapsed (at least one)."""
@@ -800,6 +829,20 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
     e2e_ms = timed(args.steps, 3, True)
+    # parity, verified in the run that is timed: the sharded frame (every owner's block) against the frame rank 0 renders
+    # alone from the WHOLE tree.  Tolerance parity by construction: early termination acts per segment.
+    full_dt = mnv.DeviceTree(tree, device=local_rank) if rank == 0 else None
+    pars = []
+    for pose in (0, 7):
+        blk = sp.render_block(cams[pose], opt)
+        torch.cuda.synchronize()
+        frame = gather_frame(torch, dist, dev, blk[:n], first, P, world)
+        if rank == 0:
+            want = full_dt.render(cams[pose], opt).cpu().numpy().reshape(P, 4)
+            pars.append(frame_parity(frame, want))
+    parity = worst_parity(pars) if rank == 0 else None
+    if full_dt is not None:
+        full_dt.close()
     nodes = torch.tensor([sp.split.local_nodes if hybrid else sp.local_nodes], device=dev)
     dist.all_reduce(nodes, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -817,6 +860,8 @@ def run_split(args, mnv, torch, dist, tree, cams, opt_kw, config, W, H, rank, wo
                 "gpu_launches": args.steps * 3,
                 "exchange": {"bytes_per_gpu_per_step": (P // sp.groups if hybrid else P) * 16, "transport": "NVLink peer stores from the march kernel "
                              "(CUDA IPC mappings), no collective"},
+                "parity": dict(parity, against="the unsharded frame rendered by rank 0 alone from the whole tree, poses 0 and 7; "
+                                               "tolerance parity by construction (early termination acts per segment)"),
                 "clocks": clocks}
         print(json.dumps(line), flush=True)
     sp.close()
@@ -981,6 +1026,20 @@ def run_guided(args, mnv, torch, dist, tree, rank, world, local_rank):
     t_end = time.time()
     clocks = sampler.stop(t_start, t_end) if sampler else None
     ms_rp, rows_rp, rows_rp_max = timed(rp.guided_block, cap)
+    # parity in the run that is timed: the sharded frame against the row-block frame of the replicated pipeline (which the
+    # tests hold bit-identical to one GPU)
+    pars = []
+    for pose in (0, 7):
+        blk, _ = sh.guided_block(cams[pose], gopt, capacity_rows=cap)
+        torch.cuda.synchronize()
+        f_sh, n_sh = mnv.multigpu.owner_range(P, world, rank)
+        got = gather_frame(torch, dist, dev, blk[:n_sh], f_sh, P, world)
+        rows_img, _ = rp.guided_block(cams[pose], gopt, capacity_rows=cap)
+        torch.cuda.synchronize()
+        r0, _nr = mnv.multigpu.row_block(H, world, rank)
+        want = gather_frame(torch, dist, dev, rows_img, r0 * W, P, world)
+        pars.append(frame_parity(got, want))
+    parity = worst_parity(pars)
     nodes = torch.tensor([sh.local_nodes], device=dev)
     dist.all_reduce(nodes, op=dist.ReduceOp.MAX)
     if rank == 0:
@@ -999,6 +1058,8 @@ def run_guided(args, mnv, torch, dist, tree, rank, world, local_rank):
                 "rows_replicated": {"ms_per_step": float(np.median(ms_rp)), "fps": 1e3 / float(np.median(ms_rp)),
                                     "mlp_rows_per_frame": rows_rp, "mlp_rows_busiest_gpu": rows_rp_max,
                                     "parallelism": "row blocks, tree + all sub-MLPs replicated, no exchange"},
+                "parity": dict(parity, against="the same frame from the replicated row-block pipeline (bit-identical to one GPU), "
+                                               "poses 0 and 7; tolerance parity by construction (transmittance carried per segment)"),
                 "gpu_launches": steps * 7, "clocks": clocks}
         print(json.dumps(line), flush=True)
     sh.close()
