@@ -70,3 +70,49 @@ def test_band_partition_two_ranks_gloo(tmp_path):
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "OK" in r.stdout
+
+
+def test_frame_parity_and_worst_of():
+    sys.path.insert(0, ROOT)
+    import bench
+
+    a = np.zeros((4, 4), np.uint8)
+    b = a.copy()
+    p0 = bench.frame_parity(a, b)
+    assert p0 == {"bit_exact": True, "max_abs": 0, "frac_within_1": 1.0, "psnr": 99.0}
+    b[0, 0] = 3
+    b[1, 1] = 1
+    p1 = bench.frame_parity(a, b)
+    assert p1["max_abs"] == 3 and not p1["bit_exact"] and p1["frac_within_1"] == 15 / 16
+    assert abs(p1["psnr"] - 10 * np.log10(255.0 ** 2 / (10 / 16))) < 1e-9
+    w = bench.worst_parity([p0, p1, p0])
+    assert w["max_abs"] == 3 and not w["bit_exact"] and w["frac_within_1"] == 15 / 16 and w["psnr"] == p1["psnr"]
+
+
+_GATHER_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import bench
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+P = 37  # ragged: the ranks own 19 and 18 pixels
+first = 0 if rank == 0 else 19
+n = 19 if rank == 0 else 18
+blk = (torch.arange(first, first + n, dtype=torch.int64)[:, None] * 4 + torch.arange(4)[None]).to(torch.uint8)
+frame = bench.gather_frame(torch, dist, torch.device("cpu"), blk, first, P, world)
+want = (np.arange(P)[:, None] * 4 + np.arange(4)[None]).astype(np.uint8)
+assert np.array_equal(frame, want), (rank, frame[:3], want[:3])
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_gather_frame_two_ranks_gloo(tmp_path):
+    """bench.gather_frame (the in-run parity of --mode split / guided): ragged owner blocks from 2 ranks -> one frame."""
+    script = tmp_path / "gather_worker.py"
+    script.write_text(_GATHER_WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29571", str(script), ROOT], capture_output=True, text=True, timeout=300,
+                       cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    assert r.stdout.count("OK") == 2

@@ -82,3 +82,44 @@ def test_mlp_config4_shape_and_determinism(mnv):
         want32 = ref(x[:4096], emulate_bf16=False).cpu().numpy()
     _check_close(a[:4096].cpu().numpy(), want, want32)
     model.close()
+
+
+_MODE_SCRIPT = r"""
+import sys, zlib, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import mega_nerf_viewer_b200 as mnv
+from mlp_reference import MegaNerfMLP
+torch.manual_seed(3)
+crc = 0
+for need_viewdir, rows in ((False, 128 * 5 + 77), (True, 1000), (False, 40000)):
+    ref = MegaNerfMLP(need_viewdir=need_viewdir).cuda().eval()
+    model = mnv.MlpModel([ref.export()])
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((rows, model.in_dim), device="cuda", generator=g) * 2 - 1
+    x[:, -1] = torch.randint(0, 4, (rows,), device="cuda", generator=g).float()
+    out = model.forward(x)
+    torch.cuda.synchronize()
+    crc = zlib.crc32(out.cpu().numpy().tobytes(), crc)
+    model.close()
+print("CRC", crc)
+"""
+
+
+def test_mlp_launch_shapes_bit_identical(tmp_path):
+    """The MLP's launch shapes — CTA pairs with cta_group::2 MMAs (M = 256 over two SMs) or one CTA (M = 128), 1 / 2 / 4 MMAs
+    per weight-ring stage — reorder nothing inside a row's dot products: outputs are equal bit for bit (odd group counts and
+    a partial last group included, so the pair's second CTA also runs a group without rows)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "mlp_mode.py"
+    script.write_text(_MODE_SCRIPT)
+    crcs = {}
+    for pair, per in ((1, 0), (1, 1), (0, 1), (0, 2)):
+        env = dict(os.environ, MNV_MLP_PAIR=str(pair), MNV_MLP_PER=str(per))
+        r = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        crcs[(pair, per)] = [l for l in r.stdout.splitlines() if l.startswith("CRC")][-1]
+    assert len(set(crcs.values())) == 1, crcs
