@@ -11,6 +11,8 @@ and no host synchronisation between ranks (csrc/mnv_multigpu.cu).
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 
 import numpy as np
 
@@ -247,11 +249,25 @@ class ReplicatedPipeline:
 
         wc = window_camera(cam, first, n)
         cap = capacity_rows or max(1 << 16, n * cam["width"] * 24)
+        timing = os.environ.get("MNV_STAGE_TIMING") == "1"  # dev: CUDA events around the three stages (adds synchronisations)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timing else None
+        if timing:
+            ev[0].record()
         g = self.dt.guided_samples(wc, opt, self.grid_dim, self.min_position, self.range, capacity_rows=cap)
         vals = torch.empty((max(g["total"], 1), self.data_dim + 1), device=f"cuda:{self.device}")
+        if timing:
+            ev[1].record()
         if g["total"]:
             self.model.query_submodules(g["cluster"], g["rows"], vals)
-        return self.dt.render_nerf_results(wc, opt, vals, g["z_vals"], g["offsets"], sigma_col=self.data_dim - 1), g["total"]
+        if timing:
+            ev[2].record()
+        img = self.dt.render_nerf_results(wc, opt, vals, g["z_vals"], g["offsets"], sigma_col=self.data_dim - 1)
+        if timing:
+            ev[3].record()
+            torch.cuda.synchronize()
+            print(f"[guided rows, rank {self.rank}] {g['total']} rows: emission {ev[0].elapsed_time(ev[1]):.3f} ms, "
+                  f"MLP {ev[1].elapsed_time(ev[2]):.3f} ms, compositing {ev[2].elapsed_time(ev[3]):.3f} ms", file=sys.stderr, flush=True)
+        return img, g["total"]
 
     def guided_blocks(self, cam: dict, opt, capacity_rows=None, parts: int = 4):
         """This rank's share of the guided-sampling frame: list of (first_row, RGBA8 [rows, W, 4]) sub-blocks and the
