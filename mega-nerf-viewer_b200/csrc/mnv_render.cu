@@ -64,14 +64,6 @@ namespace {
 // the re-sample priority (the leaf's sample count) is re-read from the cell word once per ray
 #define MNV_PACK_PRIO 1
 #endif
-#ifndef MNV_PAYLOAD_HINT
-// L1 policy of the 64-byte payload loads of shaded leaves: 0 = default (__ldg), 1 = L1::no_allocate, 2 = L1::evict_first —
-// whether keeping the payload out of L1 leaves more of it to the anchor grid and the cell words
-#define MNV_PAYLOAD_HINT 0
-#endif
-#ifndef MNV_ANCHOR_HINT
-#define MNV_ANCHOR_HINT 0  // 1 = anchor-grid loads with L1::evict_last
-#endif
 #ifndef MNV_DDA_SIGN
 #define MNV_DDA_SIGN 1  // exit distance of the unit cube by per-ray sign selection instead of three max()
 #endif
@@ -330,13 +322,7 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                 const uint32_t ax = __float_as_uint(__fmaf_rd(px, p.anchor_scale, 8388608.f));
                 const uint32_t ay = __float_as_uint(__fmaf_rd(py, p.anchor_scale, 8388608.f));
                 const uint32_t az = __float_as_uint(__fmaf_rd(pz, p.anchor_scale, 8388608.f));
-#if MNV_ANCHOR_HINT == 1
-                uint2 e;
-                asm volatile("ld.global.nc.L1::evict_last.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y)
-                             : "l"(p.anchor + ((ax * p.anchor_dim + ay) * p.anchor_dim + az - p.anchor_bias)));
-#else
                 const uint2 e = __ldg(p.anchor + ((ax * p.anchor_dim + ay) * p.anchor_dim + az - p.anchor_bias));
-#endif
                 lvl = (int) (e.y >> 28);
                 cw = e.x;
                 slot = e.y & 0x0fffffffu;
@@ -473,15 +459,9 @@ __device__ __forceinline__ void render_pixel(const RenderParams &p, const int x,
                     uint32_t w[REC_W];
 #pragma unroll
                     for (int j = 0; j < REC_W / 4; ++j) {
-#if MNV_PAYLOAD_HINT == 1
-                        uint4 v;
-                        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rec + j));
-#elif MNV_PAYLOAD_HINT == 2
-                        uint4 v;
-                        asm volatile("ld.global.nc.L1::evict_first.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(rec + j));
-#else
+                        // plain __ldg: neighbouring warps re-use payload lines through L1 (L1::no_allocate / evict_first
+                        // measured 5 % / 3 % slower, profiles/r2_variants.jsonl tags pl1 / pl2)
                         const uint4 v = __ldg(rec + j);
-#endif
                         w[4 * j] = v.x;
                         w[4 * j + 1] = v.y;
                         w[4 * j + 2] = v.z;
