@@ -16,19 +16,23 @@
 // A (activations, bf16) lives in shared memory in the UMMA K-major no-swizzle core-matrix
 // layout and is rewritten in place by the epilogue; B (weights, bf16, pre-packed on the
 // host into the same layout, 16 K-columns = 8 KiB per chunk) is streamed from L2 by 1-D
-// bulk TMA copies (cp.async.bulk -> UBLKCP) through a 5-stage mbarrier ring; D accumulates
-// in TMEM (2 x 256 fp32 columns = all 512) via tcgen05.mma issued by one thread (M=128,
-// N<=256, K=16: 128 clk each, measured); the epilogue reads D back with tcgen05.ld, applies
-// ReLU while packing to bf16 (cvt.rn.relu.bf16x2.f32) and writes the next layer's A operand.
+// bulk TMA copies (cp.async.bulk -> UBLKCP) through an mbarrier ring whose stages hold PER
+// chunks; D accumulates in TMEM (2 x 256 fp32 columns = all 512) via tcgen05.mma issued by
+// one thread (N <= 256, K = 16: 128 clk each, measured); the epilogue reads D back with
+// tcgen05.ld, applies ReLU while packing to bf16 (cvt.rn.relu.bf16x2.f32) and writes the
+// next layer's A operand.  By default two CTAs of a cluster (one TPC) form a PAIR: the MMAs
+// are cta_group::2 (M = 256 over both SMs, issued by the leader CTA), each CTA holds its own
+// rows and HALF of every weight chunk (template parameters of mlp_forward_kernel).
 //   warps 0-7 : epilogue of whichever tile completed — warp w owns TMEM lanes
 //               32(w%4)..+31 (the hardware's lane-quarter rule) and column half w/4;
 //               also the positional encodings of the next 256 rows
 //   warp  8   : TMA producer (one elected lane)
-//   warp  9   : TMEM allocation + MMA issue (one elected lane)
-// Biases ride in the GEMM: the PE operand carries two columns of ones, the weights there
-// hold bf16 hi + lo parts of the fp32 bias (error <= 2^-17 |b|), so the epilogue is
-// load -> convert -> store.  The appearance embedding enters head 1 as a per-index fp32
-// bias row (W_app . emb[i] + b, tabulated at model load with bf16-rounded operands)
+//   warp  9   : TMEM allocation; MMA issue (one elected lane) in the leader CTA, "my half
+//               has landed" relay in the peer CTA of a pair
+// Biases are added by the epilogue from an fp32 row staged in shared memory (dev switch
+// MNV_MLP_BIAS_EPILOGUE: let them ride in the GEMM as bf16 hi + lo against two columns of
+// ones of the PE operand instead).  The appearance embedding enters head 1 as a per-index
+// fp32 bias row (W_app . emb[i] + b, tabulated at model load with bf16-rounded operands)
 // instead of 48 more K columns.
 #include <cuda_bf16.h>
 
