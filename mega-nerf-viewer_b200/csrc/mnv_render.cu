@@ -9,11 +9,14 @@
 //   * query: the reference restarts at the root for every step of every ray
 //     (depth dependent loads).  The descent x*=2; f=floor(x); x-=f is exact in
 //     fp32, so the leaf containing pos is exactly the integer cell
-//     floor(pos*2^d).  Each ray keeps q = floor(pos*2^23) per axis (one
-//     FFMA.RM against the magic constant 2^23, no F2I) and the node path of its
-//     previous leaf in shared memory; a step re-descends only below the deepest
-//     common ancestor of the old and new cell (clz of the XOR), ~2 dependent
-//     loads instead of ~10, usually L1 hits.
+//     floor(pos*2^d).  One 8-byte load of the ANCHOR GRID — a dense 2^A-cube
+//     (A = 8) over the unit box, index from three FFMA.RM against the magic
+//     constant 2^23 — resolves the top A levels: it is the leaf itself when
+//     the tree ends at depth <= A there, else the level-A node, from which at
+//     most depth - A cell words remain (three funnel shifts per level build
+//     node * 8 + child).  Trees without an anchor grid (MNV_ANCHOR_LEVEL=0)
+//     take the round-1 path: each ray keeps the node path of its previous
+//     leaf in shared memory and re-descends below the deepest common ancestor.
 //   * one 4-byte "cell" word per slot holds child link OR (leaf, sigma, sample
 //     count): an empty leaf visit costs exactly one load.
 //   * shaded leaves fetch one aligned 64-byte record with 4 x LDG.128.
