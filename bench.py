@@ -20,7 +20,17 @@ over all rays of the frame.  Metric: Mrays/s (rays of the frame / device time).
             host cores, same frame
 
 N > 1: the frame is split into interleaved 8-row bands, one process per GPU,
-tree replicated, no data-path collective (strong scaling of one frame).
+tree replicated, no data-path collective (strong scaling of one frame); `parity`
+compares the union of the ranks' bands with the frame rank 0 renders alone.
+
+Sections of the default line: `mlp` (the fused tcgen05 MLP on the 262 144-row
+refinement batch, tensor roofline), `point_query`, `refinement` / `guided_sampling`
+(configs 4 / 5 through the C++ driver), `target_4k` (the north-star case: 3840x2160
+on the Mill-19-scale octree — tiles, refinement ON, guided sampling — with their own
+parity and clock records), `cpu_baseline`.
+--mode split | hybrid | guided | refine (N > 1; refine also N = 1) print their own
+lines; split / guided carry an in-run `parity` (PSNR, max-abs) against the unsharded
+/ replicated frame and the exchange bytes per GPU per frame.
 
 --impl reference: the reference's own CUDA kernel rebuilt for sm_100
 (oracle/_ref/libref_render.so, unmodified sources) on the same workload; falls
